@@ -1,0 +1,188 @@
+"""CPU oracle for the GLA hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+(``lina_speech_b200``) never does: it fails loudly when its CUDA library is
+missing instead of falling back to anything in here.
+
+Every function restates, in plain CPU torch, the arithmetic of one reference
+function (paths relative to ``/root/reference``; ``FLA/`` =
+``3rdparty/flash-linear-attention/``).  Parity of this restatement against the
+reference itself is pinned by ``tests/golden/make_golden.py`` (run in the build
+container where the reference is importable) and re-checked against the
+committed fixtures by ``tests/test_oracle.py``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# a0 / a1: the recurrence  (FLA/fla/ops/gla/naive.py:13-44)
+# ----------------------------------------------------------------------------
+def recurrent_gla(q, k, v, gk, scale: Optional[float] = None, initial_state=None,
+                  output_final_state: bool = True, acc_dtype=torch.float32
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """S_t = exp(gk_t)[:, None] * S_{t-1} + k_t^T v_t ;  o_t = (scale * q_t) S_t.
+
+    Shapes: q, k, gk [B,H,T,K]; v [B,H,T,V]; initial_state [B,H,K,V].
+    Follows FLA/fla/ops/gla/naive.py:22-44 (upcast, per-step update, output in
+    the input dtype, final state in fp32); ``scale`` defaults to K**-0.5
+    (naive.py:28, FLA/fla/ops/gla/recurrent_fuse.py:24-25).
+    """
+    odt = v.dtype
+    q, k, v, gk = (x.to(acc_dtype) for x in (q, k, v, gk))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    if scale is None or scale == -1:
+        scale = K ** -0.5
+    S = torch.zeros(B, H, K, V, dtype=acc_dtype)
+    if initial_state is not None:
+        S = S + initial_state.to(acc_dtype)
+    o = torch.empty(B, H, T, V, dtype=acc_dtype)
+    for t in range(T):
+        S = S * gk[:, :, t].exp().unsqueeze(-1) + k[:, :, t].unsqueeze(-1) * v[:, :, t].unsqueeze(-2)
+        o[:, :, t] = torch.einsum("bhk,bhkv->bhv", q[:, :, t] * scale, S)
+    return o.to(odt), (S.to(torch.float32) if output_final_state else None)
+
+
+def recurrent_gla_bwd(q, k, v, gk, h0, do, dht=None, scale: Optional[float] = None,
+                      acc_dtype=torch.float64):
+    """Explicit backward of :func:`recurrent_gla`.
+
+    Restates the identities of FLA/fla/ops/common/fused_recurrent.py:172-257
+    (forward sweep for dq, reverse sweep for dk/dv with dS carried, dh0 = dS
+    after t = 0) and :335-342 (dgk = reversed cumsum of dq*q - dk*k).
+    Returns (dq, dk, dv, dgk, dh0) in ``acc_dtype``.
+    """
+    q, k, v, gk, do = (x.to(acc_dtype) for x in (q, k, v, gk, do))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    if scale is None or scale == -1:
+        scale = K ** -0.5
+    S = torch.zeros(B, H, K, V, dtype=acc_dtype)
+    if h0 is not None:
+        S = S + h0.to(acc_dtype)
+    dq = torch.empty_like(q)
+    for t in range(T):
+        S = S * gk[:, :, t].exp().unsqueeze(-1) + k[:, :, t].unsqueeze(-1) * v[:, :, t].unsqueeze(-2)
+        dq[:, :, t] = scale * torch.einsum("bhkv,bhv->bhk", S, do[:, :, t])
+    dS = torch.zeros(B, H, K, V, dtype=acc_dtype)
+    if dht is not None:
+        dS = dS + dht.to(acc_dtype)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
+    for t in range(T - 1, -1, -1):
+        dS = dS + scale * q[:, :, t].unsqueeze(-1) * do[:, :, t].unsqueeze(-2)
+        dk[:, :, t] = torch.einsum("bhkv,bhv->bhk", dS, v[:, :, t])
+        dv[:, :, t] = torch.einsum("bhkv,bhk->bhv", dS, k[:, :, t])
+        dS = dS * gk[:, :, t].exp().unsqueeze(-1)
+    dgk = (dq * q - dk * k).flip(2).cumsum(2).flip(2)
+    if dht is not None:
+        # the reference formula (:335-342) drops this term; autograd through the
+        # naive recurrence has it: d<dht, S_T>/dgk_t = sum_v dht * S_T for every t.
+        dgk = dgk + (dht.to(acc_dtype) * S).sum(-1).unsqueeze(2)
+    return dq, dk, dv, dgk, dS
+
+
+def chunk_gla(q, k, v, gk, scale: Optional[float] = None, initial_state=None, chunk: int = 64,
+              operand_dtype: Optional[torch.dtype] = None, acc_dtype=torch.float32):
+    """Chunkwise-parallel form of the same function.
+
+    Restates FLA/fla/ops/gla/chunk.py:110-136 (inter: (q*scale*e^G) @ S),
+    :37-79 (intra scores A[t,s] = sum_k q_t k_s e^{G_t-G_s}, s <= t) and
+    FLA/fla/ops/common/chunk_h.py:74-94 (S' = e^{G_C} S + (k e^{G_C-G})^T v),
+    with a single pivot per chunk (chunk start).  ``operand_dtype`` rounds the
+    gate-rescaled MMA operands the way a bf16 tensor-core kernel does
+    (FLA/fla/ops/gla/chunk_util.py:57-60), to reason about tolerances.
+    """
+    odt = v.dtype
+    q, k, v, gk = (x.to(acc_dtype) for x in (q, k, v, gk))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    if scale is None or scale == -1:
+        scale = K ** -0.5
+    rnd = (lambda x: x.to(operand_dtype).to(acc_dtype)) if operand_dtype is not None else (lambda x: x)
+    S = torch.zeros(B, H, K, V, dtype=acc_dtype)
+    if initial_state is not None:
+        S = S + initial_state.to(acc_dtype)
+    o = torch.empty(B, H, T, V, dtype=acc_dtype)
+    for c0 in range(0, T, chunk):
+        c1 = min(T, c0 + chunk)
+        G = gk[:, :, c0:c1].cumsum(2)
+        qg = rnd(q[:, :, c0:c1] * G.exp() * scale)
+        kg = rnd(k[:, :, c0:c1] * (-G).exp())
+        vv = rnd(v[:, :, c0:c1])
+        A = torch.einsum("bhtk,bhsk->bhts", qg, kg).tril()
+        o[:, :, c0:c1] = torch.einsum("bhtk,bhkv->bhtv", qg, rnd(S)) + torch.einsum("bhts,bhsv->bhtv", rnd(A), vv)
+        GC = G[:, :, -1]
+        S = (S + torch.einsum("bhsk,bhsv->bhkv", kg, vv)) * GC.exp().unsqueeze(-1)
+    return o.to(odt), S.to(torch.float32)
+
+
+# ----------------------------------------------------------------------------
+# a5: ShortConvolution  (FLA/fla/modules/convolution.py:141-205, torch branch)
+# ----------------------------------------------------------------------------
+def short_conv_prefill(x, weight, cache=None, activation: Optional[str] = "silu"):
+    """x [B,L,D], weight [D,W] (the reference stores [D,1,W]); causal depthwise
+    conv + SiLU.  ``cache`` [B,D,W] receives the last W inputs, left-padded with
+    zeros (convolution.py:164-166).  Torch branch :175-178."""
+    B, L, D = x.shape
+    W = weight.shape[-1]
+    xt = x.transpose(1, 2)
+    if cache is not None:
+        cache.copy_(F.pad(xt, (W - L, 0)) if L < W else xt[..., L - W:])
+    y = F.conv1d(F.pad(xt.float(), (W - 1, 0)), weight.float().unsqueeze(1), groups=D)
+    if activation is not None:
+        y = F.silu(y)
+    return y.transpose(1, 2).to(x.dtype)
+
+
+def short_conv_step(x, cache, weight, activation: Optional[str] = "silu"):
+    """x [B,1,D]; cache [B,D,W] rolled left by one, x inserted at the end, then
+    dotted with the taps (convolution.py:197-204)."""
+    cache.copy_(torch.roll(cache, shifts=-1, dims=-1))
+    cache[:, :, -1] = x[:, 0].to(cache.dtype)
+    y = (cache.float() * weight.float()).sum(-1)
+    if activation is not None:
+        y = F.silu(y)
+    return y.to(x.dtype).unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------
+# a6: FusedRMSNormSwishGate  (FLA/fla/modules/fused_norm_gate.py:41-55,120-139)
+# ----------------------------------------------------------------------------
+def rmsnorm_swish_gate(x, g, weight, eps: float = 1e-5):
+    """y = x * rsqrt(mean(x^2) + eps) * w * g * sigmoid(g), fp32 math, output in
+    x.dtype (kernel :120-139; reference restatement rms_norm_ref :41-55)."""
+    xf, gf = x.float(), g.float()
+    rstd = torch.rsqrt(xf.square().mean(-1, keepdim=True) + eps)
+    y = xf * rstd
+    if weight is not None:
+        y = y * weight.float()
+    return (y * gf * torch.sigmoid(gf)).to(x.dtype)
+
+
+def rmsnorm_swish_gate_bwd(x, g, weight, dy, eps: float = 1e-5):
+    """Gradients (dx, dg, dw) by autograd over the fp64 restatement."""
+    xd = x.double().requires_grad_(True)
+    gd = g.double().requires_grad_(True)
+    wd = weight.double().requires_grad_(True)
+    rstd = torch.rsqrt(xd.square().mean(-1, keepdim=True) + eps)
+    y = xd * rstd * wd * gd * torch.sigmoid(gd)
+    y.backward(dy.double())
+    return xd.grad, gd.grad, wd.grad
+
+
+# ----------------------------------------------------------------------------
+# gate preparation  (model/gla.py:174-184)
+# ----------------------------------------------------------------------------
+def gate_logsigmoid(x, normalizer: float = 16.0, clamp_min: Optional[float] = None):
+    gk = F.logsigmoid(x) / normalizer
+    if clamp_min is not None:
+        gk = torch.clamp_min(gk, clamp_min)
+    return gk
