@@ -1,0 +1,155 @@
+/*
+ * lina_b200.h -- C ABI of liblina_b200.so, the B200 (sm_100a) implementation of
+ * Lina-Speech's GLA hot path and WavTokenizer decode tail.
+ *
+ * Every entry point replaces one function of the reference's operator API
+ * (paths relative to the reference checkout; FLA/ = 3rdparty/flash-linear-attention/,
+ * DEC/ = 3rdparty/decoder/).  The reference binds these from Python; the ctypes
+ * stub a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - plain C: pointers are DEVICE pointers, row-major contiguous, sizes are ints;
+ *   - `dtype` is the element type of the activation tensors: LINA_F32 / LINA_BF16 / LINA_F16;
+ *     all arithmetic is fp32 inside the kernels, final recurrent states are always fp32;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises,
+ *     nothing allocates -- scratch memory is passed by the caller, sized by lina_*_workspace_bytes;
+ *   - return value 0 = ok, negative = error (lina_last_error_string() describes the last
+ *     error of the calling thread); no exceptions cross the boundary;
+ *   - re-entrant and thread-safe (no global mutable state besides the per-thread error string).
+ */
+#ifndef LINA_B200_H
+#define LINA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { LINA_F32 = 0, LINA_BF16 = 1, LINA_F16 = 2 };
+enum {
+    LINA_OK = 0,
+    LINA_ERR_BAD_ARG = -1,      /* null pointer / non-positive size / unknown dtype */
+    LINA_ERR_UNSUPPORTED = -2,  /* shape outside the implemented envelope (message says which) */
+    LINA_ERR_CUDA = -3          /* a CUDA runtime call failed (message carries cudaGetErrorString) */
+};
+
+int         lina_abi_version(void);
+const char *lina_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GLA recurrence.   S_t = diag(exp(gk_t)) S_{t-1} + k_t^T v_t ;   o_t = scale * q_t S_t
+ *   q, k, gk : [B,H,T,K]   v, o : [B,H,T,V]   h0, ht : [B,H,K,V]
+ * Replaces fla.ops.gla.fused_recurrent_gla  (FLA/fla/ops/gla/recurrent_fuse.py:13-27 ->
+ * FLA/fla/ops/common/fused_recurrent.py:261-303) and is the spec of
+ * fla.ops.gla.naive.naive_recurrent_gla (FLA/fla/ops/gla/naive.py:13-44).
+ *   h0 may be NULL (zeros); its element type is h0_dtype.  ht may be NULL (not wanted), else fp32.
+ * ------------------------------------------------------------------------------------------- */
+int lina_gla_recurrent_fwd(const void *q, const void *k, const void *v, const void *gk,
+                           const void *h0, int h0_dtype, void *o, float *ht,
+                           int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
+
+/* Backward of the above (FLA/fla/ops/common/fused_recurrent.py:305-343, kernel :118-257):
+ * dq, dk, dgk [B,H,T,K] and dv [B,H,T,V] in `dtype`; dh0 [B,H,K,V] fp32 (NULL = not wanted);
+ * dht [B,H,K,V] fp32 or NULL.  `ws` is scratch of lina_gla_recurrent_bwd_workspace_bytes(). */
+size_t lina_gla_recurrent_bwd_workspace_bytes(int B, int H, int T, int K, int V);
+int lina_gla_recurrent_bwd(const void *q, const void *k, const void *v, const void *gk,
+                           const void *h0, int h0_dtype, const void *d_o, const float *dht,
+                           void *dq, void *dk, void *dv, void *dgk, float *dh0, void *ws,
+                           int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
+
+/* Chunkwise-parallel forward of the same function -- the tensor-core path.
+ * Replaces fla.ops.gla.fused_chunk_gla (FLA/fla/ops/gla/chunk_fuse.py:518-536) and
+ * fla.ops.gla.chunk_gla (FLA/fla/ops/gla/chunk.py:453-491); same contract as
+ * lina_gla_recurrent_fwd, arbitrary T.  `ws` is scratch of lina_gla_chunk_fwd_workspace_bytes(). */
+size_t lina_gla_chunk_fwd_workspace_bytes(int B, int H, int T, int K, int V, int dtype);
+int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, const void *gk,
+                       const void *h0, int h0_dtype, void *o, float *ht, void *ws,
+                       int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
+/* 1 if lina_gla_chunk_fwd runs the tcgen05 (sm_100a tensor-core) kernel for this problem,
+ * 0 if it runs the CUDA-core recurrence kernel (small/odd shapes, fp32 inputs). */
+int lina_gla_chunk_fwd_uses_tensor_cores(int B, int H, int T, int K, int V, int dtype);
+
+/* ---------------------------------------------------------------------------------------------
+ * One autoregressive step (T = 1) of a whole GLA mixer between its GEMMs, state updated IN PLACE.
+ * Replaces, for GatedLinearAttention.forward with a cache and one token (model/gla.py:146-220):
+ *   3x ShortConvolution.step (FLA/fla/modules/convolution.py:180-205), logsigmoid/normaliser
+ *   (model/gla.py:174-176), the GLA op at T = 1 (model/gla.py:187-193), Cache.update's copy_
+ *   (FLA/fla/models/utils.py:61-66) and FusedRMSNormSwishGate (FLA/fla/modules/fused_norm_gate.py:72-139).
+ *   xq, xk : [B, H*K]   xv, g : [B, H*V]     projections of the token (dtype)
+ *   gk_raw : [B, H*K]   gate logits before logsigmoid (dtype)
+ *   wq, wk : [H*K, W]   wv : [H*V, W]        depthwise taps (dtype); NULL = no short conv
+ *   cq, ck : [B, H*K, W]  cv : [B, H*V, W]   conv states (state_dtype), rolled in place
+ *   S      : [B, H, K, V]                    recurrent state (state_dtype), updated in place
+ *   norm_w : [V] (dtype)                     out : [B, H*V] (dtype) = RMSNorm(o) * w * swish(g)
+ *   ws     : scratch of lina_gla_step_workspace_bytes()
+ * ------------------------------------------------------------------------------------------- */
+size_t lina_gla_step_workspace_bytes(int B, int H, int K, int V);
+int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                  const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                  void *S, const void *norm_w, void *out, void *ws,
+                  int B, int H, int K, int V, int W, int dtype, int state_dtype,
+                  float scale, float gate_normalizer, float eps, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.
+ * Replaces causal_conv1d_fn / causal_conv1d_update (causal-conv1d 1.3.0.post1, call sites
+ * FLA/fla/modules/convolution.py:168-173,189-195; semantics = the torch branch :175-178,197-204).
+ *   x, y : [B,L,D]   w : [D,W]   cache : [B,D,W] or NULL (receives the last W inputs, :164-166).
+ * ------------------------------------------------------------------------------------------- */
+int lina_short_conv_fwd(const void *x, const void *w, void *y, void *cache, int cache_dtype,
+                        int B, int L, int D, int W, int silu, int dtype, void *stream);
+int lina_short_conv_bwd(const void *x, const void *w, const void *dy, void *dx, float *dw,
+                        int B, int L, int D, int W, int silu, int dtype, void *stream);
+int lina_short_conv_update(const void *x, void *cache, int cache_dtype, const void *w, void *y,
+                           int B, int D, int W, int silu, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FusedRMSNormSwishGate: y = x * rsqrt(mean(x^2) + eps) * w * g * sigmoid(g), rows of length N.
+ * Replaces rms_norm_swish_gate_fn (FLA/fla/modules/fused_norm_gate.py:439-518; kernels :72-139, :220-335).
+ *   x, g, y : [M,N]   w : [N] or NULL   rstd : [M] fp32 (saved for backward; may be NULL in fwd).
+ *   bwd: dw is an fp32 [N] accumulator that must be zeroed by the caller.
+ * ------------------------------------------------------------------------------------------- */
+int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void *y, float *rstd,
+                               int M, int N, float eps, int dtype, void *stream);
+int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, const float *rstd,
+                               const void *dy, void *dx, void *dg, float *dw,
+                               int M, int N, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WavTokenizer decode tail (fp32).  The dense convolutions / linears of the backbone stay library
+ * GEMMs on the host side; these are the HBM-bound stages between them.
+ * ------------------------------------------------------------------------------------------- */
+/* codes_to_features (DEC/pretrained.py:209-239): codes [K,B,L] int64, codebooks [K*bins, C] ->
+ * features [B,C,L] (sum over the K codebooks, transposed). */
+int lina_codec_codes_to_features(const int64_t *codes, const float *codebooks, float *features,
+                                 int Kq, int B, int L, int bins, int C, void *stream);
+/* GroupNorm(groups, eps, affine) + optional swish on [B,C,L] (DEC/models.py:10-16,58-70,113).
+ * `ws` = 2*B*groups floats. */
+int lina_codec_groupnorm_swish(const float *x, const float *gamma, const float *beta, float *y, float *ws,
+                               int B, int C, int L, int groups, float eps, int swish, void *stream);
+/* ConvNeXt front half (DEC/modules.py:45-50): depthwise Conv1d(k=7,pad=3) on [B,C,L] + bias, transpose
+ * to [B,L,C], LayerNorm(no affine, eps) * scale[C] + shift[C] (AdaLayerNorm, DEC/modules.py:81-86).
+ * dw_w NULL = skip the conv (plain transposing AdaLN, DEC/models.py:229). */
+int lina_codec_dwconv_adaln(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                            const float *shift, float *y, int B, int C, int L, float eps, void *stream);
+/* ConvNeXt back half (DEC/modules.py:55-59): out[b,c,l] = res[b,c,l] + gamma[c] * h[b,l,c]. */
+int lina_codec_scale_residual_t(const float *h, const float *gamma, const float *res, float *out,
+                                int B, int C, int L, void *stream);
+/* LayerNorm over the channel dim of [B,C,L] written as [B,L,C] (final_layer_norm, DEC/models.py:234). */
+int lina_codec_layernorm_t(const float *x, const float *gamma, const float *beta, float *y,
+                           int B, int C, int L, float eps, void *stream);
+/* ISTFTHead tail (DEC/heads.py:53-67 + DEC/spectral_ops.py:33-75, padding="same"):
+ * h [B,L,n_fft+2] (Linear output: log-magnitudes then phases) -> wav [B, L*hop].
+ * mag = min(exp(.),100); S = mag*(cos p + i sin p); irfft(n_fft) * window; overlap-add with hop;
+ * trim (n_fft-hop)/2 per side; divide by the overlap-added window^2 envelope.
+ * `ws` = lina_codec_istft_workspace_bytes(). */
+size_t lina_codec_istft_workspace_bytes(int B, int L, int n_fft);
+int lina_codec_istft_head(const float *h, const float *window, float *wav, void *ws,
+                          int B, int L, int n_fft, int hop, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINA_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of liblina_b200.so (the C ABI declared in include/lina_b200.h).
+
+There is no fallback: if the library is missing, ``lib()`` raises; every op
+requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblina_b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+_p, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes).  Kept in lock-step with include/lina_b200.h (tests/test_abi.py checks it).
+PROTOTYPES = {
+    "lina_abi_version": (_i, []),
+    "lina_last_error_string": (C.c_char_p, []),
+    "lina_gla_recurrent_fwd": (_i, [_p] * 5 + [_i, _p, _p] + [_i] * 6 + [_f, _p]),
+    "lina_gla_recurrent_bwd_workspace_bytes": (_sz, [_i] * 5),
+    "lina_gla_recurrent_bwd": (_i, [_p] * 5 + [_i] + [_p] * 8 + [_i] * 6 + [_f, _p]),
+    "lina_gla_chunk_fwd_workspace_bytes": (_sz, [_i] * 6),
+    "lina_gla_chunk_fwd": (_i, [_p] * 5 + [_i, _p, _p, _p] + [_i] * 6 + [_f, _p]),
+    "lina_gla_chunk_fwd_uses_tensor_cores": (_i, [_i] * 6),
+    "lina_gla_step_workspace_bytes": (_sz, [_i] * 4),
+    "lina_gla_step": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_p]),
+    "lina_short_conv_fwd": (_i, [_p] * 4 + [_i] * 7 + [_p]),
+    "lina_short_conv_bwd": (_i, [_p] * 5 + [_i] * 6 + [_p]),
+    "lina_short_conv_update": (_i, [_p, _p, _i, _p, _p] + [_i] * 5 + [_p]),
+    "lina_rmsnorm_swishgate_fwd": (_i, [_p] * 5 + [_i, _i, _f, _i, _p]),
+    "lina_rmsnorm_swishgate_bwd": (_i, [_p] * 8 + [_i, _i, _i, _p]),
+    "lina_codec_codes_to_features": (_i, [_p] * 3 + [_i] * 5 + [_p]),
+    "lina_codec_groupnorm_swish": (_i, [_p] * 5 + [_i] * 4 + [_f, _i, _p]),
+    "lina_codec_dwconv_adaln": (_i, [_p] * 6 + [_i] * 3 + [_f, _p]),
+    "lina_codec_scale_residual_t": (_i, [_p] * 4 + [_i] * 3 + [_p]),
+    "lina_codec_layernorm_t": (_i, [_p] * 4 + [_i] * 3 + [_f, _p]),
+    "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
+    "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"liblina_b200.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). There is no CPU or PyTorch fallback for these ops.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().lina_last_error_string().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 / float16 only)") from None
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("lina_speech_b200 ops run on CUDA (B200) tensors only; got a tensor on "
+                               f"{t.device}. There is no CPU fallback.")
+
+
+_launches = 0
+
+
+def count_launches(n: int) -> None:
+    """Book-keeping for bench.py's gpu_launches field: kernels of OURS enqueued so far."""
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches

@@ -1,0 +1,367 @@
+// WavTokenizer decode tail: the HBM-bound stages between the backbone's dense GEMMs / convolutions.
+//
+// Reference (DEC/ = 3rdparty/decoder/): codes_to_features DEC/pretrained.py:209-239; GroupNorm+swish
+// DEC/models.py:10-16,58-70; ConvNeXtBlock DEC/modules.py:43-60; AdaLayerNorm DEC/modules.py:81-86;
+// final LayerNorm DEC/models.py:234; ISTFTHead DEC/heads.py:53-67; ISTFT("same") DEC/spectral_ops.py:33-75.
+// Everything is fp32 like the reference.  Layout notes:
+//   backbone activations are [B,C,L] (channel-major) in the reference; the ConvNeXt MLP wants [B,L,C].
+//   dwconv_adaln fuses the depthwise conv, the transpose and the (Ada)LayerNorm in one pass over x;
+//   scale_residual_t fuses gamma*h, the transpose back and the residual add.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// codes -> features: out[b,c,l] = sum_k codebooks[k*bins + codes[k,b,l], c]   (32x32 smem transpose)
+__global__ void __launch_bounds__(256)
+codes_to_features_kernel(const int64_t *__restrict__ codes, const float *__restrict__ books,
+                         float *__restrict__ out, int Kq, int B, int L, int bins, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    for (int i = ty; i < 32; i += 8) {                               // i = l within tile, tx = c
+        const int l = l0 + i, c = c0 + tx;
+        float acc = 0.f;
+        if (l < L && c < C) {
+            for (int k = 0; k < Kq; ++k) {
+                long long id = codes[((size_t)k * B + b) * L + l];
+                id = id < 0 ? 0 : (id >= bins ? bins - 1 : id);
+                acc += books[((size_t)k * bins + id) * C + c];
+            }
+        }
+        tile[i][tx] = acc;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {                               // i = c within tile, tx = l
+        const int c = c0 + i, l = l0 + tx;
+        if (c < C && l < L) out[((size_t)b * C + c) * L + l] = tile[tx][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (+swish): one CTA per (b, group); the group's channels are one contiguous run of cpg*L floats.
+__global__ void __launch_bounds__(256)
+groupnorm_swish_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                       float *__restrict__ y, int C, int L, int groups, float eps, int swish) {
+    __shared__ double red[2][8];
+    __shared__ float stat[2];
+    const int bg = blockIdx.x, g = bg % groups;
+    const int cpg = C / groups;
+    const size_t n = (size_t)cpg * L;
+    const float *xp = x + (size_t)bg * n;
+    float *yp = y + (size_t)bg * n;
+    float s = 0.f, ss = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += 256) { const float v = xp[i]; s += v; ss = fmaf(v, v, ss); }
+    double ds = warp_sum(s), dss = warp_sum(ss);
+    // (warp_sum is float; widen across warps)
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ds; red[1][threadIdx.x >> 5] = dss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b2 = 0;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; b2 += red[1][w]; }
+        const double mean = a / (double)n;
+        double var = b2 / (double)n - mean * mean;
+        if (var < 0) var = 0;
+        stat[0] = (float)mean;
+        stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = stat[0], rstd = stat[1];
+    for (size_t i = threadIdx.x; i < n; i += 256) {
+        const int c = g * cpg + (int)(i / L);
+        float v = (xp[i] - mean) * rstd * gamma[c] + beta[c];
+        if (swish) v = v * sigmoidf_(v);
+        yp[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv k=7 (optional) + transpose [B,C,L]->[B,L,C] + LayerNorm(no affine)*scale+shift.
+constexpr int TL = 16;     // time steps per CTA
+constexpr int CCH = 64;    // channels staged per round
+__global__ void __launch_bounds__(256)
+dwconv_adaln_kernel(const float *__restrict__ x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
+                    const float *__restrict__ scale, const float *__restrict__ shift, float *__restrict__ y,
+                    int C, int L, float eps) {
+    extern __shared__ float smem[];
+    float *outs = smem;                         // [TL][C + 1]
+    float *ins = smem + TL * (C + 1);           // [CCH][TL + 6]
+    const int b = blockIdx.y, l0 = blockIdx.x * TL;
+    const int tid = threadIdx.x;
+    const int CP = C + 1;
+    for (int c0 = 0; c0 < C; c0 += CCH) {
+        const int nc = min(CCH, C - c0);
+        if (dw_w != nullptr) {
+            for (int i = tid; i < nc * (TL + 6); i += 256) {
+                const int ci = i / (TL + 6), j = i - ci * (TL + 6);
+                const int l = l0 - 3 + j;
+                ins[ci * (TL + 6) + j] = (l >= 0 && l < L) ? x[((size_t)b * C + c0 + ci) * L + l] : 0.f;
+            }
+            __syncthreads();
+            for (int i = tid; i < nc * TL; i += 256) {
+                const int ci = i / TL, lt = i - ci * TL;
+                const float *w = dw_w + (size_t)(c0 + ci) * 7;
+                float acc = dw_b != nullptr ? dw_b[c0 + ci] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc = fmaf(w[j], ins[ci * (TL + 6) + lt + j], acc);
+                outs[lt * CP + c0 + ci] = acc;
+            }
+            __syncthreads();
+        } else {
+            for (int i = tid; i < nc * TL; i += 256) {
+                const int ci = i / TL, lt = i - ci * TL;
+                const int l = l0 + lt;
+                outs[lt * CP + c0 + ci] = l < L ? x[((size_t)b * C + c0 + ci) * L + l] : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int lt = warp; lt < TL; lt += 8) {
+        const int l = l0 + lt;
+        if (l >= L) continue;
+        const float *row = outs + lt * CP;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += row[c];
+        const float mean = warp_sum(s) / (float)C;
+        float ss = 0.f;
+        for (int c = lane; c < C; c += 32) { const float d = row[c] - mean; ss = fmaf(d, d, ss); }
+        const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+        float *yr = y + ((size_t)b * L + l) * C;
+        for (int c = lane; c < C; c += 32) yr[c] = (row[c] - mean) * rstd * scale[c] + shift[c];
+    }
+}
+
+// out[b,c,l] = res[b,c,l] + gamma[c] * h[b,l,c]
+__global__ void __launch_bounds__(256)
+scale_residual_t_kernel(const float *__restrict__ h, const float *__restrict__ gamma, const float *__restrict__ res,
+                        float *__restrict__ out, int C, int L) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int l = l0 + i, c = c0 + tx;
+        tile[i][tx] = (l < L && c < C) ? h[((size_t)b * L + l) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, l = l0 + tx;
+        if (c < C && l < L) {
+            const size_t idx = ((size_t)b * C + c) * L + l;
+            out[idx] = res[idx] + (gamma != nullptr ? gamma[c] : 1.f) * tile[tx][i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ISTFT head: polar -> 1280-point inverse real FFT (as a 640-point complex Stockham FFT) -> window.
+struct FftPlan { int M; int nstage; int radix[16]; };
+
+struct cplx { float x, y; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+
+__global__ void __launch_bounds__(128)
+istft_frames_kernel(const float *__restrict__ h, const float *__restrict__ window, float *__restrict__ frames,
+                    int nframes, FftPlan plan) {
+    extern __shared__ float smem[];
+    const int M = plan.M, N = 2 * M;
+    cplx *tw = reinterpret_cast<cplx *>(smem);       // [M]   e^{+2 pi i m / M}
+    cplx *pre = tw + M;                              // [M]   e^{+2 pi i k / N}
+    cplx *bufa = pre + M;                            // [M+1] spectrum, then ping
+    cplx *bufb = bufa + (M + 1);                     // [M]   pong
+    const int tid = threadIdx.x;
+    for (int m = tid; m < M; m += 128) {
+        float s, c;
+        sincospif(2.f * (float)m / (float)M, &s, &c);
+        tw[m] = {c, s};
+        sincospif((float)m / (float)M, &s, &c);      // 2 pi m / N = pi m / M
+        pre[m] = {c, s};
+    }
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        __syncthreads();
+        const float *hf = h + (size_t)f * (N + 2);
+        // X[k] = min(exp(m_k), 100) * (cos p_k + i sin p_k)        (DEC/heads.py:54-66)
+        for (int k = tid; k <= M; k += 128) {
+            const float mag = fminf(expf(hf[k]), 100.f);
+            float s, c;
+            sincosf(hf[M + 1 + k], &s, &c);
+            cplx X = {mag * c, mag * s};
+            if (k == 0 || k == M) X.y = 0.f;         // C2R ignores the imaginary part of DC / Nyquist
+            bufa[k] = X;
+        }
+        __syncthreads();
+        // Z[k] = (X[k] + conj X[M-k]) + i w^k (X[k] - conj X[M-k]),  w = e^{2 pi i / N}
+        for (int k = tid; k < M; k += 128) {
+            const cplx A = bufa[k], Bc = {bufa[M - k].x, -bufa[M - k].y};
+            const cplx sum = cadd(A, Bc), dif = {A.x - Bc.x, A.y - Bc.y};
+            const cplx t = cmul(pre[k], dif);        // w^k * dif ; times i -> (-t.y, t.x)
+            bufb[k] = {sum.x - t.y, sum.y + t.x};
+        }
+        __syncthreads();
+        cplx *a = bufb, *b = bufa;
+        int Ns = 1;
+        for (int st = 0; st < plan.nstage; ++st) {
+            const int r = plan.radix[st], nb = M / r;
+            for (int j = tid; j < nb; j += 128) {
+                const int kk = j % Ns;
+                cplx v[5];
+                const int tstep = M / (Ns * r);
+                for (int t = 0; t < r; ++t) {
+                    cplx xin = a[j + t * nb];
+                    v[t] = t == 0 ? xin : cmul(xin, tw[(t * kk * tstep) % M]);
+                }
+                const int j0 = (j / Ns) * Ns * r + kk;
+                const int ustep = M / r;
+                for (int u = 0; u < r; ++u) {
+                    cplx acc = v[0];
+                    for (int t = 1; t < r; ++t) acc = cadd(acc, cmul(v[t], tw[(t * u * ustep) % M]));
+                    b[j0 + u * Ns] = acc;
+                }
+            }
+            __syncthreads();
+            cplx *tmp = a; a = b; b = tmp;
+            Ns *= r;
+        }
+        // x[2n] = Re z[n], x[2n+1] = Im z[n], scaled 1/N, times the window  (spectral_ops.py:57-58)
+        float *fr = frames + (size_t)f * N;
+        const float inv = 1.f / (float)N;
+        for (int n = tid; n < M; n += 128) {
+            const cplx z = a[n];
+            float2 o2 = make_float2(z.x * inv * window[2 * n], z.y * inv * window[2 * n + 1]);
+            *reinterpret_cast<float2 *>(fr + 2 * n) = o2;
+        }
+    }
+}
+
+// overlap-add + trim + envelope normalisation (spectral_ops.py:60-73)
+__global__ void __launch_bounds__(256)
+istft_ola_kernel(const float *__restrict__ frames, const float *__restrict__ window, float *__restrict__ wav,
+                 int L, int N, int hop) {
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    const int out_len = L * hop;
+    if (s >= out_len) return;
+    const int pad = (N - hop) / 2;
+    const int p = s + pad;
+    int f_hi = p / hop;
+    if (f_hi > L - 1) f_hi = L - 1;
+    int f_lo = (p - N + hop) / hop;            // ceil((p - N + 1) / hop)
+    if (p - N + 1 <= 0) f_lo = 0;
+    float acc = 0.f, env = 0.f;
+    for (int f = f_lo; f <= f_hi; ++f) {
+        const int n = p - f * hop;
+        if (n < 0 || n >= N) continue;
+        acc += frames[((size_t)b * L + f) * N + n];
+        const float w = window[n];
+        env = fmaf(w, w, env);
+    }
+    wav[(size_t)b * out_len + s] = acc / env;
+}
+
+bool make_plan(int M, FftPlan &p) {
+    p.M = M; p.nstage = 0;
+    int m = M;
+    const int cand[4] = {5, 4, 2, 3};
+    for (int ci = 0; ci < 4; ++ci) {
+        const int r = cand[ci];
+        while (m % r == 0 && m > 1) {
+            if (r == 2 && m % 4 == 0) break;     // (unreachable: 4s are removed first)
+            if (p.nstage >= 16) return false;
+            p.radix[p.nstage++] = r;
+            m /= r;
+        }
+    }
+    return m == 1;
+}
+
+}  // namespace
+
+extern "C" int lina_codec_codes_to_features(const int64_t *codes, const float *codebooks, float *features, int Kq,
+                                            int B, int L, int bins, int C, void *stream) {
+    LINA_REQUIRE(codes && codebooks && features, LINA_ERR_BAD_ARG, "codes_to_features: null pointer");
+    LINA_REQUIRE(Kq > 0 && B > 0 && L > 0 && bins > 0 && C > 0, LINA_ERR_BAD_ARG, "codes_to_features: bad size");
+    LINA_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, LINA_ERR_UNSUPPORTED, "codes_to_features: grid too large");
+    dim3 grid((L + 31) / 32, (C + 31) / 32, B);
+    codes_to_features_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, codebooks, features, Kq, B, L, bins, C);
+    LINA_LAUNCH_OK("codes_to_features_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_codec_groupnorm_swish(const float *x, const float *gamma, const float *beta, float *y, float *ws,
+                                          int B, int C, int L, int groups, float eps, int swish, void *stream) {
+    (void)ws;
+    LINA_REQUIRE(x && gamma && beta && y, LINA_ERR_BAD_ARG, "groupnorm_swish: null pointer");
+    LINA_REQUIRE(B > 0 && C > 0 && L > 0 && groups > 0 && C % groups == 0, LINA_ERR_BAD_ARG,
+                 "groupnorm_swish: bad size (C=%d groups=%d)", C, groups);
+    groupnorm_swish_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, C, L, groups, eps, swish);
+    LINA_LAUNCH_OK("groupnorm_swish_kernel");
+    return LINA_OK;
+}
+
+static int launch_dwconv_adaln(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                               const float *shift, float *y, int B, int C, int L, float eps, cudaStream_t st) {
+    LINA_REQUIRE(x && scale && shift && y, LINA_ERR_BAD_ARG, "dwconv_adaln: null pointer");
+    LINA_REQUIRE(B > 0 && C > 0 && L > 0, LINA_ERR_BAD_ARG, "dwconv_adaln: bad size");
+    LINA_REQUIRE(B <= 65535, LINA_ERR_UNSUPPORTED, "dwconv_adaln: B > 65535");
+    const size_t smem = ((size_t)TL * (C + 1) + (size_t)CCH * (TL + 6)) * sizeof(float);
+    LINA_REQUIRE(smem <= 200 * 1024, LINA_ERR_UNSUPPORTED, "dwconv_adaln: C=%d too large for shared memory", C);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((L + TL - 1) / TL, B);
+    dwconv_adaln_kernel<<<grid, 256, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
+    LINA_LAUNCH_OK("dwconv_adaln_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_codec_dwconv_adaln(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                                       const float *shift, float *y, int B, int C, int L, float eps, void *stream) {
+    return launch_dwconv_adaln(x, dw_w, dw_b, scale, shift, y, B, C, L, eps, (cudaStream_t)stream);
+}
+
+extern "C" int lina_codec_layernorm_t(const float *x, const float *gamma, const float *beta, float *y, int B, int C,
+                                      int L, float eps, void *stream) {
+    return launch_dwconv_adaln(x, nullptr, nullptr, gamma, beta, y, B, C, L, eps, (cudaStream_t)stream);
+}
+
+extern "C" int lina_codec_scale_residual_t(const float *h, const float *gamma, const float *res, float *out, int B,
+                                           int C, int L, void *stream) {
+    LINA_REQUIRE(h && res && out, LINA_ERR_BAD_ARG, "scale_residual_t: null pointer");
+    LINA_REQUIRE(B > 0 && C > 0 && L > 0, LINA_ERR_BAD_ARG, "scale_residual_t: bad size");
+    LINA_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, LINA_ERR_UNSUPPORTED, "scale_residual_t: grid too large");
+    dim3 grid((L + 31) / 32, (C + 31) / 32, B);
+    scale_residual_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, gamma, res, out, C, L);
+    LINA_LAUNCH_OK("scale_residual_t_kernel");
+    return LINA_OK;
+}
+
+extern "C" size_t lina_codec_istft_workspace_bytes(int B, int L, int n_fft) {
+    return (size_t)B * L * n_fft * sizeof(float);
+}
+
+extern "C" int lina_codec_istft_head(const float *h, const float *window, float *wav, void *ws, int B, int L,
+                                     int n_fft, int hop, void *stream) {
+    LINA_REQUIRE(h && window && wav && ws, LINA_ERR_BAD_ARG, "istft_head: null pointer");
+    LINA_REQUIRE(B > 0 && L > 0 && n_fft > 0 && hop > 0, LINA_ERR_BAD_ARG, "istft_head: bad size");
+    LINA_REQUIRE(n_fft % 4 == 0 && hop <= n_fft && (n_fft - hop) % 2 == 0, LINA_ERR_UNSUPPORTED,
+                 "istft_head: need n_fft %% 4 == 0, hop <= n_fft, (n_fft-hop) even (n_fft=%d hop=%d)", n_fft, hop);
+    FftPlan plan;
+    LINA_REQUIRE(make_plan(n_fft / 2, plan), LINA_ERR_UNSUPPORTED,
+                 "istft_head: n_fft/2=%d must factor into 2,3,4,5", n_fft / 2);
+    const int M = n_fft / 2;
+    const size_t smem = ((size_t)4 * M + 1) * 2 * sizeof(float);
+    LINA_REQUIRE(smem <= 48 * 1024, LINA_ERR_UNSUPPORTED, "istft_head: n_fft=%d too large", n_fft);
+    LINA_REQUIRE(B <= 65535, LINA_ERR_UNSUPPORTED, "istft_head: B > 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nframes = B * L;
+    const int grid = nframes < 148 * 16 ? nframes : 148 * 16;
+    istft_frames_kernel<<<grid, 128, smem, st>>>(h, window, (float *)ws, nframes, plan);
+    LINA_LAUNCH_OK("istft_frames_kernel");
+    dim3 g2((L * hop + 255) / 256, B);
+    istft_ola_kernel<<<g2, 256, 0, st>>>((const float *)ws, window, wav, L, n_fft, hop);
+    LINA_LAUNCH_OK("istft_ola_kernel");
+    return LINA_OK;
+}

@@ -1,0 +1,230 @@
+// One autoregressive step (T = 1) of a GLA mixer between its GEMMs, states updated in place.
+//
+// Replaces, per GatedLinearAttention.forward call with a cache and one token (model/gla.py:146-220):
+// 3x causal_conv1d_update (FLA/fla/modules/convolution.py:180-205), logsigmoid/normaliser
+// (model/gla.py:174-176), the T=1 GLA op (4 Triton launches + bmm + 2 sums in the default
+// fused_chunk mode, FLA/fla/ops/gla/chunk_fuse.py:307-394), Cache.update's 4 copies
+// (FLA/fla/models/utils.py:61-66) and the norm-gate kernel (FLA/fla/modules/fused_norm_gate.py:72-139).
+//
+// HBM-bound: the recurrent state S [B,H,K,V] is read once and written once (in place); the
+// algorithmic bytes are 2 * B*H*K*V * sizeof(state) per call, everything else is < 2 % of that.
+//   k1 gla_step_prep  : conv roll+dot+SiLU for q,k,v ; e = exp(logsigmoid(gk_raw)/normalizer)   (tiny)
+//   k2 gla_step_state : S <- e (.) S + k^T v ; o = scale q S     128-bit loads/stores, 8 rows in flight/thread
+//   k3 gla_step_norm  : RMSNorm(o) * w * swish(g)                                               (tiny)
+#include "common.cuh"
+
+namespace {
+
+template <typename T, typename CT>
+__global__ void gla_step_prep_kernel(const T *__restrict__ xq, const T *__restrict__ xk, const T *__restrict__ xv,
+                                     const T *__restrict__ gk_raw, const T *__restrict__ wq,
+                                     const T *__restrict__ wk, const T *__restrict__ wv, CT *__restrict__ cq,
+                                     CT *__restrict__ ck, CT *__restrict__ cv, float *__restrict__ qf,
+                                     float *__restrict__ kf, float *__restrict__ ef, float *__restrict__ vf,
+                                     int B, int HK, int HV, int W, float scale, float inv_norm) {
+    const int per_b = 3 * HK + HV;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * per_b) return;
+    const int b = (int)(i / per_b);
+    int c = (int)(i - (long long)b * per_b);
+    if (c >= 2 * HK + HV) {                         // gate channel
+        c -= 2 * HK + HV;
+        const float x = to_f(gk_raw[(size_t)b * HK + c]);
+        ef[(size_t)b * HK + c] = expf(logsigmoidf_(x) * inv_norm);
+        return;
+    }
+    const T *x; const T *w; CT *cache; float *out; int D; float mul = 1.f;
+    if (c < HK) { x = xq; w = wq; cache = cq; out = qf; D = HK; mul = scale; }
+    else if (c < 2 * HK) { c -= HK; x = xk; w = wk; cache = ck; out = kf; D = HK; }
+    else { c -= 2 * HK; x = xv; w = wv; cache = cv; out = vf; D = HV; }
+    float y = to_f(x[(size_t)b * D + c]);
+    if (w != nullptr) {
+        // cache <- roll(cache, -1); cache[-1] = x; y = silu(sum_j cache[j] * w[j])   (convolution.py:197-204)
+        CT *cp = cache + ((size_t)b * D + c) * W;
+        const T *wp = w + (size_t)c * W;
+        float acc = 0.f;
+        for (int j = 0; j < W - 1; ++j) {
+            const CT nxt = cp[j + 1];
+            cp[j] = nxt;
+            acc = fmaf(to_f(nxt), to_f(wp[j]), acc);
+        }
+        const CT last = from_f<CT>(y);
+        cp[W - 1] = last;
+        acc = fmaf(to_f(last), to_f(wp[W - 1]), acc);
+        y = siluf_(acc);
+        // the reference returns the conv output in the activation dtype before the GLA op
+        y = to_f(from_f<T>(y));
+    }
+    out[(size_t)b * D + c] = y * mul;
+}
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {  // fp32 state, 16 B
+    static __device__ __forceinline__ void load(const float *p, float *x) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float *x) {
+        *reinterpret_cast<float4 *>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+};
+template <> struct Vec<8> {  // bf16 state, 16 B
+    static __device__ __forceinline__ void load(const bf16 *p, float *x) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(p);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(bf16 *p, const float *x) {
+        uint4 t;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+
+constexpr int SW = 8;     // warps per CTA
+constexpr int SU = 4;     // state rows in flight per thread
+
+template <typename ST, int VEC>
+__global__ void __launch_bounds__(SW * 32)
+gla_step_state_kernel(ST *__restrict__ S, const float *__restrict__ qf, const float *__restrict__ kf,
+                      const float *__restrict__ ef, const float *__restrict__ vf, float *__restrict__ of,
+                      int K, int V) {
+    __shared__ float sq[256], sk[256], se[256];
+    __shared__ float red[SW][32 * VEC];
+    const int bh = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v0 = (blockIdx.x * 32 + lane) * VEC;
+    const bool vok = v0 < V;          // V % VEC == 0 is checked by the host
+    for (int i = tid; i < K; i += SW * 32) {
+        sq[i] = qf[(size_t)bh * K + i]; sk[i] = kf[(size_t)bh * K + i]; se[i] = ef[(size_t)bh * K + i];
+    }
+    float vv[VEC], acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { vv[i] = vok ? vf[(size_t)bh * V + v0 + i] : 0.f; acc[i] = 0.f; }
+    __syncthreads();
+    ST *Sb = S + (size_t)bh * K * V + v0;
+    if (vok) {
+        int r = warp;
+        for (; r + (SU - 1) * SW < K; r += SU * SW) {
+            float s[SU][VEC];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) Vec<VEC>::load(Sb + (size_t)(r + u * SW) * V, s[u]);
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int rr = r + u * SW;
+                const float e = se[rr], kk = sk[rr], qq = sq[rr];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    s[u][i] = fmaf(s[u][i], e, kk * vv[i]);
+                    acc[i] = fmaf(qq, s[u][i], acc[i]);
+                }
+                Vec<VEC>::store(Sb + (size_t)rr * V, s[u]);
+            }
+        }
+        for (; r < K; r += SW) {
+            float s[VEC];
+            Vec<VEC>::load(Sb + (size_t)r * V, s);
+            const float e = se[r], kk = sk[r], qq = sq[r];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { s[i] = fmaf(s[i], e, kk * vv[i]); acc[i] = fmaf(qq, s[i], acc[i]); }
+            Vec<VEC>::store(Sb + (size_t)r * V, s);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[warp][lane * VEC + i] = acc[i];
+    __syncthreads();
+    for (int c = tid; c < 32 * VEC; c += SW * 32) {
+        const int vc = blockIdx.x * 32 * VEC + c;
+        if (vc < V) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < SW; ++w) sum += red[w][c];
+            of[(size_t)bh * V + vc] = sum;
+        }
+    }
+}
+
+// RMSNorm over V of o (fp32 scratch) * w * swish(g); one warp per (b,h) row.
+template <typename T>
+__global__ void gla_step_norm_kernel(const float *__restrict__ of, const T *__restrict__ g,
+                                     const T *__restrict__ w, T *__restrict__ out, int rows, int V, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float *x = of + (size_t)row * V;
+    float ss = 0.f;
+    for (int i = lane; i < V; i += 32) {
+        // the reference's GLA op returns o in the activation dtype before the norm
+        const float xv = to_f(from_f<T>(x[i]));
+        ss = fmaf(xv, xv, ss);
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)V + eps);
+    for (int i = lane; i < V; i += 32) {
+        const float xv = to_f(from_f<T>(x[i]));
+        const float gv = to_f(g[(size_t)row * V + i]);
+        const float wv = w != nullptr ? to_f(w[i]) : 1.f;
+        out[(size_t)row * V + i] = from_f<T>(xv * rstd * wv * gv * sigmoidf_(gv));
+    }
+}
+
+template <typename T, typename CT>
+int launch_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g, const void *wq,
+                const void *wk, const void *wv, void *cq, void *ck, void *cv, void *S, const void *norm_w,
+                void *out, float *ws, int B, int H, int K, int V, int W, float scale, float gate_normalizer,
+                float eps, cudaStream_t st) {
+    const int HK = H * K, HV = H * V;
+    float *qf = ws, *kf = qf + (size_t)B * HK, *ef = kf + (size_t)B * HK, *vf = ef + (size_t)B * HK,
+          *of = vf + (size_t)B * HV;
+    const long long n1 = (long long)B * (3 * HK + HV);
+    gla_step_prep_kernel<T, CT><<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(
+        (const T *)xq, (const T *)xk, (const T *)xv, (const T *)gk_raw, (const T *)wq, (const T *)wk,
+        (const T *)wv, (CT *)cq, (CT *)ck, (CT *)cv, qf, kf, ef, vf, B, HK, HV, W, scale, 1.f / gate_normalizer);
+    LINA_LAUNCH_OK("gla_step_prep_kernel");
+    constexpr int VEC = sizeof(CT) == 4 ? 4 : 8;
+    dim3 grid((V + 32 * VEC - 1) / (32 * VEC), B * H);
+    gla_step_state_kernel<CT, VEC><<<grid, SW * 32, 0, st>>>((CT *)S, qf, kf, ef, vf, of, K, V);
+    LINA_LAUNCH_OK("gla_step_state_kernel");
+    const int rows = B * H;
+    gla_step_norm_kernel<T><<<(rows + 7) / 8, 256, 0, st>>>(of, (const T *)g, (const T *)norm_w, (T *)out, rows, V, eps);
+    LINA_LAUNCH_OK("gla_step_norm_kernel");
+    return LINA_OK;
+}
+
+}  // namespace
+
+extern "C" size_t lina_gla_step_workspace_bytes(int B, int H, int K, int V) {
+    return ((size_t)3 * B * H * K + (size_t)2 * B * H * V) * sizeof(float);
+}
+
+extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                             const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                             void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
+                             int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
+                             void *stream) {
+    LINA_REQUIRE(B > 0 && H > 0 && K > 0 && V > 0, LINA_ERR_BAD_ARG, "gla_step: non-positive size");
+    LINA_REQUIRE(xq && xk && xv && gk_raw && g && S && out && ws, LINA_ERR_BAD_ARG, "gla_step: null pointer");
+    const bool conv = wq != nullptr;
+    LINA_REQUIRE(!conv || (wk && wv && cq && ck && cv && W >= 1 && W <= 16), LINA_ERR_BAD_ARG,
+                 "gla_step: short conv needs all three taps/states and 1 <= W <= 16");
+    LINA_REQUIRE(K <= 256, LINA_ERR_UNSUPPORTED, "gla_step: K=%d > 256 not implemented", K);
+    LINA_REQUIRE((long long)B * H <= 65535, LINA_ERR_UNSUPPORTED, "gla_step: B*H > 65535");
+    LINA_REQUIRE(state_dtype == LINA_F32 || state_dtype == LINA_BF16, LINA_ERR_UNSUPPORTED,
+                 "gla_step: state dtype must be f32 or bf16");
+    LINA_REQUIRE(V % (state_dtype == LINA_F32 ? 4 : 8) == 0, LINA_ERR_UNSUPPORTED,
+                 "gla_step: V=%d must be a multiple of %d", V, state_dtype == LINA_F32 ? 4 : 8);
+    LINA_REQUIRE(gate_normalizer != 0.f, LINA_ERR_BAD_ARG, "gla_step: zero gate normalizer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO_(T, CT) return launch_step<T, CT>(xq, xk, xv, gk_raw, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, \
+                                             (float *)ws, B, H, K, V, W, scale, gate_normalizer, eps, st)
+    if (dtype == LINA_F32 && state_dtype == LINA_F32) GO_(float, float);
+    if (dtype == LINA_BF16 && state_dtype == LINA_BF16) GO_(bf16, bf16);
+    if (dtype == LINA_BF16 && state_dtype == LINA_F32) GO_(bf16, float);
+    if (dtype == LINA_F32 && state_dtype == LINA_BF16) GO_(float, bf16);
+#undef GO_
+    lina_set_error("gla_step: dtype %d / state dtype %d combination not implemented", dtype, state_dtype);
+    return LINA_ERR_UNSUPPORTED;
+}

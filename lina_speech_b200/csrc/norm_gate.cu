@@ -1,0 +1,178 @@
+// FusedRMSNormSwishGate: y = x * rsqrt(mean(x^2) + eps) * w * g * sigmoid(g) over rows of length N.
+//
+// Replaces FLA/fla/modules/fused_norm_gate.py:72-139 (fwd kernel) and :220-335 (bwd kernel), entry
+// rms_norm_swish_gate_fn :439-518.  HBM streaming: fwd reads x,g and writes y once (3 tensors);
+// bwd reads x,g,dy and writes dx,dg (5 tensors).  One warp per row, 16-byte vector accesses, the row
+// stays in registers between the reduction and the normalisation (N <= 32*VPL*MAXCH elements).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXCH = 4;   // 16-byte chunks per lane kept in registers
+
+template <typename T> struct V16 { static constexpr int n = 16 / sizeof(T); };
+
+template <typename T> __device__ __forceinline__ void load16(const T *p, float *x) {
+    constexpr int n = V16<T>::n;
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = to_f(e[i]);
+}
+template <typename T> __device__ __forceinline__ void store16(T *p, const float *x) {
+    constexpr int n = V16<T>::n;
+    uint4 raw;
+    T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+    for (int i = 0; i < n; ++i) e[i] = from_f<T>(x[i]);
+    *reinterpret_cast<uint4 *>(p) = raw;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_gate_fwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *__restrict__ w, T *__restrict__ y,
+                     float *__restrict__ rstd_out, int M, int N, float eps) {
+    constexpr int n = V16<T>::n;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const T *xr = x + (size_t)row * N, *gr = g + (size_t)row * N;
+    T *yr = y + (size_t)row * N;
+    const int nch = N / n;                 // host guarantees N % n == 0 and nch <= 32*MAXCH
+    float xv[MAXCH][n];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            load16<T>(xr + (size_t)ch * n, xv[c]);
+#pragma unroll
+            for (int i = 0; i < n; ++i) ss = fmaf(xv[c][i], xv[c][i], ss);
+        }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)N + eps);
+    if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            float gv[n], wv[n], out[n];
+            load16<T>(gr + (size_t)ch * n, gv);
+            if (w != nullptr) load16<T>(w + (size_t)ch * n, wv);
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float yh = xv[c][i] * rstd * (w != nullptr ? wv[i] : 1.f);
+                out[i] = yh * gv[i] * sigmoidf_(gv[i]);
+            }
+            store16<T>(yr + (size_t)ch * n, out);
+        }
+    }
+}
+
+// dx = rstd * (dxh - xh * mean(dxh * xh)), dxh = dy * w * swish(g), xh = x * rstd
+// dg = dy * xh * w * swish'(g), swish'(g) = s (1 + g (1 - s)) ;  dw += sum_rows dy * xh * swish(g)
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_gate_bwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *__restrict__ w,
+                     const float *__restrict__ rstd_in, const T *__restrict__ dy, T *__restrict__ dx,
+                     T *__restrict__ dg, float *__restrict__ dw, int M, int N, int rows_per_warp) {
+    constexpr int n = V16<T>::n;
+    const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int nch = N / n;
+    float dwl[MAXCH][n];
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c)
+#pragma unroll
+        for (int i = 0; i < n; ++i) dwl[c][i] = 0.f;
+    for (int rr = 0; rr < rows_per_warp; ++rr) {
+        const int row = wid * rows_per_warp + rr;
+        if (row >= M) break;
+        const size_t off = (size_t)row * N;
+        const float rstd = rstd_in[row];
+        float xh[MAXCH][n], dxh[MAXCH][n];
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+                float xv[n], gv[n], dyv[n], wv[n], dgo[n];
+                load16<T>(x + off + (size_t)ch * n, xv);
+                load16<T>(g + off + (size_t)ch * n, gv);
+                load16<T>(dy + off + (size_t)ch * n, dyv);
+                if (w != nullptr) load16<T>(w + (size_t)ch * n, wv);
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const float s = sigmoidf_(gv[i]);
+                    const float sw = gv[i] * s;
+                    const float wi = w != nullptr ? wv[i] : 1.f;
+                    xh[c][i] = xv[i] * rstd;
+                    dxh[c][i] = dyv[i] * wi * sw;
+                    dot = fmaf(dxh[c][i], xh[c][i], dot);
+                    dgo[i] = dyv[i] * xh[c][i] * wi * s * (1.f + gv[i] * (1.f - s));
+                    dwl[c][i] = fmaf(dyv[i] * xh[c][i], sw, dwl[c][i]);
+                }
+                store16<T>(dg + off + (size_t)ch * n, dgo);
+            }
+        }
+        dot = warp_sum(dot) / (float)N;
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+                float out[n];
+#pragma unroll
+                for (int i = 0; i < n; ++i) out[i] = rstd * (dxh[c][i] - xh[c][i] * dot);
+                store16<T>(dx + off + (size_t)ch * n, out);
+            }
+        }
+    }
+    if (dw != nullptr) {
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) atomicAdd(&dw[(size_t)ch * n + i], dwl[c][i]);
+            }
+        }
+    }
+}
+
+int check(int M, int N, int dtype) {
+    LINA_REQUIRE(M > 0 && N > 0, LINA_ERR_BAD_ARG, "rmsnorm_swishgate: non-positive size");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "rmsnorm_swishgate: unknown dtype %d", dtype);
+    const int n = 16 / (int)lina_dtype_size(dtype);
+    LINA_REQUIRE(N % n == 0 && N / n <= 32 * MAXCH, LINA_ERR_UNSUPPORTED,
+                 "rmsnorm_swishgate: row length N=%d must be a multiple of %d and <= %d", N, n, 32 * MAXCH * n);
+    return LINA_OK;
+}
+
+}  // namespace
+
+extern "C" int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void *y, float *rstd, int M,
+                                          int N, float eps, int dtype, void *stream) {
+    LINA_REQUIRE(x && g && y, LINA_ERR_BAD_ARG, "rmsnorm_swishgate_fwd: null pointer");
+    int rc = check(M, N, dtype);
+    if (rc) return rc;
+    LINA_DISPATCH_DTYPE(dtype, norm_gate_fwd_kernel<T_><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)x, (const T_ *)g, (const T_ *)w, (T_ *)y, rstd, M, N, eps));
+    LINA_LAUNCH_OK("norm_gate_fwd_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, const float *rstd,
+                                          const void *dy, void *dx, void *dg, float *dw, int M, int N, int dtype,
+                                          void *stream) {
+    LINA_REQUIRE(x && g && rstd && dy && dx && dg, LINA_ERR_BAD_ARG, "rmsnorm_swishgate_bwd: null pointer");
+    int rc = check(M, N, dtype);
+    if (rc) return rc;
+    // ~4 warps per SM-slot keeps the dw atomics to O(1000 * N)
+    int rows_per_warp = (M + 148 * 8 * 4 - 1) / (148 * 8 * 4);
+    if (rows_per_warp < 1) rows_per_warp = 1;
+    const int nwarps = (M + rows_per_warp - 1) / rows_per_warp;
+    LINA_DISPATCH_DTYPE(dtype, norm_gate_bwd_kernel<T_><<<(nwarps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)x, (const T_ *)g, (const T_ *)w, rstd, (const T_ *)dy, (T_ *)dx,
+                                   (T_ *)dg, dw, M, N, rows_per_warp));
+    LINA_LAUNCH_OK("norm_gate_bwd_kernel");
+    return LINA_OK;
+}

@@ -1,0 +1,159 @@
+// ShortConvolution: depthwise causal conv (kernel W <= 8) + SiLU over [B,L,D], channels-last.
+//
+// Replaces the external causal-conv1d 1.3.0.post1 CUDA kernels the reference calls at
+// FLA/fla/modules/convolution.py:168-173 (causal_conv1d_fn) and :189-195 (causal_conv1d_update);
+// semantics are those of the in-tree torch branch :175-178 / :197-204.
+//
+// Pure HBM streaming: x is read once (+ (W-1)/LT halo), y written once.  Threads run along the
+// channel dim (coalesced rows of [B,L,D]); each thread slides a W-tap window over LT time steps.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 16;      // time steps per thread
+constexpr int MAXW = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+short_conv_fwd_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__restrict__ y, void *__restrict__ cache,
+                      int cache_dtype, int L, int D, int W, int silu) {
+    const int d = blockIdx.x * 128 + threadIdx.x;
+    const int l0 = blockIdx.y * LT, b = blockIdx.z;
+    if (d >= D) return;
+    float wt[MAXW], win[MAXW];
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) wt[j] = j < W ? to_f(w[(size_t)d * W + j]) : 0.f;
+    const T *xb = x + (size_t)b * L * D + d;
+    T *yb = y + (size_t)b * L * D + d;
+    // win[j] holds x[l - (W-1) + j]; preload the W-1 halo values
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) {
+        const int l = l0 - (W - 1) + j;
+        win[j] = (j < W - 1 && l >= 0) ? to_f(xb[(size_t)l * D]) : 0.f;
+    }
+    const int lend = min(L, l0 + LT);
+    for (int l = l0; l < lend; ++l) {
+        const float xv = to_f(xb[(size_t)l * D]);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXW; ++j) {
+            if (j < W - 1) acc = fmaf(win[j], wt[j], acc);
+        }
+        // tap W-1 multiplies the newest sample
+        float wl = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXW; ++j) if (j == W - 1) wl = wt[j];
+        acc = fmaf(xv, wl, acc);
+        yb[(size_t)l * D] = from_f<T>(silu ? siluf_(acc) : acc);
+#pragma unroll
+        for (int j = 0; j < MAXW - 1; ++j) {
+            if (j < W - 2) win[j] = win[j + 1];
+            else if (j == W - 2) win[j] = xv;
+        }
+    }
+    // cache[b,d,:] = last W inputs, zero left-padded when L < W   (convolution.py:164-166)
+    if (cache != nullptr && lend == L) {
+        for (int j = 0; j < W; ++j) {
+            const int l = L - W + j;
+            store_dyn(cache, cache_dtype, ((size_t)b * D + d) * W + j, l >= 0 ? to_f(xb[(size_t)l * D]) : 0.f);
+        }
+    }
+}
+
+// dx[l] = sum_j w[j] * dpre[l + (W-1) - j],  dpre = dy * act'(pre) ; dw[j] += sum_l dpre[l] * x[l-(W-1)+j]
+template <typename T>
+__global__ void __launch_bounds__(128)
+short_conv_bwd_kernel(const T *__restrict__ x, const T *__restrict__ w, const T *__restrict__ dy,
+                      T *__restrict__ dx, float *__restrict__ dw, int L, int D, int W, int silu) {
+    const int d = blockIdx.x * 128 + threadIdx.x;
+    const int l0 = blockIdx.y * LT, b = blockIdx.z;
+    if (d >= D) return;
+    float wt[MAXW], dwl[MAXW];
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) { wt[j] = j < W ? to_f(w[(size_t)d * W + j]) : 0.f; dwl[j] = 0.f; }
+    const T *xb = x + (size_t)b * L * D + d;
+    const T *dyb = dy + (size_t)b * L * D + d;
+    T *dxb = dx + (size_t)b * L * D + d;
+    auto xat = [&](int l) -> float { return (l >= 0 && l < L) ? to_f(xb[(size_t)l * D]) : 0.f; };
+    auto dpre_at = [&](int l) -> float {
+        if (l < 0 || l >= L) return 0.f;
+        const float g = to_f(dyb[(size_t)l * D]);
+        if (!silu) return g;
+        float pre = 0.f;
+        for (int j = 0; j < W; ++j) pre = fmaf(xat(l - (W - 1) + j), wt[j], pre);
+        const float s = sigmoidf_(pre);
+        return g * s * (1.f + pre * (1.f - s));
+    };
+    const int lend = min(L, l0 + LT);
+    for (int l = l0; l < lend; ++l) {
+        float acc = 0.f;
+        for (int j = 0; j < W; ++j) acc = fmaf(wt[j], dpre_at(l + (W - 1) - j), acc);
+        dxb[(size_t)l * D] = from_f<T>(acc);
+        const float dp = dpre_at(l);
+        for (int j = 0; j < W; ++j) dwl[j] = fmaf(dp, xat(l - (W - 1) + j), dwl[j]);
+    }
+    for (int j = 0; j < W; ++j) atomicAdd(&dw[(size_t)d * W + j], dwl[j]);
+}
+
+template <typename T>
+__global__ void short_conv_update_kernel(const T *__restrict__ x, void *__restrict__ cache, int cache_dtype,
+                                         const T *__restrict__ w, T *__restrict__ y, int B, int D, int W,
+                                         int silu) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * D) return;
+    const int d = (int)(i % D);
+    const size_t cbase = (size_t)i * W;
+    float acc = 0.f;
+    for (int j = 0; j < W - 1; ++j) {
+        const float nxt = load_dyn(cache, cache_dtype, cbase + j + 1);
+        store_dyn(cache, cache_dtype, cbase + j, nxt);
+        acc = fmaf(nxt, to_f(w[(size_t)d * W + j]), acc);
+    }
+    const float xv = to_f(x[i]);
+    store_dyn(cache, cache_dtype, cbase + W - 1, xv);
+    const float last = load_dyn(cache, cache_dtype, cbase + W - 1);
+    acc = fmaf(last, to_f(w[(size_t)d * W + W - 1]), acc);
+    y[i] = from_f<T>(silu ? siluf_(acc) : acc);
+}
+
+}  // namespace
+
+extern "C" int lina_short_conv_fwd(const void *x, const void *w, void *y, void *cache, int cache_dtype, int B,
+                                   int L, int D, int W, int silu, int dtype, void *stream) {
+    LINA_REQUIRE(x && w && y, LINA_ERR_BAD_ARG, "short_conv_fwd: null pointer");
+    LINA_REQUIRE(B > 0 && L > 0 && D > 0, LINA_ERR_BAD_ARG, "short_conv_fwd: non-positive size");
+    LINA_REQUIRE(W >= 1 && W <= MAXW, LINA_ERR_UNSUPPORTED, "short_conv_fwd: kernel size %d not in [1,%d]", W, MAXW);
+    LINA_REQUIRE(cache == nullptr || lina_dtype_ok(cache_dtype), LINA_ERR_BAD_ARG, "short_conv_fwd: bad cache dtype");
+    LINA_REQUIRE(B <= 65535 && (L + LT - 1) / LT <= 65535, LINA_ERR_UNSUPPORTED, "short_conv_fwd: grid too large");
+    dim3 grid((D + 127) / 128, (L + LT - 1) / LT, B);
+    LINA_DISPATCH_DTYPE(dtype, short_conv_fwd_kernel<T_><<<grid, 128, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)x, (const T_ *)w, (T_ *)y, cache, cache_dtype, L, D, W, silu));
+    LINA_LAUNCH_OK("short_conv_fwd_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_short_conv_bwd(const void *x, const void *w, const void *dy, void *dx, float *dw, int B, int L,
+                                   int D, int W, int silu, int dtype, void *stream) {
+    LINA_REQUIRE(x && w && dy && dx && dw, LINA_ERR_BAD_ARG, "short_conv_bwd: null pointer");
+    LINA_REQUIRE(B > 0 && L > 0 && D > 0, LINA_ERR_BAD_ARG, "short_conv_bwd: non-positive size");
+    LINA_REQUIRE(W >= 1 && W <= MAXW, LINA_ERR_UNSUPPORTED, "short_conv_bwd: kernel size %d not in [1,%d]", W, MAXW);
+    LINA_REQUIRE(B <= 65535 && (L + LT - 1) / LT <= 65535, LINA_ERR_UNSUPPORTED, "short_conv_bwd: grid too large");
+    dim3 grid((D + 127) / 128, (L + LT - 1) / LT, B);
+    LINA_DISPATCH_DTYPE(dtype, short_conv_bwd_kernel<T_><<<grid, 128, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)x, (const T_ *)w, (const T_ *)dy, (T_ *)dx, dw, L, D, W, silu));
+    LINA_LAUNCH_OK("short_conv_bwd_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_short_conv_update(const void *x, void *cache, int cache_dtype, const void *w, void *y, int B,
+                                      int D, int W, int silu, int dtype, void *stream) {
+    LINA_REQUIRE(x && cache && w && y, LINA_ERR_BAD_ARG, "short_conv_update: null pointer");
+    LINA_REQUIRE(B > 0 && D > 0 && W >= 1 && W <= 64, LINA_ERR_BAD_ARG, "short_conv_update: bad size");
+    LINA_REQUIRE(lina_dtype_ok(cache_dtype), LINA_ERR_BAD_ARG, "short_conv_update: bad cache dtype");
+    const long long n = (long long)B * D;
+    LINA_DISPATCH_DTYPE(dtype, short_conv_update_kernel<T_><<<(unsigned)((n + 255) / 256), 256, 0,
+                                                              (cudaStream_t)stream>>>(
+                                   (const T_ *)x, cache, cache_dtype, (const T_ *)w, (T_ *)y, B, D, W, silu));
+    LINA_LAUNCH_OK("short_conv_update_kernel");
+    return LINA_OK;
+}

@@ -1,0 +1,147 @@
+"""Drop-in replacements for the reference's GLA operator API.
+
+Same names, argument meaning, return values and autograd behaviour as
+
+  fla.ops.gla.fused_recurrent_gla   FLA/fla/ops/gla/recurrent_fuse.py:13-27
+  fla.ops.gla.fused_chunk_gla       FLA/fla/ops/gla/chunk_fuse.py:518-536
+  fla.ops.gla.chunk_gla             FLA/fla/ops/gla/chunk.py:453-491
+
+(FLA/ = 3rdparty/flash-linear-attention/ of the reference), backed by the CUDA
+kernels of liblina_b200.so through the C ABI in include/lina_b200.h.
+
+Contract: q, k, gk [B,H,T,K]; v [B,H,T,V]; head-first, made
+contiguous here; any float dtype (kernels compute in fp32); ``o`` comes back in
+v.dtype, ``final_state`` always fp32 [B,H,K,V]; ``initial_state`` any float dtype
+or None; ``scale`` None / -1 means K**-0.5; gates are log-space (<= 0).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+
+
+def _prep(q, k, v, gk, h0):
+    L.require_cuda(q, k, v, gk, h0)
+    if not (q.dtype == k.dtype == v.dtype == gk.dtype):
+        q, k, v, gk = (x.float() for x in (q, k, v, gk))   # mixed dtypes: compute everything in fp32
+    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
+    if h0 is not None:
+        h0 = h0.contiguous()
+        if h0.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            h0 = h0.float()
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    if k.shape != q.shape or gk.shape != q.shape or v.shape[:3] != q.shape[:3]:
+        raise ValueError(f"GLA shapes disagree: q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} gk{tuple(gk.shape)}")
+    if h0 is not None and tuple(h0.shape) != (B, H, K, V):
+        raise ValueError(f"initial_state must be [B,H,K,V]={B, H, K, V}, got {tuple(h0.shape)}")
+    return q, k, v, gk, h0, (B, H, T, K, V)
+
+
+def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
+    lib = L.lib()
+    B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
+    o = torch.empty_like(v)
+    ht = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_ht else None
+    h0dt = L.dt(h0) if h0 is not None else 0
+    if kind == "recurrent":
+        rc = lib.lina_gla_recurrent_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(h0), h0dt, L.ptr(o),
+                                        L.ptr(ht), B, H, T, K, V, L.dt(q), scale, L.stream(q))
+        L.count_launches(1)
+    else:
+        nbytes = lib.lina_gla_chunk_fwd_workspace_bytes(B, H, T, K, V, L.dt(q))
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=q.device)
+        rc = lib.lina_gla_chunk_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(h0), h0dt, L.ptr(o), L.ptr(ht),
+                                    L.ptr(ws), B, H, T, K, V, L.dt(q), scale, L.stream(q))
+        L.count_launches(1)
+    L.check(rc, f"lina_gla_{kind}_fwd")
+    return o, ht
+
+
+def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
+    lib = L.lib()
+    B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
+    do = do.contiguous()
+    if do.dtype != q.dtype:
+        do = do.to(q.dtype)
+    if dht is not None:
+        dht = dht.contiguous().float()
+    dq, dk, dgk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(gk), torch.empty_like(v)
+    dh0 = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_dh0 else None
+    ws = torch.empty(int(lib.lina_gla_recurrent_bwd_workspace_bytes(B, H, T, K, V)), dtype=torch.uint8, device=q.device)
+    rc = lib.lina_gla_recurrent_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(h0),
+                                    L.dt(h0) if h0 is not None else 0, L.ptr(do), L.ptr(dht), L.ptr(dq), L.ptr(dk),
+                                    L.ptr(dv), L.ptr(dgk), L.ptr(dh0), L.ptr(ws), B, H, T, K, V, L.dt(q), scale,
+                                    L.stream(q))
+    L.count_launches(3)
+    L.check(rc, "lina_gla_recurrent_bwd")
+    return dq, dk, dv, dgk, dh0
+
+
+class _GLAFunction(torch.autograd.Function):
+    """kind in {'recurrent','chunk','fused_chunk'}; mirrors FusedRecurrentFunction
+    (FLA/fla/ops/common/fused_recurrent.py:261-343), ChunkGLAFunction (FLA/fla/ops/gla/chunk.py:343-450)
+    and FusedChunkGLAFunction (FLA/fla/ops/gla/chunk_fuse.py:302-502)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, q, k, v, gk, scale, initial_state, output_final_state, kind):
+        in_dtypes = (q.dtype, k.dtype, v.dtype, gk.dtype)
+        q, k, v, gk, h0, _ = _prep(q, k, v, gk, initial_state)
+        o, ht = _fwd("recurrent" if kind == "recurrent" else "chunk", q, k, v, gk, h0, scale, output_final_state)
+        ctx.save_for_backward(q, k, v, gk, h0)
+        ctx.scale, ctx.kind, ctx.in_dtypes = scale, kind, in_dtypes
+        ctx.h0_dtype = initial_state.dtype if initial_state is not None else None
+        ctx.set_materialize_grads(False)
+        return o.to(in_dtypes[2]), ht
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, do, dht=None):
+        q, k, v, gk, h0 = ctx.saved_tensors
+        if do is None:
+            do = torch.zeros_like(v)
+        want_dh0 = h0 is not None and ctx.needs_input_grad[5] and ctx.kind != "fused_chunk"
+        dq, dk, dv, dgk, dh0 = _bwd(q, k, v, gk, h0, do, dht, ctx.scale, want_dh0)
+        dts = ctx.in_dtypes
+        if dh0 is not None and ctx.h0_dtype is not None:
+            dh0 = dh0.to(ctx.h0_dtype)
+        return dq.to(dts[0]), dk.to(dts[1]), dv.to(dts[2]), dgk.to(dts[3]), None, dh0, None, None
+
+
+def _scale(scale, K: int) -> float:
+    return float(K) ** -0.5 if (scale is None or scale == -1) else float(scale)
+
+
+def fused_recurrent_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, gk: torch.Tensor = None,
+                        gv: torch.Tensor = None, scale: Optional[float] = None,
+                        initial_state: torch.Tensor = None, output_final_state: bool = False,
+                        reverse: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """FLA/fla/ops/gla/recurrent_fuse.py:13-27.  ``gv`` / ``reverse`` / ``gk=None`` are generic
+    fla options Lina never uses (model/gla.py:187-203); they raise instead of silently differing."""
+    if gv is not None or reverse or gk is None:
+        raise NotImplementedError("lina_speech_b200.fused_recurrent_gla: only the (q,k,v,gk) causal form used by "
+                                  "model/gla.py is implemented (no gv, no reverse, gk required)")
+    return _GLAFunction.apply(q, k, v, gk, _scale(scale, q.shape[-1]), initial_state, output_final_state, "recurrent")
+
+
+def fused_chunk_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, scale: float = -1,
+                    initial_state: torch.Tensor = None, output_final_state: bool = False
+                    ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """FLA/fla/ops/gla/chunk_fuse.py:518-536 -- detaches ``initial_state`` (:529-530); any T (the
+    reference pads to a multiple of 16, :505-511,:531; the kernels here mask instead)."""
+    if initial_state is not None:
+        initial_state = initial_state.detach()
+    return _GLAFunction.apply(q, k, v, g, _scale(scale, q.shape[-1]), initial_state, output_final_state, "fused_chunk")
+
+
+def chunk_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, scale: Optional[float] = None,
+              initial_state: torch.Tensor = None, output_final_state: bool = False,
+              checkpoint_level: Optional[int] = 2) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """FLA/fla/ops/gla/chunk.py:453-491 (``checkpoint_level`` is accepted and validated; nothing is
+    cached between forward and backward here, which is level 2's behaviour)."""
+    assert checkpoint_level in [0, 1, 2]
+    return _GLAFunction.apply(q, k, v, g, _scale(scale, q.shape[-1]), initial_state, output_final_state, "chunk")

@@ -1,0 +1,70 @@
+"""MixingBlock / SwiGLU / SelfAttention (model/base_blocks.py:9-69), same parameter names."""
+from typing import Callable
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class SelfAttention(nn.Module):
+    """model/base_blocks.py:9-40.  Bidirectional text-encoder attention (runs once per utterance,
+    off the hot path).  ``rotary=True`` needs rotary-embedding-torch, exactly as in the reference."""
+
+    def __init__(self, dim, heads, rotary=True, is_causal=False):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim)
+        assert dim % heads == 0
+        self.heads = heads
+        self.rotary = None
+        if rotary:
+            from rotary_embedding_torch import RotaryEmbedding  # optional dependency of the reference too
+            self.rotary = RotaryEmbedding((dim // heads) // 2)
+        self.is_causal = is_causal
+
+    def forward(self, x, mask=None, pos=None, cache=None, layer_idx=None, time_step=0):
+        B, n, d = x.shape
+        q, k, v = (t.view(B, n, self.heads, -1).transpose(1, 2) for t in self.qkv(x).chunk(3, dim=-1))
+        if cache is not None:
+            assert layer_idx is not None
+            cache.update(k, v, layer_idx=layer_idx)
+            k, v = cache[layer_idx]
+        if self.rotary is not None:
+            if pos is not None:
+                from rotary_embedding_torch import apply_rotary_emb
+                q, k = (apply_rotary_emb(self.rotary(pos).unsqueeze(1), t) for t in (q, k))
+            else:
+                q = self.rotary.rotate_queries_or_keys(q, offset=time_step)
+                k = self.rotary.rotate_queries_or_keys(k)
+        y = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=self.is_causal)
+        return y.transpose(1, 2).reshape(B, n, d)
+
+
+class SwiGLU(nn.Module):
+    """model/base_blocks.py:42-50: hidden = 4d//3, biases on both linears."""
+
+    def __init__(self, d_model):
+        super().__init__()
+        self.p_in = nn.Linear(d_model, (d_model * 4 // 3) * 2)
+        self.p_out = nn.Linear(d_model * 4 // 3, d_model)
+
+    def forward(self, x):
+        gate, u = self.p_in(x).chunk(2, dim=-1)
+        return self.p_out(F.silu(gate) * u)
+
+
+class MixingBlock(nn.Module):
+    """Pre-LN residual wrapper (model/base_blocks.py:56-69): tmix then cmix."""
+
+    def __init__(self, tmix: Callable, cmix: Callable, norm: Callable, dropout: float = 0.0):
+        super().__init__()
+        self.tmix = tmix()
+        self.cmix = cmix()
+        self.norm1 = norm()
+        self.norm2 = norm()
+        self.drop = nn.Dropout(dropout)
+
+    def forward(self, x, **kwargs):
+        t = self.tmix(self.norm1(x), **kwargs)
+        x = (t[0] if type(t) is tuple else t) + x
+        x = self.cmix(self.norm2(x)) + x
+        return self.drop(x)

@@ -1,0 +1,301 @@
+"""GLA token mixer and the AttentiveGLA backbone -- host side of the B200 hot path.
+
+Mirrors the reference's ``model/gla.py`` (class names, constructor arguments, parameter names,
+``forward / init_state / step / to_mode / get_init_state_tuning_params / get_state_from_params``)
+so checkpoints and callers (LinaModel, train_initial_state, the notebook) carry over unchanged.
+The arithmetic between the dense projections runs in liblina_b200.so:
+
+  * multi-token calls: ShortConvolution -> fused_recurrent_gla / fused_chunk_gla / chunk_gla ->
+    FusedRMSNormSwishGate, i.e. the reference's own sequence (model/gla.py:146-225) on our ops;
+  * single-token calls with a cache in eval mode: ONE fused step (``lina_gla_step``) that rolls the
+    three conv states, applies the gate non-linearity, updates the recurrent state in place and
+    applies the norm-gate -- replacing ~12 launches and 4 state copies per layer per token.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from einops import einsum, rearrange, repeat
+
+from .. import _lib as L
+from ..fla_api import (Cache, FusedRMSNormSwishGate, ShortConvolution, chunk_gla, fused_chunk_gla,
+                       fused_recurrent_gla)
+from .attentive_rnn import AttentiveRNN
+from .base_blocks import MixingBlock, SwiGLU
+from .crossatt import BlindCrossAttention, CrossAttention
+
+if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
+    def maybe_grad_ckpt(f):
+        def wrapped(*args, **kwargs):
+            return torch.utils.checkpoint.checkpoint(f, *args, **kwargs, use_reentrant=False)
+        return wrapped
+else:
+    def maybe_grad_ckpt(f):
+        return f
+
+
+class GatedLinearAttention(nn.Module):
+    """model/gla.py:44-247."""
+
+    def __init__(self, mode: str = "fused_chunk", hidden_size: int = 1024, expand_k: float = 1.0,
+                 expand_v: float = 2.0, num_heads: int = 4, use_short_conv: bool = False, conv_size: int = 4,
+                 conv_bias: bool = False, share_conv_kernel: bool = False, gate_fn: str = "swish",
+                 layernorm_eps: float = 1e-5, gate_logit_normalizer: int = 16, gate_low_rank_dim: int = 16,
+                 clamp_min: Optional[float] = None, fuse_norm: bool = True, layer_idx: int = None, **kwargs):
+        super().__init__()
+        assert mode in ["chunk", "fused_recurrent", "fused_chunk"], f"Not supported mode `{mode}`."
+        if share_conv_kernel or conv_bias or gate_fn != "swish" or not fuse_norm:
+            raise NotImplementedError("only the configuration AttentiveGLA builds (model/gla.py:270-274) is "
+                                      "implemented: separate q/k/v short convs without bias, fused swish norm-gate")
+        self.mode = mode
+        self.hidden_size, self.expand_k, self.expand_v, self.num_heads = hidden_size, expand_k, expand_v, num_heads
+        self.use_short_conv, self.conv_size, self.conv_bias = use_short_conv, conv_size, conv_bias
+        self.share_conv_kernel = share_conv_kernel
+        self.key_dim, self.value_dim = int(hidden_size * expand_k), int(hidden_size * expand_v)
+        self.clamp_min, self.layer_idx = clamp_min, layer_idx
+        assert self.key_dim % num_heads == 0 and self.value_dim % num_heads == 0
+        self.head_qk_dim, self.head_v_dim = self.key_dim // num_heads, self.value_dim // num_heads
+
+        self.q_proj = nn.Linear(hidden_size, self.key_dim, bias=False)
+        self.k_proj = nn.Linear(hidden_size, self.key_dim, bias=False)
+        self.v_proj = nn.Linear(hidden_size, self.value_dim, bias=False)
+        self.g_proj = nn.Linear(hidden_size, self.value_dim, bias=False)
+        self.gk_proj = nn.Sequential(nn.Linear(hidden_size, gate_low_rank_dim, bias=False),
+                                     nn.Linear(gate_low_rank_dim, self.key_dim, bias=True))
+        self.o_proj = nn.Linear(self.value_dim, hidden_size, bias=False)
+        if use_short_conv:
+            self.q_conv1d = ShortConvolution(self.key_dim, conv_size, activation="silu")
+            self.k_conv1d = ShortConvolution(self.key_dim, conv_size, activation="silu")
+            self.v_conv1d = ShortConvolution(self.value_dim, conv_size, activation="silu")
+        self.g_norm_swish_gate = FusedRMSNormSwishGate(self.head_v_dim, eps=layernorm_eps)
+        self.fuse_norm_and_gate = True
+        self.gate_logit_normalizer = gate_logit_normalizer
+        self._wcat = None
+        self.apply(self._initialize_weights)
+
+    def _initialize_weights(self, module: nn.Module):       # model/gla.py:122-129
+        if getattr(module, "_is_hf_initialized", False):
+            return
+        if isinstance(module, nn.Linear):
+            nn.init.xavier_uniform_(module.weight, gain=2 ** -2.5)
+            if module.bias is not None:
+                nn.init.zeros_(module.bias)
+        module._is_hf_initialized = True
+
+    # -- single-token fast path --------------------------------------------------------------------
+    def _cat_weight(self):
+        """[q;k;v;g;gk0] projection weights stacked so a decode step needs one GEMM for them."""
+        ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.g_proj.weight, self.gk_proj[0].weight)
+        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
+        if self._wcat is None or self._wcat[0] != key:
+            self._wcat = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        return self._wcat[1]
+
+    def _step(self, x: torch.Tensor, state: Tuple[torch.Tensor, ...]) -> torch.Tensor:
+        B = x.shape[0]
+        H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
+        proj = F.linear(x.view(B, -1), self._cat_weight())
+        xq, xk, xv, g, lo = torch.split(proj, [kd, kd, vd, vd, proj.shape[1] - 2 * kd - 2 * vd], dim=1)
+        gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
+        xq, xk, xv, g = xq.contiguous(), xk.contiguous(), xv.contiguous(), g.contiguous()
+        if self.use_short_conv:
+            cq, ck, cv, S = state
+            W = self.conv_size
+            wq, wk, wv = (c.weight.to(x.dtype) for c in (self.q_conv1d, self.k_conv1d, self.v_conv1d))
+        else:
+            (S,) = state
+            cq = ck = cv = wq = wk = wv = None
+            W = 1
+        if not S.is_contiguous() or (cq is not None and not (cq.is_contiguous() and ck.is_contiguous() and cv.is_contiguous())):
+            raise ValueError("cache states must be contiguous")
+        if cq is not None and not (cq.dtype == ck.dtype == cv.dtype == S.dtype):
+            raise ValueError("conv states and recurrent state must share one dtype")
+        lib = L.lib()
+        out = torch.empty(B, vd, dtype=x.dtype, device=x.device)
+        ws = torch.empty(int(lib.lina_gla_step_workspace_bytes(B, H, K, V)), dtype=torch.uint8, device=x.device)
+        nw = self.g_norm_swish_gate.weight
+        nw = nw.to(x.dtype) if nw is not None else None
+        rc = lib.lina_gla_step(L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(gk_raw), L.ptr(g), L.ptr(wq), L.ptr(wk),
+                               L.ptr(wv), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.ptr(S), L.ptr(nw), L.ptr(out),
+                               L.ptr(ws), B, H, K, V, W, L.dt(x), L.dt(S), float(K) ** -0.5,
+                               float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), L.stream(x))
+        L.count_launches(3)
+        L.check(rc, "lina_gla_step")
+        return self.o_proj(out).view(B, 1, -1)
+
+    def _can_step(self, x, state, reset_mask, attention_mask) -> bool:
+        return (x.shape[1] == 1 and state is not None and not self.training and not torch.is_grad_enabled()
+                and reset_mask is None and attention_mask is None and self.clamp_min is None
+                and x.dtype in (torch.float32, torch.bfloat16) and state[-1].dtype in (torch.float32, torch.bfloat16)
+                and self.head_v_dim % 8 == 0 and self.head_qk_dim <= 256)
+
+    # -- general path ------------------------------------------------------------------------------
+    def forward(self, hidden_states: torch.Tensor, reset_mask: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None, reset_val: float = -20,
+                past_key_values: Optional[Cache] = None, use_cache: Optional[bool] = False,
+                output_attentions: Optional[bool] = False, **kwargs) -> torch.Tensor:
+        """model/gla.py:131-227."""
+        L.require_cuda(hidden_states)
+        mode = self.mode
+        last_state = past_key_values[self.layer_idx] if use_cache else None
+        if self._can_step(hidden_states, last_state, reset_mask, attention_mask):
+            o = self._step(hidden_states, last_state)
+            past_key_values.update(last_state, self.layer_idx, 1)      # in place already: bumps seen_tokens only
+            return o
+
+        q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+        if self.use_short_conv:
+            cq, ck, cv = (last_state[0], last_state[1], last_state[2]) if use_cache else (None, None, None)
+            q = self.q_conv1d(q, attention_mask, cq)
+            k = self.k_conv1d(k, attention_mask, ck)
+            v = self.v_conv1d(v, attention_mask, cv)
+        if attention_mask is not None:
+            v = v.mul_(attention_mask.unsqueeze(-1))
+        H = self.num_heads
+        q, k, v = (rearrange(t, "b l (h d) -> b h l d", h=H) for t in (q, k, v))
+        gk = rearrange(self.gk_proj(hidden_states), "b n (h d) -> b h n d", h=H)
+        gk = F.logsigmoid(gk) / self.gate_logit_normalizer
+        if self.clamp_min is not None:
+            gk = torch.clamp_min(gk, self.clamp_min)
+        if reset_mask is not None:
+            gk = gk.masked_fill(reset_mask.unsqueeze(1).unsqueeze(3), reset_val)
+
+        recurrent_state = last_state[-1] if use_cache else None
+        if mode == "fused_recurrent":
+            o, recurrent_state = fused_recurrent_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+        elif mode == "fused_chunk":
+            o, recurrent_state = fused_chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+        elif mode == "chunk":
+            o, recurrent_state = chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+        else:
+            raise NotImplementedError(f"Not supported mode `{mode}`.")
+
+        if past_key_values is not None and not self.training:          # model/gla.py:205-213
+            if self.use_short_conv:
+                new_state = (cq, ck, cv, recurrent_state)
+            else:
+                new_state = (recurrent_state,)
+            past_key_values.update(new_state, self.layer_idx, q.shape[2])
+
+        o = rearrange(o, "b h l d -> b l h d")
+        g = rearrange(self.g_proj(hidden_states), "b l (h d) -> b l h d", h=H)
+        o = self.g_norm_swish_gate(o, g)
+        return self.o_proj(rearrange(o, "b l h d -> b l (h d)"))
+
+    def init_state(self, batch_size: int) -> Tuple[torch.Tensor, ...]:
+        """model/gla.py:229-240: zeros in the parameter dtype."""
+        p = next(self.parameters())
+        state = tuple()
+        if self.use_short_conv:
+            state += (p.new_zeros(batch_size, self.key_dim, self.conv_size),
+                      p.new_zeros(batch_size, self.key_dim, self.conv_size),
+                      p.new_zeros(batch_size, self.value_dim, self.conv_size))
+        return state + (p.new_zeros(batch_size, self.num_heads, self.head_qk_dim, self.head_v_dim),)
+
+    def state_size(self, **kwargs) -> int:
+        n = self.key_dim * self.head_v_dim
+        for m in self.children():
+            if isinstance(m, ShortConvolution):
+                n += m.state_size
+        return n
+
+
+class AttentiveGLA(AttentiveRNN):
+    """model/gla.py:252-365: n_layer encoder blocks -> cross attention (+pos_net GLA block when
+    ``blind``) -> n_layer decoder blocks; layer_idx 0..N-1, N..2N-1, 2N."""
+
+    def __init__(self, d_model: int, n_layer: int, heads: int, dropout_att: float = 0.0, dropout: float = 0.0,
+                 d_blind: int = None, blind: bool = False, cross_att_pp: bool = False, rotary: bool = False,
+                 use_short_conv: bool = False, expand_k: float = 1.0, expand_v: float = 2.0,
+                 pos_type="sinusoidal"):
+        super().__init__()
+
+        def block(d, h, i):
+            return MixingBlock(lambda: GatedLinearAttention(hidden_size=d, num_heads=h, use_short_conv=use_short_conv,
+                                                            expand_k=expand_k, expand_v=expand_v, layer_idx=i),
+                               lambda: SwiGLU(d), lambda: nn.LayerNorm(d), dropout=dropout)
+
+        self.encoder = nn.ModuleList([block(d_model, heads, i) for i in range(n_layer)])
+        self.decoder = nn.ModuleList([block(d_model, heads, i) for i in range(n_layer, 2 * n_layer)])
+        if d_blind is None:
+            d_blind = d_model
+        if blind:
+            self.cross_att = BlindCrossAttention(d_model, d_model, d_model, 1, block(d_blind, heads, 2 * n_layer),
+                                                 dropout_att, pos_dim=d_blind, rotary=rotary, pos_type=pos_type)
+        elif cross_att_pp:
+            raise NotImplementedError("cross_att_pp is an experimental variant outside the shipped model")
+        else:
+            self.cross_att = CrossAttention(d_model, d_model, d_model, heads, dropout_att)
+
+    def forward(self, x, ctx, mask=None, pos=None, reset_mask=None, attention_only=None, forced_attention=None,
+                init_state=None, crossatt_pos=None):
+        """model/gla.py:287-300.  NB the cross attention's pos_net never sees ``init_state`` here."""
+        for e in self.encoder:
+            if self.training:
+                e = maybe_grad_ckpt(e)
+            x = e(x, use_cache=init_state is not None, past_key_values=init_state)
+        v, att = self.cross_att(x, ctx, mask=mask, reset_mask=reset_mask, pos=crossatt_pos)
+        x = x + v
+        for d in self.decoder:
+            if self.training:
+                d = maybe_grad_ckpt(d)
+            x = d(x, use_cache=init_state is not None, past_key_values=init_state)
+        return x, att
+
+    def init_state(self, max_seqlen=1000, batch_size=16):
+        """model/gla.py:302-313."""
+        cache = Cache()
+        blocks = list(self.encoder) + list(self.decoder)
+        for i, b in enumerate(blocks):
+            cache.update(b.tmix.init_state(batch_size), i, offset=0)
+        if hasattr(self.cross_att, "pos_net"):
+            cache.update(self.cross_att.pos_net.tmix.init_state(batch_size), len(blocks), offset=0)
+        return cache
+
+    def get_state_from_params(self, params, batch_size, scale=0.02):
+        """model/gla.py:315-325: S = (k (x) v summed over rank) * scale, written into slot [-1]."""
+        cache = self.init_state(batch_size=batch_size)
+        for i, x in enumerate(params):
+            if len(x) == 2:
+                state = einsum(*x, "b r h k vv, b r h kk v -> b h k v") * scale
+            else:
+                state = x[0]
+            state = repeat(state, "1 ... -> bs ...", bs=batch_size).clone()
+            cache.states[i] = cache.states[i][:-1] + (state,)
+        return cache
+
+    def to_mode(self, mode):
+        """model/gla.py:327-333 (the reference sets ``pos_net.mode`` on the MixingBlock, which has no
+        effect on its tmix; here the pos_net mixer really switches too)."""
+        for b in list(self.encoder) + list(self.decoder):
+            b.tmix.mode = mode
+        if hasattr(self.cross_att, "pos_net"):
+            self.cross_att.pos_net.mode = mode
+            self.cross_att.pos_net.tmix.mode = mode
+
+    def get_init_state_tuning_params(self, lora: Optional[int] = None, scale: float = 0.02, device=None):
+        """model/gla.py:336-356: per enc/dec layer rank-r factors k [1,r,H,K,1], v [1,r,H,1,V]."""
+        params = []
+        for b in list(self.encoder) + list(self.decoder):
+            t = b.tmix
+            K, V, H = t.head_qk_dim, t.head_v_dim, t.num_heads
+            if lora is not None:
+                params.append((nn.Parameter(torch.randn(1, lora, H, K, 1, device=device)),
+                               nn.Parameter(torch.randn(1, lora, H, 1, V, device=device) * scale)))
+            else:
+                params.append(nn.Parameter(torch.randn(1, H, K, V, device=device) * scale))
+        return params
+
+    def step(self, y_embd, x_enc, time_step, cache):
+        """model/gla.py:358-365: one token through every block, all blocks stateful."""
+        for e in self.encoder:
+            y_embd = e(y_embd, past_key_values=cache, use_cache=True)
+        v, att = self.cross_att(y_embd, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)
+        y_embd = y_embd + v
+        for d in self.decoder:
+            y_embd = d(y_embd, past_key_values=cache, use_cache=True)
+        return y_embd, att, cache

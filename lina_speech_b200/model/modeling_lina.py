@@ -1,0 +1,199 @@
+"""LinaModel: embeddings, teacher-forced forward, batched autoregressive sampling loop.
+
+Mirrors ``model/modeling_lina.py`` of the reference (``LinaModel.forward`` :61-108,
+``generate_batch`` :112-192) -- same constructor, parameter names, arguments and return values --
+on top of the B200 GLA backbone.  Additions (all opt-in, defaults reproduce the reference):
+
+  * ``stop_check_interval``: poll the "all sequences stopped" flag every n steps instead of forcing a
+    device->host sync per token (modeling_lina.py:172);
+  * ``cuda_graph``: capture one decode step (13 GLA blocks + cross attention + logits + sampling +
+    embedding) in a CUDA graph and replay it;
+  * ``dist_group``: batch-sharded generation over the GPUs of one node -- every rank decodes its own
+    slice of the batch and the sampled token ids are all-gathered once per step (NCCL over NVLink).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from einops import rearrange, reduce, repeat
+from torch import Tensor, nn
+
+from .attentive_rnn import AttentiveRNN
+from .multiembed import MultiEmbedding
+from .tools import topk_sampling, undelay_rvq
+
+
+def exists(x):
+    return x is not None
+
+
+class LogitsHead(nn.Module):
+    """EinMix("b n d -> b n q l", weight_shape="q l d") of the reference (modeling_lina.py:51-57):
+    a single ``weight[q, l, d]`` parameter, no bias."""
+
+    def __init__(self, q: int, l: int, d: int):
+        super().__init__()
+        bound = (3.0 / d) ** 0.5
+        self.weight = nn.Parameter(torch.empty(q, l, d).uniform_(-bound, bound))
+
+    def forward(self, x):
+        q, l, d = self.weight.shape
+        return F.linear(x, self.weight.view(q * l, d)).view(*x.shape[:-1], q, l)
+
+
+class LinaModel(nn.Module):
+    def __init__(self, attentive_rnn: AttentiveRNN, d_model: int, n_quant: int, n_codebook: int,
+                 n_special_token_in: int, n_special_token_out: int, n_txt_vocab: int, tie_embed: bool = False,
+                 txt_encoder: Optional[nn.Module] = None, spk_encoder: Optional[nn.Module] = None,
+                 mask_text_p: float = 0.0):
+        super().__init__()
+        self.n_quant, self.n_codebook = n_quant, n_codebook
+        self.n_special_token_in, self.n_special_token_out = n_special_token_in, n_special_token_out
+        self.mask_text_p = mask_text_p
+        self.n_txt_vocab = n_txt_vocab + int(mask_text_p > 0.0)
+        self.n_target_vocab = n_codebook + n_special_token_out
+        self.txt_encoder, self.spk_encoder, self.attentive_rnn = txt_encoder, spk_encoder, attentive_rnn
+        self.txt_embed = nn.Embedding(n_txt_vocab, d_model, padding_idx=0)
+        self.rvq_embed = MultiEmbedding(n_quant, n_codebook + n_special_token_in, d_model, padding_idx=0)
+        self.logits_head = LogitsHead(n_quant, self.n_target_vocab, d_model)
+        if tie_embed:
+            self.logits_head.weight = self.rvq_embed.weight
+
+    def forward(self, x, y, encoder_mask, crossatt_mask, logits_mask=None, attention_only=False,
+                forced_attention=None, init_state=None, crossatt_pos=None):
+        """Teacher-forced pass (modeling_lina.py:61-108). x [b,n_txt] ids; y [b,n,q] ids.
+        Returns (logits [b,n-1,q,l], loss, att, masked_logits, masked_target)."""
+        if self.mask_text_p > 0.0:
+            m = torch.empty(x.shape[0]).bernoulli_(self.mask_text_p).bool()
+            x[m] = self.n_txt_vocab - 1
+        x_embd = self.txt_embed(x)
+        y_embd = self.rvq_embed(rearrange(y, "b n q -> q b n")).sum(0)
+        x_enc = self.txt_encoder(x_embd, mask=encoder_mask)
+        if self.spk_encoder is not None:
+            y_embd[:, 0] = self.spk_encoder(y_embd)
+        y_hat, att = self.attentive_rnn(
+            y_embd[:, :-1, :], x_enc, mask=crossatt_mask[:, :-1],
+            forced_attention=forced_attention[:, :, :y_embd.shape[1] - 1] if forced_attention is not None else None,
+            attention_only=attention_only, init_state=init_state, crossatt_pos=crossatt_pos)
+        if attention_only:
+            return att
+        logits = self.logits_head(y_hat)
+        if logits_mask is not None:
+            masked_logits = logits[logits_mask[:, 1:], :, :]
+            masked_target = y[:, 1:][logits_mask[:, 1:], :]
+        else:
+            masked_logits, masked_target = logits, y[:, 1:]
+        loss = F.cross_entropy(masked_logits.reshape(-1, masked_logits.shape[-1]).float(),
+                               masked_target.reshape(-1), ignore_index=1)
+        return logits, loss, att, masked_logits, masked_target
+
+    # ---------------------------------------------------------------------------------------------
+    def _sample(self, logits, k, first_greedy_quant, temp):
+        """logits [b,1,q,l] -> ids [q,b,1] (modeling_lina.py:156-165; NB quantizers with index
+        < first_greedy_quant are the *sampled* ones, the rest greedy -- the name is inverted upstream)."""
+        lg = rearrange(logits, "b 1 q l -> q b l").float()
+        out = [topk_sampling(qq, k=k, temp=temp) if i < first_greedy_quant else topk_sampling(qq, k=1)
+               for i, qq in enumerate(lg)]
+        return torch.stack(out)
+
+    @torch.inference_mode()
+    def generate_batch(self, x: Tensor, batch_size: int = 3, prompt: Optional[Tensor] = None, device: str = "cpu",
+                       max_seqlen: int = 1000, k: int = 100, first_greedy_quant: int = 1, temp: float = 1.0,
+                       init_state=None, force_max_seqlen: bool = False, stop_check_interval: int = 1,
+                       cuda_graph: bool = False, dist_group=None):
+        """modeling_lina.py:112-192.  Returns (qs [q,b,steps], atts [b,2,steps,n], stop_tokens, cuts).
+
+        With ``dist_group`` every rank passes its LOCAL ``batch_size``; qs / stop_tokens / cuts come back
+        for the GLOBAL batch (rank-major), atts stay local."""
+        if device == "cpu":
+            device = next(self.parameters()).device            # no CPU path: follow the weights
+        x = repeat(x, "n -> b n", b=batch_size).to(device)
+        stop_token = torch.full((self.n_quant, 1, 1), 2, device=device, dtype=torch.long)
+        y_start = torch.ones(self.n_quant, batch_size, 1, device=device, dtype=torch.long)
+        x_embd = self.txt_embed(x)
+        y_embd = self.rvq_embed(y_start).sum(0)
+        p_len = -1
+        if exists(prompt):
+            if prompt.shape[1] != batch_size:
+                prompt = repeat(prompt, "q 1 n -> q b n", b=batch_size) + 3
+            prompt = self.rvq_embed(prompt.to(device)).sum(0)
+            p_len = prompt.shape[1]
+            if self.spk_encoder is not None:
+                prompt[:, 0] = self.spk_encoder(prompt)
+        x_enc = self.txt_encoder(x_embd)
+        state = init_state
+        if state is None:
+            state = self.attentive_rnn.init_state(max_seqlen=max_seqlen, batch_size=batch_size)
+
+        world = 1
+        if dist_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(dist_group)
+
+        def one_step(y_in, t):
+            y_out, att, _ = self.attentive_rnn.step(y_in, x_enc, t, state)
+            q_s = self._sample(self.logits_head(y_out), k, first_greedy_quant, temp)
+            return q_s, att, self.rvq_embed(q_s).sum(0)
+
+        graph = None
+        if cuda_graph:
+            # static buffers; the step reads y_buf and writes q_buf / att_buf / emb_buf
+            y_buf = y_embd.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (allocs, cuBLAS handles)
+                snap = [tuple(s.clone() for s in st) for st in state.states]
+                for _ in range(2):
+                    one_step(y_buf, 0)
+                for st, sn in zip(state.states, snap):
+                    for a, b in zip(st, sn):
+                        a.copy_(b)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                q_buf, att_buf, emb_buf = one_step(y_buf, 0)
+            for st, sn in zip(state.states, snap):             # capture does not execute; restore anyway
+                for a, b in zip(st, sn):
+                    a.copy_(b)
+
+        qs, atts, stop_tokens = [], [], []
+        all_stop = torch.zeros(batch_size * world, 1, device=device, dtype=torch.bool)
+        for t in range(max_seqlen):
+            if graph is not None:
+                y_buf.copy_(y_embd)
+                graph.replay()
+                q_sampled, att, emb = q_buf.clone(), att_buf.clone() if att_buf is not None else None, emb_buf.clone()
+            else:
+                q_sampled, att, emb = one_step(y_embd, t)
+            atts.append(att)
+            if dist_group is not None:
+                # the one exchange of the data path: [q, b_local, 1] int64 ids -> [q, b_global, 1]
+                gathered = torch.empty(world, *q_sampled.shape, dtype=q_sampled.dtype, device=device)
+                dist.all_gather_into_tensor(gathered, q_sampled.contiguous(), group=dist_group)
+                q_all = rearrange(gathered, "w q b n -> q (w b) n")
+            else:
+                q_all = q_sampled
+            qs.append(q_all)
+            is_stop = (q_all == stop_token).prod(dim=0)
+            stop_tokens.append(is_stop)
+            all_stop.logical_or_(is_stop.bool())
+            if not force_max_seqlen and (t + 1) % stop_check_interval == 0 and bool(all_stop.all()):
+                break
+            y_embd = prompt[:, [t]] if (exists(prompt) and t < p_len) else emb
+
+        atts = torch.cat(atts, dim=2) if exists(atts[0]) else None
+        qs = torch.stack(qs, dim=2).squeeze(-1)
+        bg = batch_size * world
+        stop_tokens.append(torch.ones(bg, 1, device=device))
+        stop_tokens = torch.stack(stop_tokens, dim=1).squeeze(-1)
+        n = stop_tokens.shape[1]
+        rvq = (undelay_rvq(qs) - self.n_special_token_in).clamp_min(0)
+        stop_idx = (stop_tokens * torch.arange(n, device=device).unsqueeze(0)).long()
+        cuts = []
+        for i in range(bg):
+            idx = torch.unique(stop_idx[i])[1]
+            a = atts[i, :, :idx] if (atts is not None and i < atts.shape[0] and world == 1) else None
+            cuts.append((rvq[:, [i], :idx - self.n_quant], a))
+        return qs, atts, stop_tokens, cuts

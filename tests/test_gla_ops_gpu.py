@@ -1,0 +1,156 @@
+"""GPU parity of the GLA operator API (fla.ops.gla.* drop-ins) against the CPU oracle and the
+golden fixtures generated from the reference.  Procedure follows FLA/tests/ops/test_gla.py:
+seeded inputs, forward + every gradient incl. dh0 (:58-102), chunk vs recurrent (:10-55, :105-145)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import gla_oracle as GO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from lina_speech_b200.fla_api import fused_recurrent_gla, fused_chunk_gla, chunk_gla
+    return {"fused_recurrent": fused_recurrent_gla, "fused_chunk": fused_chunk_gla, "chunk": chunk_gla}
+
+
+def _case(g, ci):
+    p = f"c{ci}_"
+    return {k[len(p):]: v for k, v in g.items() if k.startswith(p)}
+
+
+def _assert_close(got, ref, atol, rtol=1e-4, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = atol + rtol * ref.abs().max().item()
+    assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("op", ["fused_recurrent", "fused_chunk", "chunk"])
+def test_forward_matches_reference_goldens_fp32(golden_ops, op):
+    fn = _ops()[op]
+    for ci in range(int(golden_ops["n_cases"])):
+        c = _case(golden_ops, ci)
+        h0 = c["h0"].to(DEV) if "h0" in c else None
+        o, ht = fn(c["q"].to(DEV), c["k"].to(DEV), c["v"].to(DEV), c["gk"].to(DEV), initial_state=h0,
+                   output_final_state=True)
+        assert ht.dtype == torch.float32 and o.dtype == torch.float32
+        _assert_close(o, c["o"], 1e-4, what=f"{op} case {ci} o")          # fla: atol 1e-3 (test_gla.py:96)
+        _assert_close(ht, c["ht"], 1e-4, what=f"{op} case {ci} ht")
+
+
+@pytest.mark.parametrize("op", ["fused_recurrent", "chunk", "fused_chunk"])
+def test_backward_matches_reference_goldens_fp32(golden_ops, op):
+    fn = _ops()[op]
+    for ci in range(int(golden_ops["n_cases"])):
+        c = _case(golden_ops, ci)
+        use_dht = op != "fused_chunk"
+        leaves = [c[n].to(DEV).requires_grad_(True) for n in ("q", "k", "v", "gk")]
+        h0 = c["h0"].to(DEV).requires_grad_(True) if "h0" in c else None
+        o, ht = fn(*leaves, initial_state=h0, output_final_state=True)
+        loss = (o * c["do"].to(DEV)).sum()
+        if use_dht:
+            loss = loss + (ht * c["dht"].to(DEV)).sum()
+        loss.backward()
+        if use_dht:
+            refs = [c["dq"], c["dk"], c["dv"], c["dgk"]]
+            ref_dh0 = c.get("dh0")
+        else:   # golden grads include the dht term; recompute without it from the oracle identities
+            r = GO.recurrent_gla_bwd(c["q"], c["k"], c["v"], c["gk"], c.get("h0"), c["do"], None)
+            refs, ref_dh0 = [t.float() for t in r[:4]], None
+        for name, leaf, ref in zip(("dq", "dk", "dv", "dgk"), leaves, refs):
+            _assert_close(leaf.grad, ref, 1e-3, 1e-3, what=f"{op} case {ci} {name}")
+        if h0 is not None:
+            if op == "fused_chunk":
+                assert h0.grad is None        # initial_state is detached (chunk_fuse.py:529-530)
+            else:
+                _assert_close(h0.grad, ref_dh0, 1e-3, 1e-3, what=f"{op} case {ci} dh0")
+
+
+@pytest.mark.parametrize("T", [1, 15, 16, 17, 64, 130, 300])
+@pytest.mark.parametrize("K,V", [(32, 64), (64, 128), (256, 512), (24, 40)])
+def test_ragged_lengths_and_dims(T, K, V):
+    torch.manual_seed(T * 1000 + K)
+    B, H = 2, 2
+    q, k, v = torch.randn(B, H, T, K), torch.randn(B, H, T, K), torch.randn(B, H, T, V)
+    gk = F.logsigmoid(torch.randn(B, H, T, K)).clamp_min(-3)      # fla test distribution (test_gla.py:27)
+    h0 = torch.randn(B, H, K, V)
+    ro, rh = GO.recurrent_gla(q, k, v, gk, initial_state=h0)
+    for name, fn in _ops().items():
+        o, ht = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), initial_state=h0.to(DEV), output_final_state=True)
+        _assert_close(o, ro, 2e-4, what=f"{name} T={T} K={K} o")
+        _assert_close(ht, rh, 2e-4, what=f"{name} T={T} K={K} ht")
+
+
+def test_no_initial_state_no_final_state_and_scale():
+    torch.manual_seed(3)
+    B, H, T, K, V = 1, 3, 33, 64, 64
+    q, k, v = torch.randn(B, H, T, K), torch.randn(B, H, T, K), torch.randn(B, H, T, V)
+    gk = F.logsigmoid(torch.randn(B, H, T, K)) / 16
+    for name, fn in _ops().items():
+        o, ht = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV))
+        assert ht is None
+        _assert_close(o, GO.recurrent_gla(q, k, v, gk)[0], 1e-4, what=name)
+        o2, _ = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), scale=0.5)
+        _assert_close(o2, GO.recurrent_gla(q, k, v, gk, scale=0.5)[0], 1e-4, what=name + " scale")
+
+
+@pytest.mark.parametrize("op", ["fused_recurrent", "fused_chunk", "chunk"])
+def test_chunked_continuation_equals_one_shot(op):
+    """prefill -> decode hand-off: feeding hT back as h0 reproduces the one-shot result."""
+    fn = _ops()[op]
+    torch.manual_seed(5)
+    B, H, T, K, V = 2, 4, 200, 64, 128
+    q, k, v = (torch.randn(B, H, T, d, device=DEV) for d in (K, K, V))
+    gk = F.logsigmoid(torch.randn(B, H, T, K, device=DEV)) / 16
+    o, ht = fn(q, k, v, gk, output_final_state=True)
+    cuts, h, outs = [0, 1, 70, 134, 199, 200], None, []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        oo, h = fn(q[:, :, a:b], k[:, :, a:b], v[:, :, a:b], gk[:, :, a:b], initial_state=h, output_final_state=True)
+        outs.append(oo)
+    _assert_close(torch.cat(outs, 2), o, 1e-4, what="continuation o")
+    _assert_close(h, ht, 1e-4, what="continuation ht")
+
+
+@pytest.mark.parametrize("op", ["fused_recurrent", "fused_chunk", "chunk"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_low_precision_io(op, dtype):
+    """bf16/fp16 I/O, fp32 math: compare with the oracle run on the SAME rounded inputs; the only
+    difference left is the rounding of o to the I/O dtype (north_star: rtol 1e-3 / atol 1e-4 on top of it)."""
+    fn = _ops()[op]
+    torch.manual_seed(7)
+    B, H, T, K, V = 2, 4, 300, 64, 128
+    q, k, v = (torch.randn(B, H, T, d).to(dtype) for d in (K, K, V))
+    gk = (F.logsigmoid(torch.randn(B, H, T, K)) / 16).to(dtype)
+    h0 = torch.randn(B, H, K, V).to(dtype)
+    ro, rh = GO.recurrent_gla(q.float(), k.float(), v.float(), gk.float(), initial_state=h0.float())
+    o, ht = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), initial_state=h0.to(DEV), output_final_state=True)
+    assert o.dtype == dtype and ht.dtype == torch.float32
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert torch.allclose(o.float().cpu(), ro, rtol=eps + 1e-3, atol=1e-4 + eps * 0.05)
+    _assert_close(ht, rh, 1e-4, 1e-3, what="ht")
+
+
+def test_reset_rows_do_not_overflow():
+    """gate rows of -20 (reset_val, model/gla.py:182-184) wipe the state without producing inf/nan."""
+    torch.manual_seed(11)
+    B, H, T, K, V = 1, 2, 160, 64, 64
+    q, k, v = torch.randn(B, H, T, K), torch.randn(B, H, T, K), torch.randn(B, H, T, V)
+    gk = F.logsigmoid(torch.randn(B, H, T, K)) / 16
+    gk[:, :, 40] = -20.0
+    gk[:, :, 41:45] = -20.0
+    gk[:, :, 100] = -20.0
+    ro, rh = GO.recurrent_gla(q, k, v, gk)
+    for name, fn in _ops().items():
+        o, ht = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), output_final_state=True)
+        assert torch.isfinite(o).all() and torch.isfinite(ht).all()
+        _assert_close(o, ro, 2e-4, what=name)
+
+
+def test_cpu_tensors_fail_loudly():
+    from lina_speech_b200.fla_api import fused_recurrent_gla
+    x = torch.randn(1, 1, 4, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fused_recurrent_gla(x, x, x, x)

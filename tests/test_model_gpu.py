@@ -1,0 +1,97 @@
+"""GPU parity at layer and model level against the reference's golden fixtures (tests/golden)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(got, ref, atol, rtol=1e-4, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = atol + rtol * ref.abs().max().item()
+    assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("mode", ["fused_chunk", "chunk", "fused_recurrent"])
+@pytest.mark.parametrize("sc", [False, True])
+def test_layer_cfg1(golden_layer, mode, sc):
+    """BASELINE config 1: GatedLinearAttention d256 h4 T128 B1 vs the CPU torch reference (fla off)."""
+    from lina_speech_b200.model import GatedLinearAttention
+    from lina_speech_b200.fla_api import Cache
+    g, p = golden_layer, ("sc_" if sc else "nosc_")
+    layer = GatedLinearAttention(mode=mode, hidden_size=256, num_heads=4, use_short_conv=sc, layer_idx=0).eval()
+    layer.load_state_dict({k[len(p) + 2:]: v for k, v in g.items() if k.startswith(p + "w.")})
+    layer = layer.to(DEV)
+    x = g[p + "x"].to(DEV)
+    with torch.no_grad():
+        _close(layer(x), g[p + "y"], 2e-5, what="one shot")
+        cache = Cache()
+        cache.update(layer.init_state(1), 0, offset=0)
+        _close(layer(x[:, :100], past_key_values=cache, use_cache=True), g[p + "y_pre"], 2e-5, what="prefill")
+    with torch.inference_mode():
+        ys = torch.cat([layer(x[:, t:t + 1], past_key_values=cache, use_cache=True) for t in range(100, 128)], 1)
+    _close(ys, g[p + "y_steps"], 2e-5, what="steps")
+    for i, s in enumerate(cache.states[0]):
+        _close(s, g[p + f"state{i}"], 1e-4, what=f"state{i}")
+
+
+def _tiny(golden_model):
+    import lina_speech_b200.model as m
+    rnn = m.AttentiveGLA(64, 2, 2, blind=True, use_short_conv=True, pos_type="convolutional")
+    lm = m.LinaModel(rnn, 64, 1, 64, 3, 3, 32, txt_encoder=m.TextEncoder(64, 2, n_layers=1, dropout=0.0, rotary=False))
+    lm.load_state_dict({k[2:]: v for k, v in golden_model.items() if k.startswith("w.")})
+    return lm.to(DEV).eval()
+
+
+def test_tiny_model_forward(golden_model):
+    g, lm = golden_model, _tiny(golden_model)
+    with torch.no_grad():
+        logits, loss, att, _, _ = lm(g["x"].to(DEV), g["y"].to(DEV), g["enc_mask"].to(DEV), g["ca_mask"].to(DEV),
+                                     logits_mask=g["y_mask"].to(DEV))
+    _close(logits, g["logits"], 2e-4, what="logits")
+    _close(loss, g["loss"], 1e-4, what="loss")
+    _close(att, g["att"], 1e-4, what="att")
+
+
+def test_tiny_model_forward_with_initial_state_and_its_gradient(golden_model):
+    """initial-state tuning entry point (initial_state.py:114-128): forward in train mode + fused_recurrent
+    with a rank-1 state; loss matches the reference and the state factors receive gradients (dh0 path)."""
+    g, lm = golden_model, _tiny(golden_model)
+    lm.attentive_rnn.to_mode("fused_recurrent")
+    lm.train()
+    params = [(torch.nn.Parameter(g[f"tune_k{i}"].to(DEV)), torch.nn.Parameter(g[f"tune_v{i}"].to(DEV))) for i in range(4)]
+    st = lm.attentive_rnn.get_state_from_params(params, 2, scale=0.02)
+    logits, loss, _, _, _ = lm(g["x"].to(DEV), g["y"].to(DEV), g["enc_mask"].to(DEV), g["ca_mask"].to(DEV),
+                               logits_mask=g["y_mask"].to(DEV), init_state=st)
+    _close(logits, g["logits_init_state"], 2e-4, what="logits(init_state)")
+    _close(loss, g["loss_init_state"], 1e-4, what="loss(init_state)")
+    loss.backward()
+    for kp, vp in params:
+        assert kp.grad is not None and vp.grad is not None and torch.isfinite(kp.grad).all()
+        assert kp.grad.abs().max() > 0
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_tiny_model_greedy_generation_bit_exact(golden_model, graph):
+    g, lm = golden_model, _tiny(golden_model)
+    qs, atts, stop_tokens, cuts = lm.generate_batch(g["xt"].to(DEV), batch_size=3, prompt=g["prompt"].to(DEV),
+                                                    max_seqlen=24, k=1, force_max_seqlen=True, cuda_graph=graph)
+    assert torch.equal(qs.cpu(), g["qs"]), "greedy token ids differ from the reference"
+    _close(atts, g["atts"], 1e-4, what="atts")
+    assert len(cuts) == 3
+
+
+def test_step_loop_equals_forward(golden_model):
+    """AttentiveGLA.step x T == AttentiveGLA.forward on the same tokens (cache plumbing incl. pos_net)."""
+    lm = _tiny(golden_model)
+    rnn = lm.attentive_rnn
+    torch.manual_seed(0)
+    B, T, Tx = 2, 20, 9
+    x, ctx = torch.randn(B, T, 64, device=DEV), torch.randn(B, Tx, 64, device=DEV)
+    with torch.inference_mode():
+        y, att = rnn(x, ctx)
+        cache = rnn.init_state(batch_size=B)
+        ys, atts = zip(*[rnn.step(x[:, t:t + 1], ctx, t, cache)[:2] for t in range(T)])
+    _close(torch.cat(ys, 1), y, 1e-4, what="step loop y")
+    _close(torch.cat(atts, 2), att, 1e-4, what="step loop att")

@@ -1,0 +1,115 @@
+"""GPU parity of ShortConvolution / FusedRMSNormSwishGate / the fused decode step against the oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import gla_oracle as GO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(got, ref, atol, rtol=1e-4, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = atol + rtol * ref.abs().max().item()
+    assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("B,Ln,D", [(2, 1, 8), (2, 3, 40), (3, 37, 200), (2, 128, 1024)])
+@pytest.mark.parametrize("W", [4, 2])
+def test_short_conv_prefill_and_cache(B, Ln, D, W):
+    from lina_speech_b200.fla_api import ShortConvolution
+    torch.manual_seed(B * 100 + Ln)
+    conv = ShortConvolution(D, W, activation="silu").to(DEV)
+    x = torch.randn(B, Ln, D)
+    w = conv.weight.detach().cpu()[:, 0]
+    ref_cache = torch.ones(B, D, W)
+    ref = GO.short_conv_prefill(x, w, ref_cache) if Ln > 1 else GO.short_conv_prefill(x, w)
+    cache = torch.ones(B, D, W, device=DEV)
+    y = conv(x.to(DEV), cache=cache if Ln > 1 else None)
+    _close(y, ref, 1e-5, what="conv y")
+    if Ln > 1:
+        assert torch.equal(cache.cpu(), ref_cache)
+
+
+def test_short_conv_steps_equal_prefill_and_grads():
+    from lina_speech_b200.fla_api import ShortConvolution
+    torch.manual_seed(0)
+    B, Ln, D, W = 2, 19, 96, 4
+    conv = ShortConvolution(D, W, activation="silu").to(DEV)
+    x = torch.randn(B, Ln, D, device=DEV)
+    y = conv(x)
+    cache = torch.zeros(B, D, W, device=DEV)
+    ys = torch.cat([conv(x[:, t:t + 1], cache=cache) for t in range(Ln)], 1)
+    _close(ys, y, 1e-5, what="steps vs prefill")
+    # gradients against autograd through the torch restatement
+    xr = x.detach().cpu().requires_grad_(True)
+    wr = conv.weight.detach().cpu()[:, 0].clone().requires_grad_(True)
+    dy = torch.randn(B, Ln, D)
+    yr = F.silu(F.conv1d(F.pad(xr.transpose(1, 2), (W - 1, 0)), wr.unsqueeze(1), groups=D)).transpose(1, 2)
+    (yr * dy).sum().backward()
+    xg = x.detach().clone().requires_grad_(True)
+    (conv(xg) * dy.to(DEV)).sum().backward()
+    _close(xg.grad, xr.grad, 1e-4, what="conv dx")
+    _close(conv.weight.grad[:, 0], wr.grad, 1e-3, 1e-4, what="conv dw")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N", [(5, 64), (300, 128), (1000, 512)])
+def test_rmsnorm_swishgate_fwd_bwd(dtype, M, N):
+    from lina_speech_b200.fla_api import FusedRMSNormSwishGate
+    torch.manual_seed(M + N)
+    mod = FusedRMSNormSwishGate(N, eps=1e-5).to(DEV)
+    with torch.no_grad():
+        mod.weight.uniform_(0.5, 1.5)
+    x, g, dy = (torch.randn(M, N).to(dtype) for _ in range(3))
+    xg, gg = x.to(DEV).requires_grad_(True), g.to(DEV).requires_grad_(True)
+    y = mod(xg, gg)
+    assert y.dtype == dtype
+    w = mod.weight.detach().cpu()
+    w_used = w.to(dtype).float()
+    ref = GO.rmsnorm_swish_gate(x.float(), g.float(), w_used)
+    lo = dtype != torch.float32
+    _close(y, ref, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="norm-gate y")
+    (y.float() * dy.to(DEV).float()).sum().backward()
+    rdx, rdg, rdw = GO.rmsnorm_swish_gate_bwd(x.float(), g.float(), w_used, dy.float())
+    _close(xg.grad, rdx, 3e-2 if lo else 1e-4, 2e-2 if lo else 1e-4, what="dx")
+    _close(gg.grad, rdg, 3e-2 if lo else 1e-4, 2e-2 if lo else 1e-4, what="dg")
+    _close(mod.weight.grad, rdw, 1e-3, 2e-2 if lo else 1e-4, what="dw")
+
+
+@pytest.mark.parametrize("state_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,d,H", [(3, 64, 2), (2, 256, 4), (2, 1024, 4)])
+def test_fused_step_matches_oracle_layer(state_dtype, B, d, H):
+    """GatedLinearAttention single-token path (lina_gla_step) vs the oracle's layer, 6 consecutive steps."""
+    from lina_speech_b200.model import GatedLinearAttention
+    from oracle import lina_oracle as LO
+    torch.manual_seed(d + B)
+    dtype = state_dtype            # cache dtype = parameter dtype (model/gla.py:230-239)
+    layer = GatedLinearAttention(hidden_size=d, num_heads=H, use_short_conv=True, layer_idx=0).eval()
+    with torch.no_grad():
+        layer.g_norm_swish_gate.weight.uniform_(0.5, 1.5)
+        layer.gk_proj[1].bias.normal_()
+        for p in layer.parameters():
+            p.copy_(p.to(dtype).float())                      # oracle sees the rounded weights
+    sd = {"l." + k: v.detach().clone() for k, v in layer.state_dict().items()}
+    layer = layer.to(DEV).to(dtype)
+    from lina_speech_b200.fla_api import Cache
+    cache = Cache()
+    cache.update(layer.init_state(B), 0, offset=0)
+    ost = tuple(torch.randn_like(s.float().cpu()).to(dtype).float() for s in cache.states[0])
+    for s, o in zip(cache.states[0], ost):
+        s.copy_(o.to(dtype))
+    with torch.inference_mode():
+        for t in range(6):
+            x = torch.randn(B, 1, d).to(dtype)
+            y = layer(x.to(DEV), past_key_values=cache, use_cache=True)
+            ry = LO.gla_layer(sd, "l", x.float(), H, ost)
+            if dtype == torch.bfloat16:       # the reference keeps a bf16 cache: round the oracle state the same way
+                for o in ost:
+                    o.copy_(o.to(dtype).float())
+            lo = dtype == torch.bfloat16
+            _close(y, ry, 3e-2 if lo else 2e-5, 2e-2 if lo else 1e-4, what=f"step {t} y")
+    for s, o in zip(cache.states[0], ost):
+        _close(s, o, 2e-2 if dtype == torch.bfloat16 else 1e-4, 1e-2 if dtype == torch.bfloat16 else 1e-4, what="state")
