@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: codec-tokens/sec/GPU of LinaModel d1024 l12 (13 GLA blocks) at bs32 x seq2048.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one teacher-forced pass of LinaModel.forward (the chunkwise-parallel GLA path) over one
+batch of 32 synthetic (text, codec-token) sequences of 2048 tokens -> 65 536 codec tokens per step per
+GPU.  ``value`` is timed with inputs resident in HBM; ``e2e`` is the same pass through the public API
+with HOST (pinned) token ids copied in and the loss read back inside the timed region.  The same run
+also times the autoregressive decode loop (generate_batch, CUDA-graphed step) for the RTF figure.
+
+``--impl reference`` times the reference's CPU algorithm (the oracle port in oracle/, torch fp32 on all
+host cores) on a bounded sample of the same workload.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "codec_tokens_per_sec"
+UNIT = "tokens/s"
+CFG = dict(d_model=1024, n_layer=6, heads=4, n_codebook=4096, n_txt_vocab=256, txt_layers=4, txt_heads=4,
+           batch=32, seq=2048, txt_len=128)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.max_mhz, self.reasons = None, set()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.05)
+        except Exception as e:      # noqa: BLE001  (clock sampling must never kill the bench)
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_model(device, dtype):
+    import lina_speech_b200.model as m
+    torch.manual_seed(0)
+    c = CFG
+    rnn = m.AttentiveGLA(c["d_model"], c["n_layer"], c["heads"], blind=True, use_short_conv=True,
+                         pos_type="convolutional")
+    lm = m.LinaModel(rnn, c["d_model"], 1, c["n_codebook"], 3, 3, c["n_txt_vocab"],
+                     txt_encoder=m.TextEncoder(c["d_model"], c["txt_heads"], n_layers=c["txt_layers"], dropout=0.0,
+                                               rotary=False))
+    return lm.to(device=device, dtype=dtype).eval()
+
+
+def synth_inputs(B, T, Tx, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(3, CFG["n_txt_vocab"], (B, Tx), generator=g)
+    y = torch.randint(3, CFG["n_codebook"] + 3, (B, T + 1, 1), generator=g)
+    y[:, 0] = 1
+    enc_mask = torch.ones(B, Tx, Tx, dtype=torch.bool)
+    ca_mask = torch.ones(B, T + 1, Tx, dtype=torch.bool)
+    return x, y, enc_mask, ca_mask
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(budget_s: float, repeats: int = 1):
+    """tokens/s of the reference's CPU algorithm (oracle port, torch fp32, all host cores) on a bounded
+    sample of the same workload: same architecture and weights init, B=2, T sized to the time budget."""
+    from oracle import lina_oracle as LO
+    import lina_speech_b200.model as m
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    c = CFG
+    rnn = m.AttentiveGLA(c["d_model"], c["n_layer"], c["heads"], blind=True, use_short_conv=True,
+                         pos_type="convolutional")
+    lm = m.LinaModel(rnn, c["d_model"], 1, c["n_codebook"], 3, 3, c["n_txt_vocab"],
+                     txt_encoder=m.TextEncoder(c["d_model"], c["txt_heads"], n_layers=c["txt_layers"], dropout=0.0,
+                                               rotary=False))
+    sd = {k: v.detach().float() for k, v in lm.state_dict().items()}
+    del lm, rnn
+    cfg = {"d_model": c["d_model"], "n_layer": c["n_layer"], "heads": c["heads"], "txt_heads": c["txt_heads"],
+           "pos_type": "convolutional"}
+    B = 2
+
+    def run(T):
+        x, y, em, cm = synth_inputs(B, T, c["txt_len"], 1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            LO.lina_forward(sd, cfg, x, y, em, cm)
+        return time.perf_counter() - t0
+
+    probe_T = 8
+    run(probe_T)                                   # warm-up (thread pools, allocator)
+    dt = run(probe_T)
+    rate = B * probe_T / dt
+    T = int(max(8, min(256, rate * budget_s / B)))
+    times = [run(T) for _ in range(repeats)]
+    return B * T / statistics.median(times), cores, f"oracle port, fp32, B={B} T={T} of {c['batch']}x{c['seq']}, {repeats} pass(es)"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, args.steps + args.warmup)
+    val, cores, sample = cpu_reference_rate(budget_s=max(2.0, 150.0 / n), repeats=1)
+    vals = [val]
+    for _ in range(args.steps - 1):
+        vals.append(cpu_reference_rate(budget_s=max(2.0, 150.0 / n))[0])
+    v = statistics.median(vals)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "LinaModel d1024 l12 (13 GLA blocks) teacher-forced forward, bs32 seq2048 "
+                                  "(BASELINE configs[1]); CPU arm runs a bounded sample"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch.distributed as dist
+    from lina_speech_b200 import _lib
+    from lina_speech_b200.fla_api import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    c = CFG
+    B, T, Tx = c["batch"], c["seq"], c["txt_len"]
+    dtype = torch.bfloat16
+    lm = build_model(dev, dtype)
+    x, y, em, cm = synth_inputs(B, T, Tx, seed=1000 + rank)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    xd, yd, emd, cmd = x.to(dev), y.to(dev), em.to(dev), cm.to(dev)
+    tokens_per_step = B * T
+
+    def step_resident():
+        with torch.inference_mode():
+            return lm(xd, yd, emd, cmd)[1]
+
+    def step_e2e():
+        with torch.inference_mode():
+            xx = xh.to(dev, non_blocking=True)
+            yy = yh.to(dev, non_blocking=True)
+            loss = lm(xx, yy, emd, cmd)[1]
+            return float(loss.item())                      # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    if args.profile:                       # for ncu: just W + K resident steps, nothing else
+        for _ in range(args.warmup + args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        return
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE = []
+    l0 = _lib.launches()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launches() - l0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.result()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # dominant kernel of ours: the GLA chunk-forward launch (13 per step)
+    H, K, V = c["heads"], c["d_model"] // c["heads"], 2 * c["d_model"] // c["heads"]
+    kern_ms = [a.elapsed_time(b) for (_, a, b) in prof]
+    k_ms = statistics.mean(kern_ms) if kern_ms else float("nan")
+    alg_bytes = B * H * T * (3 * K + 2 * V) * 2                      # bf16 q,k,gk + v,o per launch
+    alg_flops = B * H * T * (4 * K * V + 64 * (K + V))               # SURVEY 8(d), C = 64
+    pk = peaks()
+    uses_tc = bool(_lib.lib().lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, _lib.BF16))
+    roofline = {"kernel": "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)",
+                "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["src"],
+                "launch_ms": k_ms, "launches_timed": len(kern_ms), "share_of_step": sum(kern_ms) / ms,
+                "algorithmic_bytes": alg_bytes, "tensor_achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
+                "tensor_frac_of_sustained": alg_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
+
+    # autoregressive decode loop (generate_batch) for tokens/s per stream and RTF
+    dec_steps = 96
+    xt = x[0]
+    tm = {}
+    lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True)
+    l1 = _lib.launches()
+    lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=dec_steps, k=100, force_max_seqlen=True, cuda_graph=True,
+                      _timing=tm)
+    torch.cuda.synchronize()
+    dec_ms = tm["start"].elapsed_time(tm["end"]) / tm["steps"]
+    if world > 1:
+        t = torch.tensor([dec_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dec_ms = float(t.item())
+    n_blocks = 2 * c["n_layer"] + 1
+    state_bytes = B * n_blocks * 2 * H * K * V * 2                    # bf16 cache, read + write per step
+    decode = {"batch": B, "steps": tm["steps"], "ms_per_step": dec_ms, "tokens_per_s": world * B / (dec_ms * 1e-3),
+              "tokens_per_s_per_stream": 1.0 / (dec_ms * 1e-3), "rtf_24khz": 75.0 / (1.0 / (dec_ms * 1e-3)),
+              "state_dtype": "bf16", "state_bytes_per_step": state_bytes,
+              "state_hbm_frac": state_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "cuda_graph": True}
+
+    if rank == 0:
+        cpu_v, cores, sample = cpu_reference_rate(budget_s=20.0) if world == 1 else (None, None, None)
+        per_step = ms / args.steps
+        out = {"metric": METRIC, "value": world * tokens_per_step / (per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": per_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "LinaModel d1024 l12 (AttentiveGLA n_layer=6: 13 GLA blocks, 207M params) "
+                                      "teacher-forced forward, bs32 x seq2048 per GPU (BASELINE configs[1])",
+                          "global_batch": world * B, "seq_len": T, "text_len": Tx, "parallelism": f"dp{world}",
+                          "l2": "per-step working set (>= 64 MB per activation, 0.4 GB weights) exceeds the 126 MB L2; no flush"},
+               "e2e": {"value": world * tokens_per_step / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": xh.numel() * 8 + yh.numel() * 8, "d2h_bytes_per_step": 4},
+               "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "decode": decode}
+        if cpu_v is not None:
+            out["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="run only W+K resident steps (for ncu); prints nothing")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

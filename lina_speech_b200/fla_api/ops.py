@@ -41,8 +41,15 @@ def _prep(q, k, v, gk, h0):
     return q, k, v, gk, h0, (B, H, T, K, V)
 
 
+# bench.py sets this to a list to collect (kind, start_event, end_event) of every forward launch
+PROFILE = None
+
+
 def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
     lib = L.lib()
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(q.device))
     B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
     o = torch.empty_like(v)
     ht = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_ht else None
@@ -58,6 +65,9 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
                                     L.ptr(ws), B, H, T, K, V, L.dt(q), scale, L.stream(q))
         L.count_launches(1)
     L.check(rc, f"lina_gla_{kind}_fwd")
+    if PROFILE is not None:
+        ev1.record(torch.cuda.current_stream(q.device))
+        PROFILE.append((kind, ev0, ev1))
     return o, ht
 
 

@@ -17,6 +17,14 @@ def exists(x):
     return x is not None
 
 
+def tensor_version(t) -> int:
+    """Version counter for memo keys; inference tensors do not track one (they are immutable enough)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def scaled_dot_product_attention(query, key, value, mask=None):
     """model/crossatt.py:13-19 (eval branch: returns the attention weights too)."""
     w = query @ key.transpose(-2, -1) * (1 / math.sqrt(query.size(-1)))
@@ -79,8 +87,8 @@ class BlindCrossAttention(nn.Module):
         """ln_k(k(ctx)), ln_v(v(ctx)), pos_emb -- memoised across decode steps in eval mode."""
         key = None
         if not self.training and pos is None and not torch.is_grad_enabled():
-            key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype,
-                   self.k.weight._version, self.v.weight._version)
+            key = (ctx.data_ptr(), tensor_version(ctx), tuple(ctx.shape), ctx.dtype,
+                   tensor_version(self.k.weight), tensor_version(self.v.weight))
             if self._memo is not None and self._memo[0] == key:
                 return self._memo[1]
         v = self.ln_v(self.v(ctx)).unsqueeze(1)

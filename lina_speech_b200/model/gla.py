@@ -26,7 +26,7 @@ from ..fla_api import (Cache, FusedRMSNormSwishGate, ShortConvolution, chunk_gla
                        fused_recurrent_gla)
 from .attentive_rnn import AttentiveRNN
 from .base_blocks import MixingBlock, SwiGLU
-from .crossatt import BlindCrossAttention, CrossAttention
+from .crossatt import BlindCrossAttention, CrossAttention, tensor_version
 
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):
@@ -90,7 +90,7 @@ class GatedLinearAttention(nn.Module):
     def _cat_weight(self):
         """[q;k;v;g;gk0] projection weights stacked so a decode step needs one GEMM for them."""
         ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.g_proj.weight, self.gk_proj[0].weight)
-        key = tuple((w.data_ptr(), w._version, w.dtype) for w in ws)
+        key = tuple((w.data_ptr(), tensor_version(w), w.dtype) for w in ws)
         if self._wcat is None or self._wcat[0] != key:
             self._wcat = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
         return self._wcat[1]

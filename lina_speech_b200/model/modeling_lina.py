@@ -102,7 +102,7 @@ class LinaModel(nn.Module):
     def generate_batch(self, x: Tensor, batch_size: int = 3, prompt: Optional[Tensor] = None, device: str = "cpu",
                        max_seqlen: int = 1000, k: int = 100, first_greedy_quant: int = 1, temp: float = 1.0,
                        init_state=None, force_max_seqlen: bool = False, stop_check_interval: int = 1,
-                       cuda_graph: bool = False, dist_group=None):
+                       cuda_graph: bool = False, dist_group=None, _timing: Optional[dict] = None):
         """modeling_lina.py:112-192.  Returns (qs [q,b,steps], atts [b,2,steps,n], stop_tokens, cuts).
 
         With ``dist_group`` every rank passes its LOCAL ``batch_size``; qs / stop_tokens / cuts come back
@@ -158,6 +158,9 @@ class LinaModel(nn.Module):
                 for a, b in zip(st, sn):
                     a.copy_(b)
 
+        if _timing is not None:                                # bench hook: device time of the steady-state loop
+            _timing["start"], _timing["end"] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _timing["start"].record()
         qs, atts, stop_tokens = [], [], []
         all_stop = torch.zeros(batch_size * world, 1, device=device, dtype=torch.bool)
         for t in range(max_seqlen):
@@ -183,6 +186,9 @@ class LinaModel(nn.Module):
                 break
             y_embd = prompt[:, [t]] if (exists(prompt) and t < p_len) else emb
 
+        if _timing is not None:
+            _timing["end"].record()
+            _timing["steps"] = len(qs)
         atts = torch.cat(atts, dim=2) if exists(atts[0]) else None
         qs = torch.stack(qs, dim=2).squeeze(-1)
         bg = batch_size * world

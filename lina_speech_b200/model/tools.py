@@ -7,7 +7,7 @@ import torch
 def topk_sampling(seq, k=1, temp=1.0):
     """model/tools.py:38-44, including its quirk: the k-th largest *unscaled* logit is the
     threshold applied to the temperature-scaled logits."""
-    kth = torch.topk(seq, k, dim=-1).values[:, [-1]]
+    kth = torch.topk(seq, k, dim=-1).values[:, -1:]
     logits = seq / temp
     logits = logits.masked_fill(logits < kth, -float("inf"))
     return torch.multinomial(torch.softmax(logits, dim=-1), num_samples=1)
