@@ -149,6 +149,14 @@ size_t lina_codec_istft_workspace_bytes(int B, int L, int n_fft);
 int lina_codec_istft_head(const float *h, const float *window, float *wav, void *ws,
                           int B, int L, int n_fft, int hop, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Debug / bring-up: one-CTA tcgen05 GEMM D[128,N] = A[128,KD] * B[N,KD]^T (fp32 in, bf16 math) with the
+ * operand placements of the GLA kernel (a_mode: 0 smem K-major, 1 smem MN-major, 2 TMEM; b_mode: 0 / 1).
+ * `swap` exchanges the descriptor's leading/stride byte offsets.  Not part of the reference's API.
+ * ------------------------------------------------------------------------------------------- */
+int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
+                          int swap, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

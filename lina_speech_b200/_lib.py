@@ -43,6 +43,7 @@ PROTOTYPES = {
     "lina_codec_layernorm_t": (_i, [_p] * 4 + [_i] * 3 + [_f, _p]),
     "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
+    "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -114,11 +114,18 @@ def test_chunked_continuation_equals_one_shot(op):
     _assert_close(h, ht, 1e-4, what="continuation ht")
 
 
+def _tc(B, H, T, K, V):
+    from lina_speech_b200 import _lib as L
+    return bool(L.lib().lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, L.BF16))
+
+
 @pytest.mark.parametrize("op", ["fused_recurrent", "fused_chunk", "chunk"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_low_precision_io(op, dtype):
-    """bf16/fp16 I/O, fp32 math: compare with the oracle run on the SAME rounded inputs; the only
-    difference left is the rounding of o to the I/O dtype (north_star: rtol 1e-3 / atol 1e-4 on top of it)."""
+    """bf16/fp16 I/O.  CUDA-core kernels do fp32 math on the rounded inputs: only the rounding of o is left
+    (north_star: rtol 1e-3 / atol 1e-4 on top of it).  The bf16 chunk ops run the tcgen05 kernel, whose MMA
+    operands are rounded to bf16 exactly where the reference's are (chunk_util.py:57-60, chunk_fuse.py:72):
+    those are compared with the oracle's chunk form under the same operand rounding."""
     fn = _ops()[op]
     torch.manual_seed(7)
     B, H, T, K, V = 2, 4, 300, 64, 128
@@ -129,8 +136,62 @@ def test_low_precision_io(op, dtype):
     o, ht = fn(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), initial_state=h0.to(DEV), output_final_state=True)
     assert o.dtype == dtype and ht.dtype == torch.float32
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
-    assert torch.allclose(o.float().cpu(), ro, rtol=eps + 1e-3, atol=1e-4 + eps * 0.05)
-    _assert_close(ht, rh, 1e-4, 1e-3, what="ht")
+    if dtype == torch.bfloat16 and op != "fused_recurrent" and _tc(B, H, T, K, V):
+        eo, eh = GO.chunk_gla(q.float(), k.float(), v.float(), gk.float(), initial_state=h0.float(), chunk=64,
+                              operand_dtype=torch.bfloat16)
+        _assert_close(o, eo, 0.0, 6e-3, what="o vs bf16-operand oracle")
+        _assert_close(ht, eh, 0.0, 3e-3, what="ht vs bf16-operand oracle")
+        _assert_close(o, ro, 0.0, 3e-2, what="o vs exact recurrence")
+        _assert_close(ht, rh, 0.0, 2e-2, what="ht vs exact recurrence")
+    else:
+        assert torch.allclose(o.float().cpu(), ro, rtol=eps + 1e-3, atol=1e-4 + eps * 0.05)
+        _assert_close(ht, rh, 1e-4, 1e-3, what="ht")
+
+
+@pytest.mark.parametrize("K,V", [(64, 128), (128, 256), (256, 512)])
+@pytest.mark.parametrize("T", [32, 64, 65, 127, 300, 1024])
+@pytest.mark.parametrize("h0_dtype", [None, torch.float32, torch.bfloat16])
+def test_tensor_core_chunk_kernel(K, V, T, h0_dtype):
+    """the tcgen05 kernel itself: every supported head size, ragged T, initial state in fp32 / bf16 / absent."""
+    from lina_speech_b200.fla_api import fused_chunk_gla
+    B, H = 2, 2
+    assert _tc(B, H, T, K, V)
+    torch.manual_seed(K + T)
+    q, k, v = (torch.randn(B, H, T, d).bfloat16() for d in (K, K, V))
+    gk = (F.logsigmoid(torch.randn(B, H, T, K)) / 16).bfloat16()
+    h0 = torch.randn(B, H, K, V).to(h0_dtype) if h0_dtype is not None else None
+    h0f = h0.float() if h0 is not None else None
+    eo, eh = GO.chunk_gla(q.float(), k.float(), v.float(), gk.float(), initial_state=h0f, chunk=64,
+                          operand_dtype=torch.bfloat16)
+    ro, rh = GO.recurrent_gla(q.float(), k.float(), v.float(), gk.float(), initial_state=h0f)
+    o, ht = fused_chunk_gla(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV),
+                            initial_state=h0.to(DEV) if h0 is not None else None, output_final_state=True)
+    assert torch.isfinite(o).all() and torch.isfinite(ht).all()
+    _assert_close(o, eo, 0.0, 6e-3, what="o vs bf16-operand oracle")
+    _assert_close(ht, eh, 0.0, 3e-3, what="ht vs bf16-operand oracle")
+    _assert_close(o, ro, 0.0, 3e-2, what="o vs exact recurrence")
+    _assert_close(ht, rh, 0.0, 2e-2, what="ht vs exact recurrence")
+
+
+def test_tensor_core_chunk_continuation_and_fla_gates():
+    """state hand-off across calls on the tensor-core path, with the fla test gate distribution
+    (logsigmoid(N(0,1)).clamp_min(-3), FLA/tests/ops/test_gla.py:27) whose per-chunk decay reaches e^-60."""
+    from lina_speech_b200.fla_api import chunk_gla
+    torch.manual_seed(1)
+    B, H, T, K, V = 1, 2, 512, 128, 128
+    q, k, v = (torch.randn(B, H, T, d).bfloat16() for d in (K, K, V))
+    gk = F.logsigmoid(torch.randn(B, H, T, K)).clamp_min(-3).bfloat16()
+    ro, rh = GO.recurrent_gla(q.float(), k.float(), v.float(), gk.float())
+    qd, kd, vd, gd = (x.to(DEV) for x in (q, k, v, gk))
+    o, ht = chunk_gla(qd, kd, vd, gd, output_final_state=True)
+    assert torch.isfinite(o).all()
+    _assert_close(o, ro, 0.0, 3e-2, what="o (fla gates)")
+    _assert_close(ht, rh, 0.0, 2e-2, what="ht (fla gates)")
+    o1, h1 = chunk_gla(qd[:, :, :200], kd[:, :, :200], vd[:, :, :200], gd[:, :, :200], output_final_state=True)
+    o2, h2 = chunk_gla(qd[:, :, 200:], kd[:, :, 200:], vd[:, :, 200:], gd[:, :, 200:], initial_state=h1,
+                       output_final_state=True)
+    _assert_close(torch.cat([o1, o2], 2), ro, 0.0, 3e-2, what="o continuation")
+    _assert_close(h2, rh, 0.0, 2e-2, what="ht continuation")
 
 
 def test_reset_rows_do_not_overflow():
