@@ -22,9 +22,14 @@
 // k~ bytes serve as K-major operand of (0) and MN-major operand of (3), the same v bytes as the MN-major A of
 // (2) and (3).
 //
-// Warp roles (512 threads): WG0 gate pre-pass (cumsum, exp, q~/k~/v tiles -> smem, two stages);
-// warp 4 MMA issuer; WG2 causal mask (P: TMEM -> bf16 smem) and output epilogue (OT -> global);
-// WG3 state pass (ST *= exp(G_C), refresh SA, final state).  Synchronisation is mbarrier-only.
+// Warp roles (512 threads):
+//   warps 5,6  loaders: cp.async (16 B, zero-filled past T) of the raw q, k rows straight into the operand tile
+//              of their stage (even / odd chunks) and of gk into a side tile; warp 7 loads the v tile;
+//   WG0        gate pre-pass IN PLACE on the landed tile: cumsum over the chunk, q -> q~, k -> k~ (two stages);
+//   warp 4     MMA issuer (one thread);
+//   WG2        causal mask (P: TMEM -> bf16 smem) and output epilogue (OT -> global);
+//   WG3        state pass (ST *= exp(G_C), refresh SA, final state).
+// Synchronisation is mbarrier-only; global-load latency is hidden by the loaders running a stage ahead.
 //
 // HBM traffic per CTA = q,k,gk once + its v slice + its o slice; q,k,gk are re-read by the V/128 CTAs of
 // the same (b,h) (L2 hits).  Algorithmic bytes per token per head: (3K + 2V) * 2.
@@ -53,19 +58,24 @@ template <int K> struct Cfg {
     static constexpr int KC = K / 8;                       // 16-byte groups along K
     static constexpr uint32_t GQK = (128 + 1) * 16;        // qk tile : [KC][128 rows (q~ 0..63, k~ 64..127) (+1 pad)][8]
     static constexpr uint32_t QK_BYTES = ((KC * GQK + 127) / 128) * 128;
+    static constexpr uint32_t GG = (C + 1) * 16;           // gk tile : [KC][64 rows (+1 pad)][8]
+    static constexpr uint32_t G_BYTES = ((KC * GG + 127) / 128) * 128;
     static constexpr int NRG = 128 / KC;                   // row groups of the pre-pass
     static constexpr int RPG = C / NRG;                    // rows per group
     static constexpr uint32_t OFF_QK = 0;
-    static constexpr uint32_t OFF_V = OFF_QK + 2 * QK_BYTES;
-    static constexpr uint32_t OFF_P = OFF_V + 2 * VT_BYTES;
+    static constexpr uint32_t OFF_G = OFF_QK + 2 * QK_BYTES;
+    static constexpr uint32_t OFF_V = OFF_G + 2 * G_BYTES;
+    static constexpr uint32_t OFF_P = OFF_V + VT_BYTES;               // single v stage
     static constexpr uint32_t OFF_DVEC = OFF_P + PT_BYTES;            // [4][K] fp32
-    static constexpr uint32_t OFF_PART = OFF_DVEC + 4 * K * 4;        // [2][NRG][K] fp32
-    static constexpr uint32_t OFF_BAR = OFF_PART + 2 * NRG * K * 4;   // mbarriers
-    static constexpr uint32_t SMEM = OFF_BAR + 16 * 8 + 16;
+    static constexpr uint32_t OFF_PART = OFF_DVEC + 4 * K * 4;        // [NRG][K] fp32
+    static constexpr uint32_t OFF_BAR = OFF_PART + NRG * K * 4;       // mbarriers
+    static constexpr uint32_t SMEM = OFF_BAR + 24 * 8 + 16;
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_EMPTY,
-       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_SA_FULL, B_COUNT };
+       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_SA_FULL, B_RAW_FULL0, B_RAW_FULL1, B_G_EMPTY0, B_G_EMPTY1, B_V_FULL,
+       B_V_EMPTY, B_COUNT };
 
 // mbarrier wait that traps instead of hanging forever (a protocol bug must not wedge the GPU)
 __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
@@ -94,7 +104,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
     constexpr uint32_t GQK = cfg::GQK;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cfg::OFF_BAR);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + cfg::OFF_BAR + 16 * 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + cfg::OFF_BAR + 24 * 8);
     float *dvec = reinterpret_cast<float *>(smem + cfg::OFF_DVEC);
     float *part = reinterpret_cast<float *>(smem + cfg::OFF_PART);
 
@@ -110,6 +120,9 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
         mbar_init(&bars[B_PS_FULL], 128); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
         mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], 128);
+        mbar_init(&bars[B_RAW_FULL0], 32); mbar_init(&bars[B_RAW_FULL1], 32);
+        mbar_init(&bars[B_G_EMPTY0], 128); mbar_init(&bars[B_G_EMPTY1], 128);
+        mbar_init(&bars[B_V_FULL], 32); mbar_init(&bars[B_V_EMPTY], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -119,46 +132,30 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 4) {
-        // ====================== WG0: gate pre-pass, q~ / k~ / v tiles ======================
+        // ====================== WG0: gate pre-pass, in place on the landed q / k rows ======================
         const int p = tid;                         // 0..127
         const int c = p % KC, rg = p / KC;
+        constexpr uint32_t GG = cfg::GG;
         for (int n = 0; n < n_items; ++n) {
-            const int s = n & 1, t0 = n * C;
-            wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+            const int s = n & 1;
             uint8_t *qk_tile = smem + cfg::OFF_QK + s * cfg::QK_BYTES;
-            uint8_t *v_tile = smem + cfg::OFF_V + s * VT_BYTES;
-            float *pt = part + (size_t)(n & 1) * NRG * K;
+            const uint8_t *g_tile = smem + cfg::OFF_G + s * cfg::G_BYTES;
+            wait_bar(&bars[B_RAW_FULL0 + s], (n >> 1) & 1);
             // pass A: column sums of gk over this thread's rows
             float csum[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) csum[j] = 0.f;
-            uint4 graw[RPG];
-#pragma unroll
-            for (int i = 0; i < RPG; ++i) {
-                const int t = t0 + rg * RPG + i;
-                graw[i] = t < T ? *reinterpret_cast<const uint4 *>(gk + qbase + (size_t)t * K + c * 8) : make_uint4(0, 0, 0, 0);
-            }
 #pragma unroll
             for (int i = 0; i < RPG; ++i) {
                 float g8[8];
-                unpack8(graw[i], g8);
+                unpack8(*reinterpret_cast<const uint4 *>(g_tile + c * GG + (rg * RPG + i) * 16), g8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) csum[j] += g8[j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pt[rg * K + c * 8 + j] = csum[j];
-            // v tile copy (independent of the gates): 1024 16-byte pieces
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = p + 128 * i;
-                const int sr = j >> 4, vc = j & 15;
-                const int t = t0 + sr;
-                const uint4 val = t < T ? *reinterpret_cast<const uint4 *>(v + vbase + (size_t)t * V + v0 + vc * 8)
-                                        : make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4 *>(v_tile + vc * GV + sr * 16) = val;
-            }
+            for (int j = 0; j < 8; ++j) part[rg * K + c * 8 + j] = csum[j];
             named_sync(1, 128);
-            // pass B: prefix of earlier row groups, then walk the rows
+            // prefix of the earlier row groups + chunk total
             float G[8], tot[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { G[j] = 0.f; tot[j] = 0.f; }
@@ -166,41 +163,82 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             for (int r2 = 0; r2 < NRG; ++r2) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float x = pt[r2 * K + c * 8 + j];
+                    const float x = part[r2 * K + c * 8 + j];
                     tot[j] += x;
                     if (r2 < rg) G[j] += x;
                 }
             }
+            named_sync(1, 128);                    // `part` may be rewritten by the next item from here on
             if (rg == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dvec[(n & 3) * K + c * 8 + j] = __expf(tot[j]);
             }
-#pragma unroll
+            // pass B: walk the rows; rows past T were zero-filled by the loaders (gk = 0, q = k = 0)
+#pragma unroll 4
             for (int i = 0; i < RPG; ++i) {
-                const int r = rg * RPG + i, t = t0 + r;
-                uint4 qo = make_uint4(0, 0, 0, 0), ko = make_uint4(0, 0, 0, 0);
-                if (t < T) {
-                    const uint4 qraw = *reinterpret_cast<const uint4 *>(q + qbase + (size_t)t * K + c * 8);
-                    const uint4 kraw = *reinterpret_cast<const uint4 *>(k + qbase + (size_t)t * K + c * 8);
-                    float g8[8], q8[8], k8[8];
-                    unpack8(graw[i], g8); unpack8(qraw, q8); unpack8(kraw, k8);
-                    uint32_t qp[4], kp[4];
+                const int r = rg * RPG + i;
+                uint4 *qp4 = reinterpret_cast<uint4 *>(qk_tile + c * GQK + r * 16);
+                uint4 *kp4 = reinterpret_cast<uint4 *>(qk_tile + c * GQK + (64 + r) * 16);
+                float g8[8], q8[8], k8[8];
+                unpack8(*reinterpret_cast<const uint4 *>(g_tile + c * GG + r * 16), g8);
+                unpack8(*qp4, q8);
+                unpack8(*kp4, k8);
+                uint32_t qp[4], kp[4];
 #pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
-                        G[j] += g8[j]; G[j + 1] += g8[j + 1];
-                        const float e0 = __expf(G[j]), e1 = __expf(G[j + 1]);
-                        const float i0 = __expf(-G[j]), i1 = __expf(-G[j + 1]);
-                        qp[j >> 1] = pack_bf16(q8[j] * e0 * scale, q8[j + 1] * e1 * scale);
-                        kp[j >> 1] = pack_bf16(k8[j] * i0, k8[j + 1] * i1);
-                    }
-                    qo = make_uint4(qp[0], qp[1], qp[2], qp[3]);
-                    ko = make_uint4(kp[0], kp[1], kp[2], kp[3]);
+                for (int j = 0; j < 8; j += 2) {
+                    G[j] += g8[j]; G[j + 1] += g8[j + 1];
+                    const float e0 = __expf(G[j]), e1 = __expf(G[j + 1]);
+                    const float i0 = __expf(-G[j]), i1 = __expf(-G[j + 1]);
+                    qp[j >> 1] = pack_bf16(q8[j] * e0 * scale, q8[j + 1] * e1 * scale);
+                    kp[j >> 1] = pack_bf16(k8[j] * i0, k8[j + 1] * i1);
                 }
-                *reinterpret_cast<uint4 *>(qk_tile + c * GQK + r * 16) = qo;
-                *reinterpret_cast<uint4 *>(qk_tile + c * GQK + (64 + r) * 16) = ko;
+                *qp4 = make_uint4(qp[0], qp[1], qp[2], qp[3]);
+                *kp4 = make_uint4(kp[0], kp[1], kp[2], kp[3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_QK_FULL0 + s]);
+            mbar_arrive(&bars[B_G_EMPTY0 + s]);
+        }
+    } else if (warp == 5 || warp == 6) {
+        // ====================== loaders: raw q, k -> operand tile of the stage, gk -> side tile ======================
+        const int s = warp - 5;                    // warp 5: even items (stage 0), warp 6: odd items (stage 1)
+        constexpr uint32_t GG = cfg::GG;
+        const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
+        const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
+        for (int n = s; n < n_items; n += 2) {
+            const int t0 = n * C;
+            wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+            wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+            for (int cc = lane; cc < KC; cc += 32) {
+#pragma unroll 8
+                for (int r = 0; r < C; ++r) {
+                    const int t = t0 + r;
+                    const uint32_t nb = t < T ? 16u : 0u;
+                    const size_t off = qbase + (size_t)(t < T ? t : 0) * K + cc * 8;
+                    cp_async16(qk_tile + cc * GQK + r * 16, q + off, nb);
+                    cp_async16(qk_tile + cc * GQK + (64 + r) * 16, k + off, nb);
+                    cp_async16(g_tile + cc * GG + r * 16, gk + off, nb);
+                }
+            }
+            cp_async_wait_all();
+            mbar_arrive(&bars[B_RAW_FULL0 + s]);
+        }
+    } else if (warp == 7) {
+        // ====================== loader: v tile (single stage) ======================
+        const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
+        for (int n = 0; n < n_items; ++n) {
+            const int t0 = n * C;
+            wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int j = lane + 32 * i;
+                const int sr = j >> 4, vc = j & 15;
+                const int t = t0 + sr;
+                cp_async16(v_tile + vc * GV + sr * 16, v + vbase + (size_t)(t < T ? t : 0) * V + v0 + vc * 8, t < T ? 16u : 0u);
+            }
+            cp_async_wait_all();
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[B_V_FULL]);
         }
     } else if (warp == 4) {
         // ====================== MMA issuer (one thread) ======================
@@ -212,7 +250,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1;
                 const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
-                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V + s * VT_BYTES);
+                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
                 wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
@@ -234,6 +272,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                     mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, bd, id_p, ks > 0);
                 }
                 wait_bar(&bars[B_PS_FULL], n & 1);
+                wait_bar(&bars[B_V_FULL], n & 1);
                 tc_fence_after();
                 // (2) OT += v^T P^T
 #pragma unroll
@@ -253,6 +292,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 }
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
+                mma_commit(&bars[B_V_EMPTY]);
             }
         }
         __syncwarp();
