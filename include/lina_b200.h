@@ -156,6 +156,14 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * ------------------------------------------------------------------------------------------- */
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);
+/* Same with 128-byte-swizzled operands (a_mode / b_mode: 0 K-major, 1 MN-major); use_tma != 0 loads A from
+ * A_bf16 [128,KD] through a 2-D tensor map with CU_TENSOR_MAP_SWIZZLE_128B instead of writing it by hand. */
+int lina_debug_umma_probe_sw128(const float *A, const float *B, float *D, const void *A_bf16, int N, int KD,
+                                int a_mode, int b_mode, int use_tma, void *stream);
+/* The tcgen05 GLA kernel (K = 256, bf16) with a clock64 timeline of CTA (0,0) written to
+ * trace[6 roles][64 items][4 events] (int64) -- profiles/trace_gla_chunk.py prints it. */
+int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
+                               int H, int T, int K, int V, float scale, long long *trace, void *stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,8 @@ PROTOTYPES = {
     "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
     "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
+    "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
+    "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

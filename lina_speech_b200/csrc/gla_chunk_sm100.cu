@@ -22,13 +22,13 @@
 // k~ bytes serve as K-major operand of (0) and MN-major operand of (3), the same v bytes as the MN-major A of
 // (2) and (3).
 //
-// Warp roles (512 threads):
+// Warp roles (576 threads):
 //   warps 5,6  loaders: cp.async (16 B, zero-filled past T) of the raw q, k rows straight into the operand tile
 //              of their stage (even / odd chunks) and of gk into a side tile; warp 7 loads the v tile;
 //   WG0        gate pre-pass IN PLACE on the landed tile: cumsum over the chunk, q -> q~, k -> k~ (two stages);
 //   warp 4     MMA issuer (one thread);
-//   WG2        causal mask (P: TMEM -> bf16 smem) and output epilogue (OT -> global);
-//   WG3        state pass (ST *= exp(G_C), refresh SA, final state).
+//   warps 8-11 output epilogue (OT: TMEM -> global);   warps 16,17 causal mask (P: TMEM -> bf16 smem);
+//   warps 12-15 state pass (ST *= exp(G_C), refresh SA, final state).
 // Synchronisation is mbarrier-only; global-load latency is hidden by the loaders running a stage ahead.
 //
 // HBM traffic per CTA = q,k,gk once + its v slice + its o slice; q,k,gk are re-read by the V/128 CTAs of
@@ -46,7 +46,7 @@ namespace {
 
 constexpr int C = 64;            // chunk length (tokens)
 constexpr int BV = 128;          // V slice per CTA
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = 576;      // 18 warps, see the role table below
 constexpr uint32_t GV = (C + 1) * 16;     // v tile   : [BV/8][64 rows s (+1 pad)][8]
 constexpr uint32_t GP = C * 16;           // P tile   : [C/8][64 rows t][8]
 constexpr uint32_t VT_BYTES = (BV / 8) * GV;
@@ -86,6 +86,11 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// bring-up timeline: role r, item n, event e -> clock64 of CTA (0,0)   (trace == nullptr in production)
+constexpr int TR_EV = 4, TR_MAXN = 64;
+#define TRACE(role, n, ev) do { if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (n) < TR_MAXN) \
+    trace[((role) * TR_MAXN + (n)) * TR_EV + (ev)] = clock64(); } while (0)
+
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
@@ -98,7 +103,8 @@ template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, const bf16 *__restrict__ v,
                            const bf16 *__restrict__ gk, const void *__restrict__ h0, int h0_dtype,
-                           bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, float scale) {
+                           bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, float scale,
+                           long long *__restrict__ trace) {
     using cfg = Cfg<K>;
     constexpr int KC = cfg::KC, NRG = cfg::NRG, RPG = cfg::RPG;
     constexpr uint32_t GQK = cfg::GQK;
@@ -116,8 +122,8 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
     if (tid == 0) {
         mbar_init(&bars[B_QK_FULL0], 128); mbar_init(&bars[B_QK_FULL1], 128);
         mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1);
-        mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 128);
-        mbar_init(&bars[B_PS_FULL], 128); mbar_init(&bars[B_PS_EMPTY], 1);
+        mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
+        mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
         mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], 128);
         mbar_init(&bars[B_RAW_FULL0], 32); mbar_init(&bars[B_RAW_FULL1], 32);
@@ -141,6 +147,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             uint8_t *qk_tile = smem + cfg::OFF_QK + s * cfg::QK_BYTES;
             const uint8_t *g_tile = smem + cfg::OFF_G + s * cfg::G_BYTES;
             wait_bar(&bars[B_RAW_FULL0 + s], (n >> 1) & 1);
+            if (p == 0) TRACE(0, n, 0);
             // pass A: column sums of gk over this thread's rows
             float csum[8];
 #pragma unroll
@@ -173,6 +180,9 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dvec[(n & 3) * K + c * 8 + j] = __expf(tot[j]);
             }
+            // from here on G is kept in log2 units so every exponential is a single ex2
+#pragma unroll
+            for (int j = 0; j < 8; ++j) G[j] *= 1.44269504088896340736f;
             // pass B: walk the rows; rows past T were zero-filled by the loaders (gk = 0, q = k = 0)
 #pragma unroll 4
             for (int i = 0; i < RPG; ++i) {
@@ -186,10 +196,11 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 uint32_t qp[4], kp[4];
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
-                    G[j] += g8[j]; G[j + 1] += g8[j + 1];
-                    const float e0 = __expf(G[j]), e1 = __expf(G[j + 1]);
-                    const float i0 = __expf(-G[j]), i1 = __expf(-G[j + 1]);
-                    qp[j >> 1] = pack_bf16(q8[j] * e0 * scale, q8[j + 1] * e1 * scale);
+                    G[j] = fmaf(g8[j], 1.44269504088896340736f, G[j]);
+                    G[j + 1] = fmaf(g8[j + 1], 1.44269504088896340736f, G[j + 1]);
+                    const float e0 = ex2_approx(G[j]) * scale, e1 = ex2_approx(G[j + 1]) * scale;
+                    const float i0 = ex2_approx(-G[j]), i1 = ex2_approx(-G[j + 1]);
+                    qp[j >> 1] = pack_bf16(q8[j] * e0, q8[j + 1] * e1);
                     kp[j >> 1] = pack_bf16(k8[j] * i0, k8[j + 1] * i1);
                 }
                 *qp4 = make_uint4(qp[0], qp[1], qp[2], qp[3]);
@@ -198,6 +209,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_QK_FULL0 + s]);
             mbar_arrive(&bars[B_G_EMPTY0 + s]);
+            if (p == 0) TRACE(0, n, 1);
         }
     } else if (warp == 5 || warp == 6) {
         // ====================== loaders: raw q, k -> operand tile of the stage, gk -> side tile ======================
@@ -209,6 +221,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             const int t0 = n * C;
             wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
             wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+            if (lane == 0) TRACE(1, n, 0);
             for (int cc = lane; cc < KC; cc += 32) {
 #pragma unroll 8
                 for (int r = 0; r < C; ++r) {
@@ -220,8 +233,10 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                     cp_async16(g_tile + cc * GG + r * 16, gk + off, nb);
                 }
             }
+            if (lane == 0) TRACE(1, n, 1);
             cp_async_wait_all();
             mbar_arrive(&bars[B_RAW_FULL0 + s]);
+            if (lane == 0) TRACE(1, n, 2);
         }
     } else if (warp == 7) {
         // ====================== loader: v tile (single stage) ======================
@@ -254,6 +269,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
+                TRACE(2, n, 0);
                 // (0) P = [q~;k~] k~^T
 #pragma unroll 4
                 for (int ks = 0; ks < K / 16; ++ks) {
@@ -265,6 +281,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 wait_bar(&bars[B_SA_FULL], n & 1);
                 wait_bar(&bars[B_O_EMPTY], (n & 1) ^ 1);
                 tc_fence_after();
+                TRACE(2, n, 1);
                 // (1) OT = SA q~^T   (A from TMEM)
 #pragma unroll 4
                 for (int ks = 0; ks < K / 16; ++ks) {
@@ -274,6 +291,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 wait_bar(&bars[B_PS_FULL], n & 1);
                 wait_bar(&bars[B_V_FULL], n & 1);
                 tc_fence_after();
+                TRACE(2, n, 2);
                 // (2) OT += v^T P^T
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks) {
@@ -293,47 +311,52 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY]);
+                TRACE(2, n, 3);
             }
         }
         __syncwarp();
-    } else if (warp >= 8 && warp < 12) {
-        // ====================== WG2: causal mask of P, output epilogue ======================
-        const int qd = warp - 8, r = qd * 32 + lane;              // TMEM lane of this thread
+    } else if (warp >= 16) {
+        // ====================== warps 16,17: causal mask of P (rows t = TMEM lanes 0..63) ======================
+        const int qd = warp - 16, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         uint8_t *p_tile = smem + cfg::OFF_P;
         for (int n = 0; n < n_items; ++n) {
-            const int t0 = n * C;
             wait_bar(&bars[B_P_FULL], n & 1);
             tc_fence_after();
+            if (r == 0) TRACE(3, n, 0);
             uint32_t pr[2][32];
-            if (qd < 2) {
-                tmem_ld32(tmem + lane_addr + COL_P, pr[0]);
-                tmem_ld32(tmem + lane_addr + COL_P + 32, pr[1]);
-                tmem_ld_wait();
-            }
+            tmem_ld32(tmem + lane_addr + COL_P, pr[0]);
+            tmem_ld32(tmem + lane_addr + COL_P + 32, pr[1]);
+            tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_P_TEMPTY]);
             wait_bar(&bars[B_PS_EMPTY], (n & 1) ^ 1);
-            if (qd < 2) {
-                // row t = r ; keep s <= t ; bf16 ; P tile [s/8][t][8]
+            // row t = r ; keep s <= t ; bf16 ; P tile [s/8][t][8]
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    uint32_t w[4];
+            for (int g = 0; g < 8; ++g) {
+                uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int s0 = g * 8 + 2 * j;
-                        const float a = s0 <= r ? __uint_as_float(pr[s0 >> 5][s0 & 31]) : 0.f;
-                        const float b = s0 + 1 <= r ? __uint_as_float(pr[(s0 + 1) >> 5][(s0 + 1) & 31]) : 0.f;
-                        w[j] = pack_bf16(a, b);
-                    }
-                    *reinterpret_cast<uint4 *>(p_tile + g * GP + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int j = 0; j < 4; ++j) {
+                    const int s0 = g * 8 + 2 * j;
+                    const float a = s0 <= r ? __uint_as_float(pr[s0 >> 5][s0 & 31]) : 0.f;
+                    const float b = s0 + 1 <= r ? __uint_as_float(pr[(s0 + 1) >> 5][(s0 + 1) & 31]) : 0.f;
+                    w[j] = pack_bf16(a, b);
                 }
+                *reinterpret_cast<uint4 *>(p_tile + g * GP + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_PS_FULL]);
-            // ---- epilogue: OT[lane = v][col = t] -> o[t][v0 + lane]
+            if (r == 0) TRACE(3, n, 1);
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ====================== warps 8-11: output epilogue  OT[lane = v][col = t] -> o[t][v0 + lane] ======================
+        const int qd = warp - 8, r = qd * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        for (int n = 0; n < n_items; ++n) {
+            const int t0 = n * C;
             wait_bar(&bars[B_O_FULL], n & 1);
             tc_fence_after();
+            if (r == 0) TRACE(4, n, 0);
             uint32_t orr[2][32];
             tmem_ld32(tmem + lane_addr + COL_OT, orr[0]);
             tmem_ld32(tmem + lane_addr + COL_OT + 32, orr[1]);
@@ -342,12 +365,18 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             mbar_arrive(&bars[B_O_EMPTY]);
             bf16 *ob = o + vbase + (size_t)t0 * V + v0 + r;
             const int nrow = min(C, T - t0);
+            if (nrow == C) {
 #pragma unroll
-            for (int t = 0; t < C; ++t) {
-                if (t < nrow) ob[(size_t)t * V] = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31]));
+                for (int t = 0; t < C; ++t) { *ob = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31])); ob += V; }
+            } else {
+#pragma unroll
+                for (int t = 0; t < C; ++t) {
+                    if (t < nrow) ob[(size_t)t * V] = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31]));
+                }
             }
+            if (r == 0) TRACE(4, n, 1);
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && warp < 16) {
         // ====================== WG3: state pass ======================
         const int qd = warp - 12, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
@@ -374,6 +403,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);         // dvec of this item is published with it
             wait_bar(&bars[B_ST_FULL], n & 1);
             tc_fence_after();
+            if (r == 0) TRACE(5, n, 0);
             const float *dv = dvec + (n & 3) * K;
             const bool last = n == n_items - 1;
 #pragma unroll 1
@@ -402,6 +432,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_SA_FULL]);
+            if (r == 0) TRACE(5, n, 1);
         }
     }
     tc_fence_before();
@@ -411,7 +442,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
 
 template <int K>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
-           float *ht, int B, int H, int T, int V, float scale, cudaStream_t st) {
+           float *ht, int B, int H, int T, int V, float scale, cudaStream_t st, long long *trace = nullptr) {
     using cfg = Cfg<K>;
     static thread_local bool configured = false;
     if (!configured) {
@@ -421,7 +452,7 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
     }
     dim3 grid(V / BV, B * H);
     gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(
-        (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)gk, h0, h0_dtype, (bf16 *)o, ht, T, V, scale);
+        (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)gk, h0, h0_dtype, (bf16 *)o, ht, T, V, scale, trace);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
 }
@@ -454,4 +485,11 @@ extern "C" int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, c
     if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
     if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
     return launch<256>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
+}
+
+// bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]
+extern "C" int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
+                                          int H, int T, int K, int V, float scale, long long *trace, void *stream) {
+    LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16) && K == 256, LINA_ERR_UNSUPPORTED, "trace: K=256 bf16 only");
+    return launch<256>(q, k, v, gk, nullptr, 0, o, nullptr, B, H, T, V, scale, (cudaStream_t)stream, trace);
 }

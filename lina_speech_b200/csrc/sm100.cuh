@@ -127,10 +127,48 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+}  // namespace sm100
+
+// ================================ 128-byte-swizzled operands + TMA ================================
+// A [rows][64] bf16 block (128 B per row, 1024-byte aligned) stores element (r, c) at
+//     r*128 + (((c/8) ^ (r%8)) * 16) + (c%8)*2          (CU_TENSOR_MAP_SWIZZLE_128B / UMMA SWIZZLE_128B)
+// read K-major  (rows = M/N, 64 cols = K): SBO = 1024 (next 8 rows), LBO unused, +32 B per K=16 step;
+// read MN-major (rows = K, 64 cols = M/N): SBO = 1024 (next 8 k),   LBO = stride of the next 64-wide MN block,
+//                                          +2048 B per K=16 step.
+namespace sm100 {
+
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) { return (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA tile loads (one thread); coordinates innermost first; completion = complete_tx on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
 }  // namespace sm100

@@ -101,3 +101,98 @@ extern "C" int lina_debug_umma_probe(const float *A, const float *B, float *D, i
     LINA_LAUNCH_OK("umma_probe_kernel");
     return LINA_OK;
 }
+
+// ---- second probe: 128-byte-swizzled operands (K-major / MN-major) and a TMA-loaded A ----------------------
+#include "tma.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128)
+umma_probe_sw128_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ D, int N, int KD,
+                        int a_mode, int b_mode, int use_tma, const __grid_constant__ CUtensorMap tmapA) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar, tbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *a_tile = smem;                    // K-major: KD/64 blocks of [128 rows][128 B]; MN-major: 2 blocks of [KD rows][128 B]
+    uint8_t *b_tile = smem + 64 * 1024;        // K-major: KD/64 blocks of [N rows][128 B];   MN-major: N/64 blocks of [KD rows][128 B]
+    const uint32_t a_blk = a_mode == 0 ? 128 * 128 : KD * 128;
+    const uint32_t b_blk = b_mode == 0 ? N * 128 : KD * 128;
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&tbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (use_tma && a_mode == 0) {
+        if (tid == 0) {
+            mbar_expect_tx(&tbar, 128 * KD * 2);
+            for (int kb = 0; kb < KD / 64; ++kb) tma_load_2d(smem_u32(a_tile + kb * a_blk), &tmapA, kb * 64, 0, &tbar);
+        }
+        mbar_wait(&tbar, 0);
+    } else {
+        for (int i = tid; i < 128 * KD; i += 128) {
+            const int m = i / KD, k = i % KD;
+            const bf16 v = __float2bfloat16_rn(A[i]);
+            if (a_mode == 0) *reinterpret_cast<bf16 *>(a_tile + (k / 64) * a_blk + sw128_off(m, (k % 64) / 8) + (k % 8) * 2) = v;
+            else *reinterpret_cast<bf16 *>(a_tile + (m / 64) * a_blk + sw128_off(k, (m % 64) / 8) + (m % 8) * 2) = v;
+        }
+    }
+    for (int i = tid; i < N * KD; i += 128) {
+        const int n = i / KD, k = i % KD;
+        const bf16 v = __float2bfloat16_rn(Bm[i]);
+        if (b_mode == 0) *reinterpret_cast<bf16 *>(b_tile + (k / 64) * b_blk + sw128_off(n, (k % 64) / 8) + (k % 8) * 2) = v;
+        else *reinterpret_cast<bf16 *>(b_tile + (n / 64) * b_blk + sw128_off(k, (n % 64) / 8) + (n % 8) * 2) = v;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = idesc_bf16(128, N, a_mode == 1, b_mode == 1);
+        for (int ks = 0; ks < KD / 16; ++ks) {
+            uint64_t ad, bd;
+            if (a_mode == 0) ad = smem_desc_sw128(smem_u32(a_tile) + (ks / 4) * a_blk + (ks % 4) * 32, 0, 1024);
+            else ad = smem_desc_sw128(smem_u32(a_tile) + ks * 2048, a_blk, 1024);
+            if (b_mode == 0) bd = smem_desc_sw128(smem_u32(b_tile) + (ks / 4) * b_blk + (ks % 4) * 32, 0, 1024);
+            else bd = smem_desc_sw128(smem_u32(b_tile) + ks * 2048, b_blk, 1024);
+            mma_ss(tbase, ad, bd, idesc, ks > 0);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+}  // namespace
+
+// A_bf16 [128, KD] row-major (only read when use_tma != 0, through a 2-D tensor map with 128-byte swizzle)
+extern "C" int lina_debug_umma_probe_sw128(const float *A, const float *B, float *D, const void *A_bf16, int N, int KD,
+                                           int a_mode, int b_mode, int use_tma, void *stream) {
+    LINA_REQUIRE(A && B && D, LINA_ERR_BAD_ARG, "umma_probe_sw128: null pointer");
+    LINA_REQUIRE(N % 64 == 0 && N >= 64 && N <= 256 && KD % 64 == 0 && KD >= 64 && KD <= 128, LINA_ERR_BAD_ARG,
+                 "umma_probe_sw128: need N in [64,256] %% 64, KD in {64,128}");
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (use_tma) {
+        LINA_REQUIRE(A_bf16 != nullptr && a_mode == 0, LINA_ERR_BAD_ARG, "umma_probe_sw128: TMA needs A_bf16 and a_mode 0");
+        const uint64_t dims[2] = {(uint64_t)KD, 128}, strides[2] = {2, (uint64_t)KD * 2};
+        const uint32_t box[2] = {64, 128};
+        int rc = lina_make_tmap_bf16(&tm, A_bf16, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    const int smem = 140 * 1024;
+    LINA_CUDA_OK(cudaFuncSetAttribute(umma_probe_sw128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_probe_sw128_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, KD, a_mode, b_mode, use_tma, tm);
+    LINA_LAUNCH_OK("umma_probe_sw128_kernel");
+    return LINA_OK;
+}
