@@ -18,23 +18,24 @@
 // All four MMAs of a chunk are M = 128 tcgen05.mma (kind::f16, bf16 x bf16 -> fp32), single-thread issued:
 //     (0) P  = [q~;k~] k~^T   (rows 64..127 are a by-product; M=128 costs what M=64 would)
 //     (1) OT = SA q~^T        (A from TMEM)        (2) OT += v^T P^T        (3) ST += v^T k~
-// Shared-memory operands use the SWIZZLE_NONE core-matrix layout [depth/8][row][8] (see sm100.cuh); the same
-// k~ bytes serve as K-major operand of (0) and MN-major operand of (3), the same v bytes as the MN-major A of
-// (2) and (3).
+// Shared-memory operands are 128-byte-swizzled [rows][64] blocks (TMA's CU_TENSOR_MAP_SWIZZLE_128B = UMMA
+// SWIZZLE_128B, see sm100.cuh): the raw q, k, gk, v tiles are landed by TMA directly in operand layout, q and k
+// are rescaled IN PLACE, and the same k~ bytes serve as K-major operand of (0) and MN-major operand of (3), the
+// same v bytes as the MN-major A of (2) and (3).
 //
-// Warp roles (576 threads):
-//   warps 5,6  loaders: cp.async (16 B, zero-filled past T) of the raw q, k rows straight into the operand tile
-//              of their stage (even / odd chunks) and of gk into a side tile; warp 7 loads the v tile;
-//   WG0        gate pre-pass IN PLACE on the landed tile: cumsum over the chunk, q -> q~, k -> k~ (two stages);
-//   warp 4     MMA issuer (one thread);
-//   warps 8-11 output epilogue (OT: TMEM -> global);   warps 16,17 causal mask (P: TMEM -> bf16 smem);
+// Warp roles (640 threads):
+//   warp 19     TMA loader (one thread): 3-D tensor maps (K|V, T, B*H), 64x64 boxes, rows past T zero-filled;
+//   warps 0-7   gate pre-pass IN PLACE on the landed stage: cumsum over the chunk, q -> q~, k -> k~ (two stages);
+//   warp 18     MMA issuer (one thread);
+//   warps 16,17 causal mask (P: TMEM -> bf16 smem);      warps 8-11 output epilogue (OT: TMEM -> global);
 //   warps 12-15 state pass (ST *= exp(G_C), refresh SA, final state).
-// Synchronisation is mbarrier-only; global-load latency is hidden by the loaders running a stage ahead.
+// Synchronisation is mbarrier-only; global-load latency is hidden by TMA running a stage ahead.
 //
 // HBM traffic per CTA = q,k,gk once + its v slice + its o slice; q,k,gk are re-read by the V/128 CTAs of
 // the same (b,h) (L2 hits).  Algorithmic bytes per token per head: (3K + 2V) * 2.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "tma.cuh"
 
 using namespace sm100;
 
@@ -46,31 +47,33 @@ namespace {
 
 constexpr int C = 64;            // chunk length (tokens)
 constexpr int BV = 128;          // V slice per CTA
-constexpr int NTHREADS = 576;      // 18 warps, see the role table below
-constexpr uint32_t GV = (C + 1) * 16;     // v tile   : [BV/8][64 rows s (+1 pad)][8]
-constexpr uint32_t GP = C * 16;           // P tile   : [C/8][64 rows t][8]
-constexpr uint32_t VT_BYTES = (BV / 8) * GV;
-constexpr uint32_t PT_BYTES = (C / 8) * GP;
+constexpr int NTHREADS = 640;    // 20 warps, see the role table above
+constexpr int NPREP = 256;       // warps 0-7
+constexpr uint32_t VT_BYTES = 2 * 8192;   // v tile : 2 blocks of [64 rows s][64 v] (128 B rows, 128B-swizzled)
+constexpr uint32_t PT_BYTES = 8192;       // P tile : [64 rows t][64 s]
 // TMEM columns
 constexpr uint32_t COL_ST = 0, COL_OT = 256, COL_P = 320, COL_SA = 384;
 
 template <int K> struct Cfg {
     static constexpr int KC = K / 8;                       // 16-byte groups along K
-    static constexpr uint32_t GQK = (128 + 1) * 16;        // qk tile : [KC][128 rows (q~ 0..63, k~ 64..127) (+1 pad)][8]
-    static constexpr uint32_t QK_BYTES = ((KC * GQK + 127) / 128) * 128;
-    static constexpr uint32_t GG = (C + 1) * 16;           // gk tile : [KC][64 rows (+1 pad)][8]
-    static constexpr uint32_t G_BYTES = ((KC * GG + 127) / 128) * 128;
-    static constexpr int NRG = 128 / KC;                   // row groups of the pre-pass
+    static constexpr int KB = K / 64;                      // 64-wide (128-byte) swizzle blocks along K
+    static constexpr uint32_t QK_BLK = 128 * 128;          // [128 rows: q~ 0..63, k~ 64..127][64 k]
+    static constexpr uint32_t QK_BYTES = KB * QK_BLK;
+    static constexpr uint32_t G_BLK = 64 * 128;            // [64 rows][64 k]
+    static constexpr uint32_t G_BYTES = KB * G_BLK;
+    static constexpr int NRG = NPREP / KC;                 // row groups of the pre-pass
     static constexpr int RPG = C / NRG;                    // rows per group
     static constexpr uint32_t OFF_QK = 0;
     static constexpr uint32_t OFF_G = OFF_QK + 2 * QK_BYTES;
     static constexpr uint32_t OFF_V = OFF_G + 2 * G_BYTES;
     static constexpr uint32_t OFF_P = OFF_V + VT_BYTES;               // single v stage
-    static constexpr uint32_t OFF_DVEC = OFF_P + PT_BYTES;            // [4][K] fp32
-    static constexpr uint32_t OFF_PART = OFF_DVEC + 4 * K * 4;        // [NRG][K] fp32
-    static constexpr uint32_t OFF_BAR = OFF_PART + NRG * K * 4;       // mbarriers
+    static constexpr uint32_t OFF_DVEC = OFF_P + PT_BYTES;            // [3][K] fp32
+    static constexpr uint32_t OFF_PART = OFF_DVEC + 3 * K * 4;        // [NRG-1][K] fp32
+    static constexpr uint32_t OFF_BAR = OFF_PART + (NRG - 1) * K * 4; // mbarriers
     static constexpr uint32_t SMEM = OFF_BAR + 24 * 8 + 16;
+    static constexpr uint32_t RAW_TX = 3u * K * C * 2u;               // bytes landed per stage by TMA (q, k, gk)
     static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(OFF_G % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
 enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_EMPTY,
@@ -99,16 +102,16 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
+struct TMaps { CUtensorMap q, k, g, v; };
+
 template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, const bf16 *__restrict__ v,
-                           const bf16 *__restrict__ gk, const void *__restrict__ h0, int h0_dtype,
+gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
                            bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, float scale,
                            long long *__restrict__ trace) {
     using cfg = Cfg<K>;
-    constexpr int KC = cfg::KC, NRG = cfg::NRG, RPG = cfg::RPG;
-    constexpr uint32_t GQK = cfg::GQK;
-    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cfg::OFF_BAR);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + cfg::OFF_BAR + 24 * 8);
     float *dvec = reinterpret_cast<float *>(smem + cfg::OFF_DVEC);
@@ -117,18 +120,19 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, v0 = blockIdx.x * BV;
     const int n_items = (T + C - 1) / C;
-    const size_t qbase = (size_t)bh * T * K, vbase = (size_t)bh * T * V;
+    const size_t vbase = (size_t)bh * T * V;
 
     if (tid == 0) {
-        mbar_init(&bars[B_QK_FULL0], 128); mbar_init(&bars[B_QK_FULL1], 128);
+        if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
+        mbar_init(&bars[B_QK_FULL0], NPREP); mbar_init(&bars[B_QK_FULL1], NPREP);
         mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1);
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
         mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
         mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], 128);
-        mbar_init(&bars[B_RAW_FULL0], 32); mbar_init(&bars[B_RAW_FULL1], 32);
-        mbar_init(&bars[B_G_EMPTY0], 128); mbar_init(&bars[B_G_EMPTY1], 128);
-        mbar_init(&bars[B_V_FULL], 32); mbar_init(&bars[B_V_EMPTY], 1);
+        mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1);
+        mbar_init(&bars[B_G_EMPTY0], NPREP); mbar_init(&bars[B_G_EMPTY1], NPREP);
+        mbar_init(&bars[B_V_FULL], 1); mbar_init(&bars[B_V_EMPTY], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -137,15 +141,15 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
-        // ====================== WG0: gate pre-pass, in place on the landed q / k rows ======================
-        const int p = tid;                         // 0..127
-        const int c = p % KC, rg = p / KC;
-        constexpr uint32_t GG = cfg::GG;
+    if (warp < 8) {
+        // ====================== warps 0-7: gate pre-pass, in place on the landed q / k rows ======================
+        const int p = tid;                         // 0..255
+        const int c = p % KC, rg = p / KC;         // 16-byte column group, row group
+        const uint32_t cb = (uint32_t)(c >> 3), c16 = (uint32_t)(c & 7);
         for (int n = 0; n < n_items; ++n) {
             const int s = n & 1;
-            uint8_t *qk_tile = smem + cfg::OFF_QK + s * cfg::QK_BYTES;
-            const uint8_t *g_tile = smem + cfg::OFF_G + s * cfg::G_BYTES;
+            uint8_t *qk_tile = smem + cfg::OFF_QK + s * cfg::QK_BYTES + cb * cfg::QK_BLK;
+            const uint8_t *g_tile = smem + cfg::OFF_G + s * cfg::G_BYTES + cb * cfg::G_BLK;
             wait_bar(&bars[B_RAW_FULL0 + s], (n >> 1) & 1);
             if (p == 0) TRACE(0, n, 0);
             // pass A: column sums of gk over this thread's rows
@@ -155,42 +159,43 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
 #pragma unroll
             for (int i = 0; i < RPG; ++i) {
                 float g8[8];
-                unpack8(*reinterpret_cast<const uint4 *>(g_tile + c * GG + (rg * RPG + i) * 16), g8);
+                unpack8(*reinterpret_cast<const uint4 *>(g_tile + sw128_off(rg * RPG + i, c16)), g8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) csum[j] += g8[j];
             }
+            if (rg < NRG - 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[rg * K + c * 8 + j] = csum[j];
-            named_sync(1, 128);
-            // prefix of the earlier row groups + chunk total
-            float G[8], tot[8];
+                for (int j = 0; j < 8; j += 4)
+                    *reinterpret_cast<float4 *>(part + rg * K + c * 8 + j) = make_float4(csum[j], csum[j + 1], csum[j + 2], csum[j + 3]);
+            }
+            named_sync(1, NPREP);
+            // prefix of the earlier row groups (+ chunk total in the last row group)
+            float G[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { G[j] = 0.f; tot[j] = 0.f; }
+            for (int j = 0; j < 8; ++j) G[j] = 0.f;
+            for (int r2 = 0; r2 < rg; ++r2) {
 #pragma unroll
-            for (int r2 = 0; r2 < NRG; ++r2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float x = part[r2 * K + c * 8 + j];
-                    tot[j] += x;
-                    if (r2 < rg) G[j] += x;
+                for (int j = 0; j < 8; j += 4) {
+                    const float4 x = *reinterpret_cast<const float4 *>(part + r2 * K + c * 8 + j);
+                    G[j] += x.x; G[j + 1] += x.y; G[j + 2] += x.z; G[j + 3] += x.w;
                 }
             }
-            named_sync(1, 128);                    // `part` may be rewritten by the next item from here on
-            if (rg == 0) {
+            named_sync(1, NPREP);                  // `part` may be rewritten by the next item from here on
+            if (rg == NRG - 1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dvec[(n & 3) * K + c * 8 + j] = __expf(tot[j]);
+                for (int j = 0; j < 8; ++j) dvec[(n % 3) * K + c * 8 + j] = __expf(G[j] + csum[j]);
             }
             // from here on G is kept in log2 units so every exponential is a single ex2
 #pragma unroll
             for (int j = 0; j < 8; ++j) G[j] *= 1.44269504088896340736f;
-            // pass B: walk the rows; rows past T were zero-filled by the loaders (gk = 0, q = k = 0)
-#pragma unroll 4
+            // pass B: walk the rows; rows past T were zero-filled by TMA (gk = 0, q = k = 0)
+#pragma unroll
             for (int i = 0; i < RPG; ++i) {
                 const int r = rg * RPG + i;
-                uint4 *qp4 = reinterpret_cast<uint4 *>(qk_tile + c * GQK + r * 16);
-                uint4 *kp4 = reinterpret_cast<uint4 *>(qk_tile + c * GQK + (64 + r) * 16);
+                uint4 *qp4 = reinterpret_cast<uint4 *>(qk_tile + sw128_off(r, c16));
+                uint4 *kp4 = reinterpret_cast<uint4 *>(qk_tile + sw128_off(64 + r, c16));
                 float g8[8], q8[8], k8[8];
-                unpack8(*reinterpret_cast<const uint4 *>(g_tile + c * GG + r * 16), g8);
+                unpack8(*reinterpret_cast<const uint4 *>(g_tile + sw128_off(r, c16)), g8);
                 unpack8(*qp4, q8);
                 unpack8(*kp4, k8);
                 uint32_t qp[4], kp[4];
@@ -211,61 +216,45 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             mbar_arrive(&bars[B_G_EMPTY0 + s]);
             if (p == 0) TRACE(0, n, 1);
         }
-    } else if (warp == 5 || warp == 6) {
-        // ====================== loaders: raw q, k -> operand tile of the stage, gk -> side tile ======================
-        const int s = warp - 5;                    // warp 5: even items (stage 0), warp 6: odd items (stage 1)
-        constexpr uint32_t GG = cfg::GG;
-        const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
-        const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
-        for (int n = s; n < n_items; n += 2) {
-            const int t0 = n * C;
-            wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
-            wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
-            if (lane == 0) TRACE(1, n, 0);
-            for (int cc = lane; cc < KC; cc += 32) {
-#pragma unroll 8
-                for (int r = 0; r < C; ++r) {
-                    const int t = t0 + r;
-                    const uint32_t nb = t < T ? 16u : 0u;
-                    const size_t off = qbase + (size_t)(t < T ? t : 0) * K + cc * 8;
-                    cp_async16(qk_tile + cc * GQK + r * 16, q + off, nb);
-                    cp_async16(qk_tile + cc * GQK + (64 + r) * 16, k + off, nb);
-                    cp_async16(g_tile + cc * GG + r * 16, gk + off, nb);
+    } else if (warp == 19) {
+        // ====================== TMA loader (one thread): q, k -> operand tile of the stage, gk -> side tile, v ======================
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.g); tma_prefetch_desc(&tm.v);
+            for (int n = 0; n < n_items; ++n) {
+                const int s = n & 1, t0 = n * C;
+                const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
+                const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
+                wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                TRACE(1, n, 0);
+                mbar_expect_tx(&bars[B_RAW_FULL0 + s], cfg::RAW_TX);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_3d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
+                    tma_load_3d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
+                    tma_load_3d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
                 }
+                TRACE(1, n, 1);
+                wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
+                mbar_expect_tx(&bars[B_V_FULL], VT_BYTES);
+                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
+                tma_load_3d(v_tile, &tm.v, v0, t0, bh, &bars[B_V_FULL]);
+                tma_load_3d(v_tile + 8192, &tm.v, v0 + 64, t0, bh, &bars[B_V_FULL]);
+                TRACE(1, n, 2);
             }
-            if (lane == 0) TRACE(1, n, 1);
-            cp_async_wait_all();
-            mbar_arrive(&bars[B_RAW_FULL0 + s]);
-            if (lane == 0) TRACE(1, n, 2);
         }
-    } else if (warp == 7) {
-        // ====================== loader: v tile (single stage) ======================
-        const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
-        for (int n = 0; n < n_items; ++n) {
-            const int t0 = n * C;
-            wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const int j = lane + 32 * i;
-                const int sr = j >> 4, vc = j & 15;
-                const int t = t0 + sr;
-                cp_async16(v_tile + vc * GV + sr * 16, v + vbase + (size_t)(t < T ? t : 0) * V + v0 + vc * 8, t < T ? 16u : 0u);
-            }
-            cp_async_wait_all();
-            fence_proxy_async_smem();
-            mbar_arrive(&bars[B_V_FULL]);
-        }
-    } else if (warp == 4) {
+        __syncwarp();
+    } else if (warp == 18) {
         // ====================== MMA issuer (one thread) ======================
         if (lane == 0) {
             const uint32_t id_p = idesc_bf16(128, 64, 0, 0);     // (0),(1): K-major x K-major, N = 64
             const uint32_t id_o = idesc_bf16(128, 64, 1, 0);     // (2): MN-major A (v^T), K-major B (P)
             const uint32_t id_s = idesc_bf16(128, K, 1, 1);      // (3): MN-major A (v^T), MN-major B (k~)
             const uint32_t p_tile = smem_u32(smem + cfg::OFF_P);
+            const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1;
                 const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
-                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
                 wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
@@ -273,9 +262,8 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 // (0) P = [q~;k~] k~^T
 #pragma unroll 4
                 for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t ad = smem_desc(qk_tile + ks * 2 * GQK, GQK, 128);
-                    const uint64_t bd = smem_desc(qk_tile + ks * 2 * GQK + 64 * 16, GQK, 128);
-                    mma_ss(tmem + COL_P, ad, bd, id_p, ks > 0);
+                    const uint32_t a = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
+                    mma_ss(tmem + COL_P, smem_desc_sw128(a, 0, 1024), smem_desc_sw128(a + 8192, 0, 1024), id_p, ks > 0);
                 }
                 mma_commit(&bars[B_P_FULL]);
                 wait_bar(&bars[B_SA_FULL], n & 1);
@@ -285,8 +273,8 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 // (1) OT = SA q~^T   (A from TMEM)
 #pragma unroll 4
                 for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t bd = smem_desc(qk_tile + ks * 2 * GQK, GQK, 128);
-                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, bd, id_p, ks > 0);
+                    const uint32_t b = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
+                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, smem_desc_sw128(b, 0, 1024), id_p, ks > 0);
                 }
                 wait_bar(&bars[B_PS_FULL], n & 1);
                 wait_bar(&bars[B_V_FULL], n & 1);
@@ -294,20 +282,16 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                 TRACE(2, n, 2);
                 // (2) OT += v^T P^T
 #pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks) {
-                    const uint64_t ad = smem_desc(v_tile + ks * 256, 128, GV);
-                    const uint64_t bd = smem_desc(p_tile + ks * 2 * GP, GP, 128);
-                    mma_ss(tmem + COL_OT, ad, bd, id_o, 1);
-                }
+                for (int ks = 0; ks < C / 16; ++ks)
+                    mma_ss(tmem + COL_OT, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
+                           smem_desc_sw128(p_tile + ks * 32, 0, 1024), id_o, 1);
                 mma_commit(&bars[B_O_FULL]);
                 mma_commit(&bars[B_PS_EMPTY]);
                 // (3) ST += v^T k~
 #pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks) {
-                    const uint64_t ad = smem_desc(v_tile + ks * 256, 128, GV);
-                    const uint64_t bd = smem_desc(qk_tile + 64 * 16 + ks * 256, 128, GQK);
-                    mma_ss(tmem + COL_ST, ad, bd, id_s, 1);
-                }
+                for (int ks = 0; ks < C / 16; ++ks)
+                    mma_ss(tmem + COL_ST, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
+                           smem_desc_sw128(qk_tile + 8192 + ks * 2048, cfg::QK_BLK, 1024), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY]);
@@ -315,7 +299,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             }
         }
         __syncwarp();
-    } else if (warp >= 16) {
+    } else if (warp == 16 || warp == 17) {
         // ====================== warps 16,17: causal mask of P (rows t = TMEM lanes 0..63) ======================
         const int qd = warp - 16, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
@@ -331,7 +315,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             tc_fence_before();
             mbar_arrive(&bars[B_P_TEMPTY]);
             wait_bar(&bars[B_PS_EMPTY], (n & 1) ^ 1);
-            // row t = r ; keep s <= t ; bf16 ; P tile [s/8][t][8]
+            // row t = r ; keep s <= t ; bf16 ; P tile [t][s], 128B-swizzled
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 uint32_t w[4];
@@ -342,7 +326,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
                     const float b = s0 + 1 <= r ? __uint_as_float(pr[(s0 + 1) >> 5][(s0 + 1) & 31]) : 0.f;
                     w[j] = pack_bf16(a, b);
                 }
-                *reinterpret_cast<uint4 *>(p_tile + g * GP + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(p_tile + sw128_off(r, g)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_PS_FULL]);
@@ -377,7 +361,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             if (r == 0) TRACE(4, n, 1);
         }
     } else if (warp >= 12 && warp < 16) {
-        // ====================== WG3: state pass ======================
+        // ====================== warps 12-15: state pass ======================
         const int qd = warp - 12, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         const size_t sbase = (size_t)bh * K * V + v0 + r;          // + kappa * V
@@ -404,7 +388,7 @@ gla_chunk_fwd_sm100_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ 
             wait_bar(&bars[B_ST_FULL], n & 1);
             tc_fence_after();
             if (r == 0) TRACE(5, n, 0);
-            const float *dv = dvec + (n & 3) * K;
+            const float *dv = dvec + (n % 3) * K;
             const bool last = n == n_items - 1;
 #pragma unroll 1
             for (int cb = 0; cb < K / 32; ++cb) {
@@ -450,9 +434,23 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
                                           (int)cfg::SMEM));
         configured = true;
     }
+    // 3-D views (innermost first): q,k,gk = (K, T, B*H), v = (V, T, B*H); 64 x 64 boxes, rows past T read as zero
+    TMaps tm;
+    const uint64_t BH = (uint64_t)B * H;
+    {
+        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)T, BH};
+        const uint64_t strides[3] = {2, (uint64_t)K * 2, (uint64_t)T * K * 2};
+        const uint32_t box[3] = {64, 64, 1};
+        int rc;
+        if ((rc = lina_make_tmap_bf16(&tm.q, q, 3, dims, strides, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.k, k, 3, dims, strides, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.g, gk, 3, dims, strides, box))) return rc;
+        const uint64_t vdims[3] = {(uint64_t)V, (uint64_t)T, BH};
+        const uint64_t vstrides[3] = {2, (uint64_t)V * 2, (uint64_t)T * V * 2};
+        if ((rc = lina_make_tmap_bf16(&tm.v, v, 3, vdims, vstrides, box))) return rc;
+    }
     dim3 grid(V / BV, B * H);
-    gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(
-        (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)gk, h0, h0_dtype, (bf16 *)o, ht, T, V, scale, trace);
+    gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, scale, trace);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
 }
