@@ -143,10 +143,10 @@ def main_reference(args):
     if rank != 0:
         return
     n = max(1, args.steps + args.warmup)
-    val, cores, sample = cpu_reference_rate(budget_s=max(2.0, 150.0 / n), repeats=1)
+    val, cores, sample = cpu_reference_rate(budget_s=max(1.0, args.cpu_budget / n), repeats=1)
     vals = [val]
     for _ in range(args.steps - 1):
-        vals.append(cpu_reference_rate(budget_s=max(2.0, 150.0 / n))[0])
+        vals.append(cpu_reference_rate(budget_s=max(1.0, args.cpu_budget / n))[0])
     v = statistics.median(vals)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
@@ -295,6 +295,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work for the whole --impl reference run")
     ap.add_argument("--profile", action="store_true", help="run only W+K resident steps (for ncu); prints nothing")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -67,6 +67,14 @@ size_t lina_gla_chunk_fwd_workspace_bytes(int B, int H, int T, int K, int V, int
 int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, const void *gk,
                        const void *h0, int h0_dtype, void *o, float *ht, void *ws,
                        int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
+/* Same function on the layout the projections produce: q, k, gk [B,T,H,K], v, o [B,T,H,V] (h0 / ht stay
+ * [B,H,K,V]).  Replaces the `rearrange(..., 'b l (h d) -> b h l d')` + `.contiguous()` copies in front of the
+ * op (model/gla.py:173, FLA/fla/utils.py:9-15) and the inverse rearrange after it (model/gla.py:215): TMA reads
+ * the strided view in place.  Tensor-core envelope only (see lina_gla_chunk_fwd_uses_tensor_cores), else
+ * LINA_ERR_UNSUPPORTED. */
+int lina_gla_chunk_fwd_bthd(const void *q, const void *k, const void *v, const void *gk,
+                            const void *h0, int h0_dtype, void *o, float *ht, void *ws,
+                            int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
 /* 1 if lina_gla_chunk_fwd runs the tcgen05 (sm_100a tensor-core) kernel for this problem,
  * 0 if it runs the CUDA-core recurrence kernel (small/odd shapes, fp32 inputs). */
 int lina_gla_chunk_fwd_uses_tensor_cores(int B, int H, int T, int K, int V, int dtype);
@@ -116,6 +124,15 @@ int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void
 int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, const float *rstd,
                                const void *dy, void *dx, void *dg, float *dw,
                                int M, int N, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused element-wise passes of the block around the mixer.
+ *   gate : y = logsigmoid(x) / normalizer, optionally clamped from below     (model/gla.py:174-181), n elements
+ *   swiglu: out[m, j] = silu(h[m, j]) * h[m, Hp + j], h [M, 2*Hp] -> out [M, Hp]  (model/base_blocks.py:48-50)
+ * ------------------------------------------------------------------------------------------- */
+int lina_gate_logsigmoid(const void *x, void *y, long long n, float normalizer, float clamp_min, int use_clamp,
+                         int dtype, void *stream);
+int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * WavTokenizer decode tail (fp32).  The dense convolutions / linears of the backbone stay library

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "lina_gla_recurrent_bwd": (_i, [_p] * 5 + [_i] + [_p] * 8 + [_i] * 6 + [_f, _p]),
     "lina_gla_chunk_fwd_workspace_bytes": (_sz, [_i] * 6),
     "lina_gla_chunk_fwd": (_i, [_p] * 5 + [_i, _p, _p, _p] + [_i] * 6 + [_f, _p]),
+    "lina_gla_chunk_fwd_bthd": (_i, [_p] * 5 + [_i, _p, _p, _p] + [_i] * 6 + [_f, _p]),
     "lina_gla_chunk_fwd_uses_tensor_cores": (_i, [_i] * 6),
     "lina_gla_step_workspace_bytes": (_sz, [_i] * 4),
     "lina_gla_step": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_p]),
@@ -36,6 +37,8 @@ PROTOTYPES = {
     "lina_short_conv_update": (_i, [_p, _p, _i, _p, _p] + [_i] * 5 + [_p]),
     "lina_rmsnorm_swishgate_fwd": (_i, [_p] * 5 + [_i, _i, _f, _i, _p]),
     "lina_rmsnorm_swishgate_bwd": (_i, [_p] * 8 + [_i, _i, _i, _p]),
+    "lina_gate_logsigmoid": (_i, [_p, _p, C.c_longlong, _f, _f, _i, _i, _p]),
+    "lina_swiglu_act": (_i, [_p, _p, _i, _i, _i, _p]),
     "lina_codec_codes_to_features": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_codec_groupnorm_swish": (_i, [_p] * 5 + [_i] * 4 + [_f, _i, _p]),
     "lina_codec_dwconv_adaln": (_i, [_p] * 6 + [_i] * 3 + [_f, _p]),

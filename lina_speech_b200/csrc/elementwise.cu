@@ -1,0 +1,85 @@
+// Small fused element-wise passes around the GLA mixer (HBM streaming, 16-byte vectors).
+//   lina_gate_logsigmoid : gk = logsigmoid(x) / normalizer [clamped]           (model/gla.py:174-181)
+//   lina_swiglu_act      : out[m, j] = silu(h[m, j]) * h[m, Hp + j]             (model/base_blocks.py:48-50)
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_logsigmoid_kernel(const T *__restrict__ x, T *__restrict__ y, long long n, float inv_norm, float clamp_min,
+                       int use_clamp) {
+    constexpr int VEC = 16 / sizeof(T);
+    const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (i >= n) return;
+    if (i + VEC <= n) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(x + i);
+        const T *e = reinterpret_cast<const T *>(&raw);
+        uint4 outr;
+        T *oe = reinterpret_cast<T *>(&outr);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            // the reference rounds logsigmoid to the activation dtype before the division (a power of two)
+            float g = to_f(from_f<T>(logsigmoidf_(to_f(e[c])))) * inv_norm;
+            if (use_clamp) g = fmaxf(g, clamp_min);
+            oe[c] = from_f<T>(g);
+        }
+        *reinterpret_cast<uint4 *>(y + i) = outr;
+    } else {
+        for (long long j = i; j < n; ++j) {
+            float g = to_f(from_f<T>(logsigmoidf_(to_f(x[j])))) * inv_norm;
+            if (use_clamp) g = fmaxf(g, clamp_min);
+            y[j] = from_f<T>(g);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+swiglu_act_kernel(const T *__restrict__ h, T *__restrict__ out, int M, int Hp) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int nv = Hp / VEC;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)M * nv) return;
+    const int m = (int)(idx / nv), j = (int)(idx - (long long)m * nv) * VEC;
+    const uint4 graw = *reinterpret_cast<const uint4 *>(h + (size_t)m * 2 * Hp + j);
+    const uint4 uraw = *reinterpret_cast<const uint4 *>(h + (size_t)m * 2 * Hp + Hp + j);
+    const T *ge = reinterpret_cast<const T *>(&graw), *ue = reinterpret_cast<const T *>(&uraw);
+    uint4 outr;
+    T *oe = reinterpret_cast<T *>(&outr);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        const float g = to_f(ge[c]);
+        oe[c] = from_f<T>(to_f(from_f<T>(siluf_(g))) * to_f(ue[c]));
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)m * Hp + j) = outr;
+}
+
+}  // namespace
+
+extern "C" int lina_gate_logsigmoid(const void *x, void *y, long long n, float normalizer, float clamp_min,
+                                    int use_clamp, int dtype, void *stream) {
+    LINA_REQUIRE(x && y && n > 0 && normalizer != 0.f, LINA_ERR_BAD_ARG, "gate_logsigmoid: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "gate_logsigmoid: unknown dtype");
+    LINA_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0, LINA_ERR_BAD_ARG, "gate_logsigmoid: 16-byte alignment");
+    const int vec = 16 / (int)lina_dtype_size(dtype);
+    const long long nthreads = (n + vec - 1) / vec;
+    LINA_DISPATCH_DTYPE(dtype, gate_logsigmoid_kernel<T_><<<(unsigned)((nthreads + 255) / 256), 256, 0,
+                                                             (cudaStream_t)stream>>>(
+                                   (const T_ *)x, (T_ *)y, n, 1.f / normalizer, clamp_min, use_clamp));
+    LINA_LAUNCH_OK("gate_logsigmoid_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtype, void *stream) {
+    LINA_REQUIRE(h && out && M > 0 && Hp > 0, LINA_ERR_BAD_ARG, "swiglu_act: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "swiglu_act: unknown dtype");
+    const int vec = 16 / (int)lina_dtype_size(dtype);
+    LINA_REQUIRE(Hp % vec == 0 && (uintptr_t)h % 16 == 0 && (uintptr_t)out % 16 == 0, LINA_ERR_UNSUPPORTED,
+                 "swiglu_act: hidden size %d must be a multiple of %d and pointers 16-byte aligned", Hp, vec);
+    const long long nthreads = (long long)M * (Hp / vec);
+    LINA_DISPATCH_DTYPE(dtype, swiglu_act_kernel<T_><<<(unsigned)((nthreads + 255) / 256), 256, 0,
+                                                        (cudaStream_t)stream>>>((const T_ *)h, (T_ *)out, M, Hp));
+    LINA_LAUNCH_OK("swiglu_act_kernel");
+    return LINA_OK;
+}

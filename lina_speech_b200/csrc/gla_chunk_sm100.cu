@@ -107,7 +107,7 @@ struct TMaps { CUtensorMap q, k, g, v; };
 template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
-                           bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, float scale,
+                           bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, int H, int bthd, float scale,
                            long long *__restrict__ trace) {
     using cfg = Cfg<K>;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
@@ -120,7 +120,10 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, v0 = blockIdx.x * BV;
     const int n_items = (T + C - 1) / C;
-    const size_t vbase = (size_t)bh * T * V;
+    const int bb = bh / H, hh = bh - bb * H;
+    // o is [B,H,T,V] (bthd == 0) or [B,T,H,V] (bthd == 1)
+    const size_t obase = bthd ? ((size_t)bb * T * H + hh) * V : (size_t)bh * T * V;
+    const size_t o_tstride = bthd ? (size_t)H * V : (size_t)V;
 
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
@@ -230,16 +233,16 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 mbar_expect_tx(&bars[B_RAW_FULL0 + s], cfg::RAW_TX);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_3d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
-                    tma_load_3d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
-                    tma_load_3d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, bh, &bars[B_RAW_FULL0 + s]);
+                    tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                    tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                    tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                 }
                 TRACE(1, n, 1);
                 wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
                 mbar_expect_tx(&bars[B_V_FULL], VT_BYTES);
                 const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
-                tma_load_3d(v_tile, &tm.v, v0, t0, bh, &bars[B_V_FULL]);
-                tma_load_3d(v_tile + 8192, &tm.v, v0 + 64, t0, bh, &bars[B_V_FULL]);
+                tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL]);
+                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL]);
                 TRACE(1, n, 2);
             }
         }
@@ -347,15 +350,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_O_EMPTY]);
-            bf16 *ob = o + vbase + (size_t)t0 * V + v0 + r;
+            bf16 *ob = o + obase + (size_t)t0 * o_tstride + v0 + r;
             const int nrow = min(C, T - t0);
             if (nrow == C) {
 #pragma unroll
-                for (int t = 0; t < C; ++t) { *ob = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31])); ob += V; }
+                for (int t = 0; t < C; ++t) { *ob = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31])); ob += o_tstride; }
             } else {
 #pragma unroll
                 for (int t = 0; t < C; ++t) {
-                    if (t < nrow) ob[(size_t)t * V] = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31]));
+                    if (t < nrow) ob[(size_t)t * o_tstride] = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31]));
                 }
             }
             if (r == 0) TRACE(4, n, 1);
@@ -426,7 +429,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
 
 template <int K>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
-           float *ht, int B, int H, int T, int V, float scale, cudaStream_t st, long long *trace = nullptr) {
+           float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr) {
     using cfg = Cfg<K>;
     static thread_local bool configured = false;
     if (!configured) {
@@ -434,23 +437,25 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
                                           (int)cfg::SMEM));
         configured = true;
     }
-    // 3-D views (innermost first): q,k,gk = (K, T, B*H), v = (V, T, B*H); 64 x 64 boxes, rows past T read as zero
+    // 4-D views (innermost first) (D, T, H, B) of [B,H,T,D] (bthd == 0) or [B,T,H,D] (bthd == 1) tensors;
+    // 64 x 64 boxes over (D, T); rows past T read as zero.
     TMaps tm;
-    const uint64_t BH = (uint64_t)B * H;
     {
-        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)T, BH};
-        const uint64_t strides[3] = {2, (uint64_t)K * 2, (uint64_t)T * K * 2};
-        const uint32_t box[3] = {64, 64, 1};
+        const uint64_t kd = K, vd = V, t = T, h = H, b = B;
+        const uint64_t dims[4] = {kd, t, h, b}, vdims[4] = {vd, t, h, b};
+        const uint64_t str_bhtd[4] = {2, kd * 2, t * kd * 2, h * t * kd * 2}, str_bthd[4] = {2, h * kd * 2, kd * 2, t * h * kd * 2};
+        const uint64_t vstr_bhtd[4] = {2, vd * 2, t * vd * 2, h * t * vd * 2}, vstr_bthd[4] = {2, h * vd * 2, vd * 2, t * h * vd * 2};
+        const uint32_t box[4] = {64, 64, 1, 1};
+        const uint64_t *sk = bthd ? str_bthd : str_bhtd, *sv = bthd ? vstr_bthd : vstr_bhtd;
         int rc;
-        if ((rc = lina_make_tmap_bf16(&tm.q, q, 3, dims, strides, box))) return rc;
-        if ((rc = lina_make_tmap_bf16(&tm.k, k, 3, dims, strides, box))) return rc;
-        if ((rc = lina_make_tmap_bf16(&tm.g, gk, 3, dims, strides, box))) return rc;
-        const uint64_t vdims[3] = {(uint64_t)V, (uint64_t)T, BH};
-        const uint64_t vstrides[3] = {2, (uint64_t)V * 2, (uint64_t)T * V * 2};
-        if ((rc = lina_make_tmap_bf16(&tm.v, v, 3, vdims, vstrides, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.q, q, 4, dims, sk, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.k, k, 4, dims, sk, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.g, gk, 4, dims, sk, box))) return rc;
+        if ((rc = lina_make_tmap_bf16(&tm.v, v, 4, vdims, sv, box))) return rc;
     }
     dim3 grid(V / BV, B * H);
-    gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, scale, trace);
+    gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
+                                                                   trace);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
 }
@@ -471,23 +476,38 @@ extern "C" size_t lina_gla_chunk_fwd_workspace_bytes(int B, int H, int T, int K,
     return 16;
 }
 
+static int chunk_fwd_tc(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype,
+                        void *o, float *ht, int B, int H, int T, int K, int V, int bthd, float scale, void *stream) {
+    LINA_REQUIRE(q && k && v && gk && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd: null tensor pointer");
+    LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd: bad h0 dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+    if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+    return launch<256>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+}
+
 extern "C" int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, const void *gk, const void *h0,
                                   int h0_dtype, void *o, float *ht, void *ws, int B, int H, int T, int K, int V,
                                   int dtype, float scale, void *stream) {
     (void)ws;
     if (!tc_eligible(B, H, T, K, V, dtype))
         return lina_gla_recurrent_fwd_impl(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, K, V, dtype, scale, stream);
-    LINA_REQUIRE(q && k && v && gk && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd: null tensor pointer");
-    LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd: bad h0 dtype");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
-    if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
-    return launch<256>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, scale, st);
+    return chunk_fwd_tc(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, K, V, 0, scale, stream);
+}
+
+extern "C" int lina_gla_chunk_fwd_bthd(const void *q, const void *k, const void *v, const void *gk, const void *h0,
+                                       int h0_dtype, void *o, float *ht, void *ws, int B, int H, int T, int K,
+                                       int V, int dtype, float scale, void *stream) {
+    (void)ws;
+    LINA_REQUIRE(tc_eligible(B, H, T, K, V, dtype), LINA_ERR_UNSUPPORTED,
+                 "gla_chunk_fwd_bthd: only the tensor-core envelope (bf16, K in {64,128,256}, V %% 128 == 0, T >= 32) "
+                 "reads the [B,T,H,D] layout in place; make the tensors [B,H,T,D]-contiguous and call lina_gla_chunk_fwd");
+    return chunk_fwd_tc(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, K, V, 1, scale, stream);
 }
 
 // bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]
 extern "C" int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
                                           int H, int T, int K, int V, float scale, long long *trace, void *stream) {
     LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16) && K == 256, LINA_ERR_UNSUPPORTED, "trace: K=256 bf16 only");
-    return launch<256>(q, k, v, gk, nullptr, 0, o, nullptr, B, H, T, V, scale, (cudaStream_t)stream, trace);
+    return launch<256>(q, k, v, gk, nullptr, 0, o, nullptr, B, H, T, V, 0, scale, (cudaStream_t)stream, trace);
 }

@@ -60,6 +60,71 @@ short_conv_fwd_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__res
     }
 }
 
+// Vectorised variant for the shipped configuration (W = 4, D a multiple of the 16-byte vector): each thread
+// owns 16 bytes of channels and slides over LTV time steps -> 512 B contiguous per warp per row.
+constexpr int LTV = 32;
+template <typename T>
+__global__ void __launch_bounds__(128)
+short_conv_fwd_w4_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__restrict__ y, void *__restrict__ cache,
+                         int cache_dtype, int L, int D, int silu) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int dv = blockIdx.x * 128 + threadIdx.x;          // vector index along D
+    const int d0 = dv * VEC;
+    const int l0 = blockIdx.y * LTV, b = blockIdx.z;
+    if (d0 >= D) return;
+    float wt[4][VEC], win[3][VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wt[j][c] = to_f(w[(size_t)(d0 + c) * 4 + j]);
+    const T *xb = x + (size_t)b * L * D + d0;
+    T *yb = y + (size_t)b * L * D + d0;
+    auto load = [&](int l, float *out) {
+        if (l < 0) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) out[c] = 0.f;
+            return;
+        }
+        const uint4 raw = *reinterpret_cast<const uint4 *>(xb + (size_t)l * D);
+        const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) out[c] = to_f(e[c]);
+    };
+    load(l0 - 3, win[0]); load(l0 - 2, win[1]); load(l0 - 1, win[2]);
+    const int lend = min(L, l0 + LTV);
+#pragma unroll 4
+    for (int l = l0; l < lend; ++l) {
+        float xv[VEC];
+        load(l, xv);
+        uint4 raw;
+        T *e = reinterpret_cast<T *>(&raw);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            float acc = win[0][c] * wt[0][c];
+            acc = fmaf(win[1][c], wt[1][c], acc);
+            acc = fmaf(win[2][c], wt[2][c], acc);
+            acc = fmaf(xv[c], wt[3][c], acc);
+            e[c] = from_f<T>(silu ? siluf_(acc) : acc);
+            win[0][c] = win[1][c]; win[1][c] = win[2][c]; win[2][c] = xv[c];
+        }
+        *reinterpret_cast<uint4 *>(yb + (size_t)l * D) = raw;
+    }
+    if (cache != nullptr && lend == L) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            const size_t cb = ((size_t)b * D + d0 + c) * 4;
+            if (L >= 4) {
+                store_dyn(cache, cache_dtype, cb + 0, to_f(xb[(size_t)(L - 4) * D + c]));
+            } else {
+                store_dyn(cache, cache_dtype, cb + 0, 0.f);
+            }
+            store_dyn(cache, cache_dtype, cb + 1, L >= 3 ? win[0][c] : 0.f);
+            store_dyn(cache, cache_dtype, cb + 2, L >= 2 ? win[1][c] : 0.f);
+            store_dyn(cache, cache_dtype, cb + 3, win[2][c]);
+        }
+    }
+}
+
 // dx[l] = sum_j w[j] * dpre[l + (W-1) - j],  dpre = dy * act'(pre) ; dw[j] += sum_l dpre[l] * x[l-(W-1)+j]
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -125,6 +190,15 @@ extern "C" int lina_short_conv_fwd(const void *x, const void *w, void *y, void *
     LINA_REQUIRE(W >= 1 && W <= MAXW, LINA_ERR_UNSUPPORTED, "short_conv_fwd: kernel size %d not in [1,%d]", W, MAXW);
     LINA_REQUIRE(cache == nullptr || lina_dtype_ok(cache_dtype), LINA_ERR_BAD_ARG, "short_conv_fwd: bad cache dtype");
     LINA_REQUIRE(B <= 65535 && (L + LT - 1) / LT <= 65535, LINA_ERR_UNSUPPORTED, "short_conv_fwd: grid too large");
+    const int vec = 16 / (int)lina_dtype_size(dtype);
+    if (W == 4 && D % vec == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+        const int nv = D / vec;
+        dim3 gridv((nv + 127) / 128, (L + LTV - 1) / LTV, B);
+        LINA_DISPATCH_DTYPE(dtype, short_conv_fwd_w4_kernel<T_><<<gridv, 128, 0, (cudaStream_t)stream>>>(
+                                       (const T_ *)x, (const T_ *)w, (T_ *)y, cache, cache_dtype, L, D, silu));
+        LINA_LAUNCH_OK("short_conv_fwd_w4_kernel");
+        return LINA_OK;
+    }
     dim3 grid((D + 127) / 128, (L + LT - 1) / LT, B);
     LINA_DISPATCH_DTYPE(dtype, short_conv_fwd_kernel<T_><<<grid, 128, 0, (cudaStream_t)stream>>>(
                                    (const T_ *)x, (const T_ *)w, (T_ *)y, cache, cache_dtype, L, D, W, silu));

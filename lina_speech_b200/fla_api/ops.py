@@ -23,11 +23,20 @@ import torch
 from .. import _lib as L
 
 
-def _prep(q, k, v, gk, h0):
+def _is_bthd(x: torch.Tensor) -> bool:
+    """[B,H,T,D] view of a contiguous [B,T,H,D] tensor (what rearrange('b l (h d) -> b h l d') returns)."""
+    return (not x.is_contiguous()) and x.transpose(1, 2).is_contiguous()
+
+
+def _prep(q, k, v, gk, h0, kind="recurrent"):
     L.require_cuda(q, k, v, gk, h0)
     if not (q.dtype == k.dtype == v.dtype == gk.dtype):
         q, k, v, gk = (x.float() for x in (q, k, v, gk))   # mixed dtypes: compute everything in fp32
-    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
+    B_, H_, T_, K_ = q.shape
+    bthd = (kind != "recurrent" and all(_is_bthd(x) for x in (q, k, v, gk)) and
+            bool(L.lib().lina_gla_chunk_fwd_uses_tensor_cores(B_, H_, T_, K_, v.shape[-1], L._DT.get(q.dtype, -1))))
+    if not bthd:
+        q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
     if h0 is not None:
         h0 = h0.contiguous()
         if h0.dtype not in (torch.float32, torch.bfloat16, torch.float16):
@@ -38,20 +47,23 @@ def _prep(q, k, v, gk, h0):
         raise ValueError(f"GLA shapes disagree: q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} gk{tuple(gk.shape)}")
     if h0 is not None and tuple(h0.shape) != (B, H, K, V):
         raise ValueError(f"initial_state must be [B,H,K,V]={B, H, K, V}, got {tuple(h0.shape)}")
-    return q, k, v, gk, h0, (B, H, T, K, V)
+    return q, k, v, gk, h0, bthd
 
 
 # bench.py sets this to a list to collect (kind, start_event, end_event) of every forward launch
 PROFILE = None
 
 
-def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
+def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool, bthd: bool = False):
     lib = L.lib()
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.current_stream(q.device))
     B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
-    o = torch.empty_like(v)
+    if bthd:     # inputs are [B,H,T,D] views of [B,T,H,D] memory; produce o the same way (no copies either side)
+        o = torch.empty(B, T, H, V, dtype=v.dtype, device=v.device).transpose(1, 2)
+    else:
+        o = torch.empty_like(v)
     ht = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_ht else None
     h0dt = L.dt(h0) if h0 is not None else 0
     if kind == "recurrent":
@@ -61,7 +73,8 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
     else:
         nbytes = lib.lina_gla_chunk_fwd_workspace_bytes(B, H, T, K, V, L.dt(q))
         ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=q.device)
-        rc = lib.lina_gla_chunk_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(h0), h0dt, L.ptr(o), L.ptr(ht),
+        entry = lib.lina_gla_chunk_fwd_bthd if bthd else lib.lina_gla_chunk_fwd
+        rc = entry(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(h0), h0dt, L.ptr(o), L.ptr(ht),
                                     L.ptr(ws), B, H, T, K, V, L.dt(q), scale, L.stream(q))
         L.count_launches(1)
     L.check(rc, f"lina_gla_{kind}_fwd")
@@ -73,6 +86,7 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool):
 
 def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     lib = L.lib()
+    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))     # the backward kernels read [B,H,T,D]
     B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
     do = do.contiguous()
     if do.dtype != q.dtype:
@@ -100,8 +114,8 @@ class _GLAFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, q, k, v, gk, scale, initial_state, output_final_state, kind):
         in_dtypes = (q.dtype, k.dtype, v.dtype, gk.dtype)
-        q, k, v, gk, h0, _ = _prep(q, k, v, gk, initial_state)
-        o, ht = _fwd("recurrent" if kind == "recurrent" else "chunk", q, k, v, gk, h0, scale, output_final_state)
+        q, k, v, gk, h0, bthd = _prep(q, k, v, gk, initial_state, kind)
+        o, ht = _fwd("recurrent" if kind == "recurrent" else "chunk", q, k, v, gk, h0, scale, output_final_state, bthd)
         ctx.save_for_backward(q, k, v, gk, h0)
         ctx.scale, ctx.kind, ctx.in_dtypes = scale, kind, in_dtypes
         ctx.h0_dtype = initial_state.dtype if initial_state is not None else None

@@ -157,10 +157,20 @@ class GatedLinearAttention(nn.Module):
             v = v.mul_(attention_mask.unsqueeze(-1))
         H = self.num_heads
         q, k, v = (rearrange(t, "b l (h d) -> b h l d", h=H) for t in (q, k, v))
-        gk = rearrange(self.gk_proj(hidden_states), "b n (h d) -> b h n d", h=H)
-        gk = F.logsigmoid(gk) / self.gate_logit_normalizer
-        if self.clamp_min is not None:
-            gk = torch.clamp_min(gk, self.clamp_min)
+        gk = self.gk_proj(hidden_states)
+        if not torch.is_grad_enabled() and gk.is_contiguous():
+            gko = torch.empty_like(gk)                                   # one fused pass: logsigmoid / normalizer [clamp]
+            rc = L.lib().lina_gate_logsigmoid(L.ptr(gk), L.ptr(gko), gk.numel(), float(self.gate_logit_normalizer),
+                                              float(self.clamp_min or 0.0), int(self.clamp_min is not None),
+                                              L.dt(gk), L.stream(gk))
+            L.count_launches(1)
+            L.check(rc, "lina_gate_logsigmoid")
+            gk = rearrange(gko, "b n (h d) -> b h n d", h=H)
+        else:
+            gk = rearrange(gk, "b n (h d) -> b h n d", h=H)
+            gk = F.logsigmoid(gk) / self.gate_logit_normalizer
+            if self.clamp_min is not None:
+                gk = torch.clamp_min(gk, self.clamp_min)
         if reset_mask is not None:
             gk = gk.masked_fill(reset_mask.unsqueeze(1).unsqueeze(3), reset_val)
 

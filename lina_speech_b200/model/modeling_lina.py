@@ -22,6 +22,7 @@ from torch import Tensor, nn
 
 from .attentive_rnn import AttentiveRNN
 from .multiembed import MultiEmbedding
+from ..parallel import gather_tokens
 from .tools import topk_sampling, undelay_rvq
 
 
@@ -173,9 +174,7 @@ class LinaModel(nn.Module):
             atts.append(att)
             if dist_group is not None:
                 # the one exchange of the data path: [q, b_local, 1] int64 ids -> [q, b_global, 1]
-                gathered = torch.empty(world, *q_sampled.shape, dtype=q_sampled.dtype, device=device)
-                dist.all_gather_into_tensor(gathered, q_sampled.contiguous(), group=dist_group)
-                q_all = rearrange(gathered, "w q b n -> q (w b) n")
+                q_all = gather_tokens(q_sampled, dist_group)
             else:
                 q_all = q_sampled
             qs.append(q_all)

@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/lina_b200.h declares; the ctypes
+prototype table covers exactly those symbols; ops fail loudly without a GPU (no CPU / oracle fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "lina_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lina_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lina_speech_b200 import _lib
+    names = _declared()
+    assert len(names) >= 25
+    assert os.path.exists(_lib.LIB_PATH), "liblina_b200.so must be built in-tree"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(raw, n)]
+    assert not missing, f"declared in include/lina_b200.h but not exported: {missing}"
+
+
+def test_ctypes_prototypes_match_header():
+    from lina_speech_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == _declared()
+    lib = _lib.lib()
+    assert lib.lina_abi_version() >= 1
+    assert lib.lina_last_error_string() is not None
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    """error codes + messages travel through the C ABI without a device (no compute is launched)."""
+    from lina_speech_b200 import _lib
+    lib = _lib.lib()
+    rc = lib.lina_gla_recurrent_fwd(None, None, None, None, None, 0, None, None, 1, 1, 8, 512, 64, _lib.F32, 1.0, None)
+    assert rc == -2 and b"K=512" in lib.lina_last_error_string()          # LINA_ERR_UNSUPPORTED
+    rc = lib.lina_gla_recurrent_fwd(None, None, None, None, None, 0, None, None, 1, 1, 8, 64, 64, _lib.F32, 1.0, None)
+    assert rc == -1                                                        # LINA_ERR_BAD_ARG: null pointers
+    rc = lib.lina_rmsnorm_swishgate_fwd(None, None, None, None, None, 4, 8, 1e-5, 7, None)
+    assert rc == -1
+    assert lib.lina_gla_chunk_fwd_uses_tensor_cores(32, 4, 2048, 256, 512, _lib.BF16) == 1
+    assert lib.lina_gla_chunk_fwd_uses_tensor_cores(32, 4, 2048, 256, 512, _lib.F32) == 0
+    assert lib.lina_gla_chunk_fwd_uses_tensor_cores(1, 4, 128, 48, 128, _lib.BF16) == 0
+    assert lib.lina_gla_recurrent_bwd_workspace_bytes(2, 3, 5, 7, 11) == (2 * 2 * 3 * 5 * 7 + 2 * 3 * 7) * 4
+
+
+def test_ops_refuse_cpu_tensors():
+    from lina_speech_b200.fla_api import fused_chunk_gla, chunk_gla, ShortConvolution, FusedRMSNormSwishGate
+    x = torch.randn(1, 2, 8, 16)
+    for fn in (fused_chunk_gla, chunk_gla):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(x, x, x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ShortConvolution(16, 4)(torch.randn(1, 8, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedRMSNormSwishGate(16)(torch.randn(4, 16), torch.randn(4, 16))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under lina_speech_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "lina_speech_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"

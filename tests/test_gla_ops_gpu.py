@@ -215,3 +215,22 @@ def test_cpu_tensors_fail_loudly():
     x = torch.randn(1, 1, 4, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fused_recurrent_gla(x, x, x, x)
+
+
+def test_bthd_layout_is_read_in_place():
+    """[B,H,T,D] views of [B,T,H,D] projections (what rearrange('b l (h d) -> b h l d') yields) go through
+    lina_gla_chunk_fwd_bthd without copies and give the same result; o comes back as the same kind of view."""
+    from lina_speech_b200.fla_api import fused_chunk_gla
+    torch.manual_seed(2)
+    B, H, T, K, V = 2, 4, 200, 128, 256
+    qb, kb, gb = (torch.randn(B, T, H, K, device=DEV).bfloat16() for _ in range(3))
+    gb = (F.logsigmoid(gb.float()) / 16).bfloat16()
+    vb = torch.randn(B, T, H, V, device=DEV).bfloat16()
+    h0 = torch.randn(B, H, K, V, device=DEV)
+    q, k, v, g = (x.transpose(1, 2) for x in (qb, kb, vb, gb))
+    assert not q.is_contiguous()
+    o1, h1 = fused_chunk_gla(q, k, v, g, initial_state=h0, output_final_state=True)
+    o2, h2 = fused_chunk_gla(q.contiguous(), k.contiguous(), v.contiguous(), g.contiguous(), initial_state=h0,
+                             output_final_state=True)
+    assert o1.shape == (B, H, T, V) and o1.transpose(1, 2).is_contiguous()
+    assert torch.equal(o1, o2) and torch.equal(h1, h2)

@@ -1,0 +1,69 @@
+"""CPU: host-side logic that needs no kernel -- token tools, the state cache, module / state-dict layout."""
+import torch
+
+from lina_speech_b200.fla_api import Cache
+from lina_speech_b200.model import tools
+import lina_speech_b200.model as m
+from lina_speech_b200.codec import WavTokenizer
+
+
+def test_delay_undelay_roundtrip():
+    code = torch.randint(3, 50, (3, 11))
+    d = tools.delay_rvq(code, head_token=1, tail_token=2)
+    assert d.shape == (3, 11 + 4)
+    assert (d[0, 0] == 1) and (d[2, :3] == 1).all() and (d[0, -3:] == 2).all()
+    u = tools.undelay_rvq(d.unsqueeze(1))
+    assert torch.equal(u[:, 0], code)
+
+
+def test_topk_sampling_greedy_is_argmax():
+    torch.manual_seed(0)
+    x = torch.randn(5, 40)
+    assert torch.equal(tools.topk_sampling(x.clone(), k=1).squeeze(-1), x.argmax(-1))
+    s = tools.topk_sampling(x.clone(), k=5, temp=0.7).squeeze(-1)
+    top5 = x.topk(5, dim=-1).indices
+    assert all(s[i] in top5[i] for i in range(5))
+
+
+def test_cache_update_is_in_place_and_skips_self_copies():
+    c = Cache()
+    a, b = torch.zeros(2, 3), torch.zeros(2, 4)
+    c.update((a, b), 0, offset=0)
+    assert c[0][0] is a and len(c) == 1
+    c.update((torch.ones(2, 3), b), 0)            # b is the same storage: no copy, a receives the new values
+    assert torch.equal(a, torch.ones(2, 3)) and c.get_seq_length() == 1
+    try:
+        c[3]
+        assert False
+    except KeyError:
+        pass
+
+
+def test_state_layout_matches_reference_init_state():
+    rnn = m.AttentiveGLA(64, 2, 2, blind=True, use_short_conv=True, pos_type="convolutional")
+    cache = rnn.init_state(batch_size=3)
+    assert len(cache) == 5                                          # 2 enc + 2 dec + pos_net (model/gla.py:302-313)
+    shapes = [tuple(t.shape) for t in cache[0]]
+    assert shapes == [(3, 64, 4), (3, 64, 4), (3, 128, 4), (3, 2, 32, 64)]
+    params = rnn.get_init_state_tuning_params(lora=1)
+    assert len(params) == 4 and params[0][0].shape == (1, 1, 2, 32, 1) and params[0][1].shape == (1, 1, 2, 1, 64)
+    st = rnn.get_state_from_params(params, 3, scale=0.02)
+    assert st[0][-1].shape == (3, 2, 32, 64) and st[0][-1].requires_grad
+
+
+def test_flagship_parameter_count_is_the_readme_169M():
+    """AttentiveGLA(d1024, n_layer=6, blind) = 169.35 M parameters (README.md:36)."""
+    with torch.device("meta"):
+        rnn = m.AttentiveGLA(1024, 6, 4, blind=True, use_short_conv=True, pos_type="convolutional")
+    n = sum(p.numel() for p in rnn.parameters())
+    assert abs(n / 1e6 - 169.35) < 0.3, n
+
+
+def test_codec_module_tree_has_reference_key_names():
+    wt = WavTokenizer.from_hparams(vq_bins=64, dim=64, intermediate_dim=128, num_layers=2)
+    keys = set(wt.state_dict().keys())
+    for k in ("backbone.embed.weight", "backbone.pos_net.0.norm1.weight", "backbone.pos_net.2.q.weight",
+              "backbone.pos_net.5.bias", "backbone.norm.scale.weight", "backbone.convnext.1.dwconv.weight",
+              "backbone.convnext.0.gamma", "backbone.final_layer_norm.weight", "head.out.weight",
+              "head.istft.window", "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"):
+        assert k in keys, k

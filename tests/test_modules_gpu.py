@@ -113,3 +113,19 @@ def test_fused_step_matches_oracle_layer(state_dtype, B, d, H):
             _close(y, ry, 3e-2 if lo else 2e-5, 2e-2 if lo else 1e-4, what=f"step {t} y")
     for s, o in zip(cache.states[0], ost):
         _close(s, o, 2e-2 if dtype == torch.bfloat16 else 1e-4, 1e-2 if dtype == torch.bfloat16 else 1e-4, what="state")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_swiglu_inference_path_matches_reference_formula(dtype):
+    """padded-weight GEMMs + fused silu*mul (no-grad CUDA path) == p_out(silu(gate) * u) (model/base_blocks.py:48-50)."""
+    from lina_speech_b200.model import SwiGLU
+    torch.manual_seed(0)
+    m = SwiGLU(1024).to(DEV).to(dtype)
+    x = torch.randn(3, 50, 1024, device=DEV).to(dtype)
+    with torch.no_grad():
+        y = m(x)
+    with torch.enable_grad():
+        gate, u = m.p_in(x).chunk(2, dim=-1)
+        ref = m.p_out(F.silu(gate) * u)
+    lo = dtype == torch.bfloat16
+    _close(y, ref, 2e-2 if lo else 1e-5, 2e-2 if lo else 1e-5, what="swiglu")
