@@ -108,7 +108,6 @@ def cpu_reference_rate(budget_s: float, repeats: int = 1):
     from oracle import lina_oracle as LO
     import lina_speech_b200.model as m
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(0)
     c = CFG
     rnn = m.AttentiveGLA(c["d_model"], c["n_layer"], c["heads"], blind=True, use_short_conv=True,
@@ -130,8 +129,15 @@ def cpu_reference_rate(budget_s: float, repeats: int = 1):
         return time.perf_counter() - t0
 
     probe_T = 8
-    run(probe_T)                                   # warm-up (thread pools, allocator)
-    dt = run(probe_T)
+    best = None
+    for nt in sorted({cores, min(cores, 32), min(cores, 16)}, reverse=True):    # many-core hosts: all threads is not always fastest
+        torch.set_num_threads(nt)
+        run(probe_T)                               # warm-up (thread pools, allocator)
+        dt = min(run(probe_T), run(probe_T))
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    dt, cores = best
+    torch.set_num_threads(cores)
     rate = B * probe_T / dt
     T = int(max(8, min(256, rate * budget_s / B)))
     times = [run(T) for _ in range(repeats)]
@@ -269,6 +275,18 @@ def main_ours(args):
               "state_dtype": "bf16", "state_bytes_per_step": state_bytes,
               "state_hbm_frac": state_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "cuda_graph": True}
 
+    # same loop at the batch where the state traffic dominates (BASELINE configs[2]: bs 128)
+    B2 = 128
+    tm2 = {}
+    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True)
+    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=64, k=100, force_max_seqlen=True, cuda_graph=True, _timing=tm2)
+    torch.cuda.synchronize()
+    dec2_ms = tm2["start"].elapsed_time(tm2["end"]) / tm2["steps"]
+    sb2 = B2 * n_blocks * 2 * H * K * V * 2
+    decode_bs128 = {"batch": B2, "steps": tm2["steps"], "ms_per_step": dec2_ms, "tokens_per_s": world * B2 / (dec2_ms * 1e-3),
+                    "rtf_24khz": 75.0 * dec2_ms * 1e-3, "state_bytes_per_step": sb2,
+                    "state_hbm_frac": sb2 / (dec2_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+
     if rank == 0:
         cpu_v, cores, sample = cpu_reference_rate(budget_s=20.0) if world == 1 else (None, None, None)
         per_step = ms / args.steps
@@ -281,7 +299,8 @@ def main_ours(args):
                           "l2": "per-step working set (>= 64 MB per activation, 0.4 GB weights) exceeds the 126 MB L2; no flush"},
                "e2e": {"value": world * tokens_per_step / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                        "h2d_bytes_per_step": xh.numel() * 8 + yh.numel() * 8, "d2h_bytes_per_step": 4},
-               "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "decode": decode}
+               "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "decode": decode,
+               "decode_bs128": decode_bs128}
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out), flush=True)

@@ -5,6 +5,10 @@
 
 namespace {
 
+// log(sigmoid(x)) with fast intrinsics; the result is rounded to the activation dtype right after, so the
+// ~1e-7 absolute error of __logf/__expf is invisible
+__device__ __forceinline__ float logsigmoid_fast(float x) { return fminf(x, 0.f) - __logf(1.f + __expf(-fabsf(x))); }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gate_logsigmoid_kernel(const T *__restrict__ x, T *__restrict__ y, long long n, float inv_norm, float clamp_min,
@@ -20,7 +24,7 @@ gate_logsigmoid_kernel(const T *__restrict__ x, T *__restrict__ y, long long n, 
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
             // the reference rounds logsigmoid to the activation dtype before the division (a power of two)
-            float g = to_f(from_f<T>(logsigmoidf_(to_f(e[c])))) * inv_norm;
+            float g = to_f(from_f<T>(sizeof(T) == 4 ? logsigmoidf_(to_f(e[c])) : logsigmoid_fast(to_f(e[c])))) * inv_norm;
             if (use_clamp) g = fmaxf(g, clamp_min);
             oe[c] = from_f<T>(g);
         }

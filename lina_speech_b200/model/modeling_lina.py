@@ -41,6 +41,17 @@ class LogitsHead(nn.Module):
 
     def forward(self, x):
         q, l, d = self.weight.shape
+        if q == 1 and l % 8 and x.is_cuda and not torch.is_grad_enabled():
+            # l = n_codebook + 3 = 4099 is odd: the unpadded GEMM runs on cuBLAS' unaligned legacy kernels.
+            # Inference pads the vocabulary dim of the weight once to a multiple of 8 and slices the result.
+            key = (self.weight.data_ptr(), getattr(self.weight, "_version", 0) if not self.weight.is_inference() else -1,
+                   self.weight.dtype)
+            if getattr(self, "_wpad", None) is None or self._wpad[0] != key:
+                lp = (l + 7) // 8 * 8
+                wp = self.weight.new_zeros(lp, d)
+                wp[:l] = self.weight.detach()[0]
+                self._wpad = (key, wp)
+            return F.linear(x, self._wpad[1])[..., :l].unsqueeze(-2)
         return F.linear(x, self.weight.view(q * l, d)).view(*x.shape[:-1], q, l)
 
 
