@@ -177,6 +177,9 @@ int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int K
  * A_bf16 [128,KD] through a 2-D tensor map with CU_TENSOR_MAP_SWIZZLE_128B instead of writing it by hand. */
 int lina_debug_umma_probe_sw128(const float *A, const float *B, float *D, const void *A_bf16, int N, int KD,
                                 int a_mode, int b_mode, int use_tma, void *stream);
+/* Cycles of `nmma` back-to-back M=128 x N x 16 bf16 MMAs issued by one thread (A from TMEM / smem K-major /
+ * smem MN-major, B K-/MN-major, same or alternating accumulator): out[6] = (issue, issue+completion) x 3 reps. */
+int lina_debug_umma_timing(long long *out, int N, int a_tmem, int a_mn, int b_mn, int nmma, int same_d, void *stream);
 /* The tcgen05 GLA kernel (K = 256, bf16) with a clock64 timeline of CTA (0,0) written to
  * trace[6 roles][64 items][4 events] (int64) -- profiles/trace_gla_chunk.py prints it. */
 int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,

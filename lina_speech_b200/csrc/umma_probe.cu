@@ -196,3 +196,63 @@ extern "C" int lina_debug_umma_probe_sw128(const float *A, const float *B, float
     LINA_LAUNCH_OK("umma_probe_sw128_kernel");
     return LINA_OK;
 }
+
+// ---- third probe: cycles per tcgen05.mma for the shapes the GLA kernel issues (SW128 operands; data = garbage) ----
+namespace {
+
+__global__ void __launch_bounds__(128)
+umma_timing_kernel(long long *__restrict__ out, int N, int a_tmem, int a_mn, int b_mn, int nmma, int same_d) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = idesc_bf16(128, N, a_mn, b_mn);
+        const uint32_t a_tile = smem_u32(smem), b_tile = smem_u32(smem + 64 * 1024);
+        const uint64_t ad0 = a_mn ? smem_desc_sw128(a_tile, 8192, 1024) : smem_desc_sw128(a_tile, 0, 1024);
+        const uint64_t bd0 = b_mn ? smem_desc_sw128(b_tile, 16384, 1024) : smem_desc_sw128(b_tile, 0, 1024);
+        const uint64_t a_step = a_mn ? (2048 >> 4) : (32 >> 4), b_step = b_mn ? (2048 >> 4) : (32 >> 4);
+        const uint32_t d1 = same_d ? 0u : 256u;
+        for (int rep = 0; rep < 3; ++rep) {
+            const long long t0 = clock64();
+            for (int i = 0; i < nmma; i += 4) {          // descriptors advanced by constants: 4 k-steps per round
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t d = tbase + ((j & 1) ? d1 : 0u);
+                    if (a_tmem) mma_ts(d, tbase + 384 + j * 8, bd0 + j * b_step, idesc, 1);
+                    else mma_ss(d, ad0 + j * a_step, bd0 + j * b_step, idesc, 1);
+                }
+            }
+            const long long t1 = clock64();
+            mma_commit(&bar);
+            mbar_wait(&bar, rep & 1);
+            const long long t2 = clock64();
+            out[rep * 2 + 0] = t1 - t0;      // issue time
+            out[rep * 2 + 1] = t2 - t0;      // issue + completion
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+}  // namespace
+
+// out[6]: (issue cycles, total cycles) x 3 repetitions of `nmma` back-to-back M=128 x N x K=16 bf16 MMAs
+extern "C" int lina_debug_umma_timing(long long *out, int N, int a_tmem, int a_mn, int b_mn, int nmma, int same_d,
+                                      void *stream) {
+    LINA_REQUIRE(out && N % 16 == 0 && N >= 16 && N <= 256 && nmma > 0 && nmma <= 4096, LINA_ERR_BAD_ARG, "umma_timing: bad argument");
+    const int smem = 160 * 1024;
+    LINA_CUDA_OK(cudaFuncSetAttribute(umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, N, a_tmem, a_mn, b_mn, nmma, same_d);
+    LINA_LAUNCH_OK("umma_timing_kernel");
+    return LINA_OK;
+}
