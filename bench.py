@@ -254,14 +254,15 @@ def main_ours(args):
                 "algorithmic_bytes": alg_bytes, "tensor_achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
                 "tensor_frac_of_sustained": alg_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
 
+    grp = dist.group.WORLD if world > 1 else None          # batch-sharded generation: token all-gather per step
     # autoregressive decode loop (generate_batch) for tokens/s per stream and RTF
     dec_steps = 96
     xt = x[0]
     tm = {}
-    lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True)
+    lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True, dist_group=grp)
     l1 = _lib.launches()
     lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=dec_steps, k=100, force_max_seqlen=True, cuda_graph=True,
-                      _timing=tm)
+                      dist_group=grp, _timing=tm)
     torch.cuda.synchronize()
     dec_ms = tm["start"].elapsed_time(tm["end"]) / tm["steps"]
     if world > 1:
@@ -273,13 +274,15 @@ def main_ours(args):
     decode = {"batch": B, "steps": tm["steps"], "ms_per_step": dec_ms, "tokens_per_s": world * B / (dec_ms * 1e-3),
               "tokens_per_s_per_stream": 1.0 / (dec_ms * 1e-3), "rtf_24khz": 75.0 / (1.0 / (dec_ms * 1e-3)),
               "state_dtype": "bf16", "state_bytes_per_step": state_bytes,
-              "state_hbm_frac": state_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "cuda_graph": True}
+              "state_hbm_frac": state_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "cuda_graph": True,
+              "token_all_gather": world > 1}
 
     # same loop at the batch where the state traffic dominates (BASELINE configs[2]: bs 128)
     B2 = 128
     tm2 = {}
-    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True)
-    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=64, k=100, force_max_seqlen=True, cuda_graph=True, _timing=tm2)
+    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True, dist_group=grp)
+    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=64, k=100, force_max_seqlen=True, cuda_graph=True,
+                      dist_group=grp, _timing=tm2)
     torch.cuda.synchronize()
     dec2_ms = tm2["start"].elapsed_time(tm2["end"]) / tm2["steps"]
     sb2 = B2 * n_blocks * 2 * H * K * V * 2

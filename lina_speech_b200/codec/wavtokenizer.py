@@ -252,6 +252,10 @@ class WavTokenizer(nn.Module):
     def __init__(self, feature_extractor: CodebookFeatures, backbone: VocosBackbone, head: ISTFTHead):
         super().__init__()
         self.feature_extractor, self.backbone, self.head = feature_extractor, backbone, head
+        # "fp32": library GEMMs / convolutions in full fp32 (bit-for-bit the reference's default math);
+        # "tf32": let cuBLAS / cuDNN use TF32 tensor cores for them (10-bit mantissa operands, fp32 accumulate) --
+        #         ~10x faster GEMMs, waveform error ~1e-3 relative.  The kernels of liblina_b200 are fp32 either way.
+        self.gemm_precision = "fp32"
 
     @classmethod
     def from_hparams(cls, *, num_quantizers=1, vq_bins=4096, input_channels=512, dim=768, intermediate_dim=2304,
@@ -269,7 +273,15 @@ class WavTokenizer(nn.Module):
 
     @torch.inference_mode()
     def decode(self, features_input: torch.Tensor, **kwargs: Any) -> torch.Tensor:
-        return self.head(self.backbone(features_input, **kwargs))
+        if self.gemm_precision not in ("fp32", "tf32"):
+            raise ValueError("gemm_precision must be 'fp32' or 'tf32'")
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        tf32 = self.gemm_precision == "tf32"
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32, tf32
+        try:
+            return self.head(self.backbone(features_input, **kwargs))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
     @torch.inference_mode()
     def codes_to_features(self, codes: torch.Tensor) -> torch.Tensor:

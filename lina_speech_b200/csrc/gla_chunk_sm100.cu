@@ -24,11 +24,9 @@
 // same v bytes as the MN-major A of (2) and (3).
 //
 // Warp roles (640 threads):
+//   warp 19     TMA loader (one thread): 3-D tensor maps (K|V, T, B*H), 64x64 boxes, rows past T zero-filled;
 //   warps 0-7   gate pre-pass IN PLACE on the landed stage: cumsum over the chunk, q -> q~, k -> k~ (two stages);
-//   warp 18     one thread: MMA issuer of the state chain (1),(2),(3) AND TMA producer (4-D tensor maps (D,T,H,B),
-//               64x64 boxes, rows past T zero-filled) -- it refills a stage right after the MMAs that freed it;
-//   warp 19     one thread: issues the independent score MMA (0), so the two dependent-accumulate chains overlap
-//               in the tensor pipe;
+//   warp 18     MMA issuer (one thread);
 //   warps 16,17 causal mask (P: TMEM -> bf16 smem);      warps 8-11 output epilogue (OT: TMEM -> global);
 //   warps 12-15 state pass (ST *= exp(G_C), refresh SA, final state).
 // Synchronisation is mbarrier-only; global-load latency is hidden by TMA running a stage ahead.
@@ -106,30 +104,6 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
 
 struct TMaps { CUtensorMap q, k, g, v; };
 
-// one 32-column block of the state pass: f *= decay; then either (not last) write it back as fp32 master + bf16
-// operand copy, or (last item) emit the final state
-__device__ __forceinline__ void scale_store(uint32_t (&f)[32], const float *dv, uint32_t tlane, int cb, bool last,
-                                            float *__restrict__ ht, size_t sbase, int V) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 d4 = *reinterpret_cast<const float4 *>(dv + j);
-        f[j + 0] = __float_as_uint(__uint_as_float(f[j + 0]) * d4.x);
-        f[j + 1] = __float_as_uint(__uint_as_float(f[j + 1]) * d4.y);
-        f[j + 2] = __float_as_uint(__uint_as_float(f[j + 2]) * d4.z);
-        f[j + 3] = __float_as_uint(__uint_as_float(f[j + 3]) * d4.w);
-    }
-    if (!last) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
-        tmem_st32(tlane + COL_ST + cb * 32, f);
-        tmem_st16(tlane + COL_SA + cb * 16, pk);
-    } else if (ht != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ht[sbase + (size_t)(cb * 32 + j) * V] = __uint_as_float(f[j]);
-    }
-}
-
 template <int K>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
@@ -154,7 +128,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
         mbar_init(&bars[B_QK_FULL0], NPREP); mbar_init(&bars[B_QK_FULL1], NPREP);
-        mbar_init(&bars[B_QK_EMPTY0], 2); mbar_init(&bars[B_QK_EMPTY1], 2);   // one commit from each MMA issuer
+        mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1);
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
         mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
@@ -245,6 +219,34 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             mbar_arrive(&bars[B_G_EMPTY0 + s]);
             if (p == 0) TRACE(0, n, 1);
         }
+    } else if (warp == 19) {
+        // ====================== TMA loader (one thread): q, k -> operand tile of the stage, gk -> side tile, v ======================
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.g); tma_prefetch_desc(&tm.v);
+            for (int n = 0; n < n_items; ++n) {
+                const int s = n & 1, t0 = n * C;
+                const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
+                const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
+                wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                TRACE(1, n, 0);
+                mbar_expect_tx(&bars[B_RAW_FULL0 + s], cfg::RAW_TX);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                    tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                    tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                }
+                TRACE(1, n, 1);
+                wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
+                mbar_expect_tx(&bars[B_V_FULL], VT_BYTES);
+                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
+                tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL]);
+                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL]);
+                TRACE(1, n, 2);
+            }
+        }
+        __syncwarp();
     } else if (warp == 18) {
         // ====================== MMA issuer (one thread) ======================
         if (lane == 0) {
@@ -253,55 +255,30 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             const uint32_t id_s = idesc_bf16(128, K, 1, 1);      // (3): MN-major A (v^T), MN-major B (k~)
             const uint32_t p_tile = smem_u32(smem + cfg::OFF_P);
             const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
-            // TMA producer: raw q, k, gk of item m -> stage m & 1 ; v of item m -> the single v tile
-            auto load_raw = [&](int m) {
-                const int sm = m & 1, t0 = m * C;
-                const uint32_t qk_t = smem_u32(smem + cfg::OFF_QK + sm * cfg::QK_BYTES);
-                const uint32_t g_t = smem_u32(smem + cfg::OFF_G + sm * cfg::G_BYTES);
-                wait_bar(&bars[B_QK_EMPTY0 + sm], ((m >> 1) & 1) ^ 1);
-                wait_bar(&bars[B_G_EMPTY0 + sm], ((m >> 1) & 1) ^ 1);
-                TRACE(1, m, 0);
-                mbar_expect_tx(&bars[B_RAW_FULL0 + sm], cfg::RAW_TX);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_4d(g_t + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + sm]);
-                    tma_load_4d(qk_t + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + sm]);
-                    tma_load_4d(qk_t + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + sm]);
-                }
-                TRACE(1, m, 1);
-            };
-            auto load_v = [&](int m) {
-                wait_bar(&bars[B_V_EMPTY], (m & 1) ^ 1);
-                mbar_expect_tx(&bars[B_V_FULL], VT_BYTES);
-                tma_load_4d(v_tile, &tm.v, v0, m * C, hh, bb, &bars[B_V_FULL]);
-                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, m * C, hh, bb, &bars[B_V_FULL]);
-                TRACE(1, m, 2);
-            };
-            tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.g); tma_prefetch_desc(&tm.v);
-            load_raw(0);
-            load_v(0);
-            if (n_items > 1) load_raw(1);
-            // The issuing thread is alone in its warp: every dependent scalar instruction costs its full latency, so
-            // descriptors are built ONCE and advanced by adding compile-time constants to the 16-byte-unit address
-            // field (measured: ~200 cycles per MMA when rebuilt per instruction, tensor-pipe-bound when not).
-            const uint64_t dQ0 = smem_desc_sw128(smem_u32(smem + cfg::OFF_QK), 0, 1024);                       // q~ K-major, stage 0
-            const uint64_t dKmn0 = smem_desc_sw128(smem_u32(smem + cfg::OFF_QK) + 8192, cfg::QK_BLK, 1024);    // k~ MN-major, stage 0
-            const uint64_t dV = smem_desc_sw128(v_tile, 8192, 1024);                                           // v  MN-major
-            const uint64_t dP = smem_desc_sw128(p_tile, 0, 1024);                                              // P  K-major
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1;
-                const uint64_t st_off = (uint64_t)((s * cfg::QK_BYTES) >> 4);
-                const uint64_t dQ = dQ0 + st_off, dKmn = dKmn0 + st_off;
+                const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
                 wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
+                wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
+                tc_fence_after();
+                TRACE(2, n, 0);
+                // (0) P = [q~;k~] k~^T
+#pragma unroll 4
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const uint32_t a = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
+                    mma_ss(tmem + COL_P, smem_desc_sw128(a, 0, 1024), smem_desc_sw128(a + 8192, 0, 1024), id_p, ks > 0);
+                }
+                mma_commit(&bars[B_P_FULL]);
                 wait_bar(&bars[B_SA_FULL], n & 1);
                 wait_bar(&bars[B_O_EMPTY], (n & 1) ^ 1);
                 tc_fence_after();
                 TRACE(2, n, 1);
                 // (1) OT = SA q~^T   (A from TMEM)
-#pragma unroll
-                for (int ks = 0; ks < K / 16; ++ks)
-                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, dQ + (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4),
-                           id_p, ks > 0);
+#pragma unroll 4
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const uint32_t b = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
+                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, smem_desc_sw128(b, 0, 1024), id_p, ks > 0);
+                }
                 wait_bar(&bars[B_PS_FULL], n & 1);
                 wait_bar(&bars[B_V_FULL], n & 1);
                 tc_fence_after();
@@ -309,45 +286,19 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 // (2) OT += v^T P^T
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks)
-                    mma_ss(tmem + COL_OT, dV + (uint64_t)((ks * 2048) >> 4), dP + (uint64_t)((ks * 32) >> 4), id_o, 1);
+                    mma_ss(tmem + COL_OT, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
+                           smem_desc_sw128(p_tile + ks * 32, 0, 1024), id_o, 1);
                 mma_commit(&bars[B_O_FULL]);
                 mma_commit(&bars[B_PS_EMPTY]);
                 // (3) ST += v^T k~
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks)
-                    mma_ss(tmem + COL_ST, dV + (uint64_t)((ks * 2048) >> 4), dKmn + (uint64_t)((ks * 2048) >> 4), id_s, 1);
+                    mma_ss(tmem + COL_ST, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
+                           smem_desc_sw128(qk_tile + 8192 + ks * 2048, cfg::QK_BLK, 1024), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY]);
                 TRACE(2, n, 3);
-                // refill what these MMAs free (they complete within a few hundred cycles; the state pass of this
-                // item runs meanwhile, so this thread is otherwise idle)
-                if (n + 1 < n_items) load_v(n + 1);
-                if (n + 2 < n_items) load_raw(n + 2);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 19) {
-        // ====================== score MMA issuer (one thread): (0) P = [q~;k~] k~^T ======================
-        if (lane == 0) {
-            const uint32_t id_p = idesc_bf16(128, 64, 0, 0);
-            const uint64_t dA0 = smem_desc_sw128(smem_u32(smem + cfg::OFF_QK), 0, 1024);            // [q~;k~] K-major, stage 0
-            const uint64_t dB0 = smem_desc_sw128(smem_u32(smem + cfg::OFF_QK) + 8192, 0, 1024);     // k~ K-major, stage 0
-            for (int n = 0; n < n_items; ++n) {
-                const int s = n & 1;
-                const uint64_t st_off = (uint64_t)((s * cfg::QK_BYTES) >> 4);
-                const uint64_t dA = dA0 + st_off, dB = dB0 + st_off;
-                wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
-                wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
-                tc_fence_after();
-                TRACE(2, n, 0);
-#pragma unroll
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
-                    mma_ss(tmem + COL_P, dA + off, dB + off, id_p, ks > 0);
-                }
-                mma_commit(&bars[B_P_FULL]);
-                mma_commit(&bars[B_QK_EMPTY0 + s]);
             }
         }
         __syncwarp();
@@ -442,17 +393,28 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             if (r == 0) TRACE(5, n, 0);
             const float *dv = dvec + (n % 3) * K;
             const bool last = n == n_items - 1;
-            // two column blocks in flight: the TMEM load of block cb+1 overlaps the scale / pack / store of block cb
-            uint32_t fa[32], fb[32];
-            tmem_ld32(tmem + lane_addr + COL_ST, fa);
 #pragma unroll 1
-            for (int cb = 0; cb < K / 32; cb += 2) {
+            for (int cb = 0; cb < K / 32; ++cb) {
+                uint32_t f[32], pk[16];
+                tmem_ld32(tmem + lane_addr + COL_ST + cb * 32, f);
                 tmem_ld_wait();
-                tmem_ld32(tmem + lane_addr + COL_ST + (cb + 1) * 32, fb);
-                scale_store(fa, dv + cb * 32, tmem + lane_addr, cb, last, ht, sbase, V);
-                tmem_ld_wait();
-                if (cb + 2 < K / 32) tmem_ld32(tmem + lane_addr + COL_ST + (cb + 2) * 32, fa);
-                scale_store(fb, dv + (cb + 1) * 32, tmem + lane_addr, cb + 1, last, ht, sbase, V);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 d4 = *reinterpret_cast<const float4 *>(dv + cb * 32 + j);
+                    f[j + 0] = __float_as_uint(__uint_as_float(f[j + 0]) * d4.x);
+                    f[j + 1] = __float_as_uint(__uint_as_float(f[j + 1]) * d4.y);
+                    f[j + 2] = __float_as_uint(__uint_as_float(f[j + 2]) * d4.z);
+                    f[j + 3] = __float_as_uint(__uint_as_float(f[j + 3]) * d4.w);
+                }
+                if (!last) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
+                    tmem_st32(tmem + lane_addr + COL_ST + cb * 32, f);
+                    tmem_st16(tmem + lane_addr + COL_SA + cb * 16, pk);
+                } else if (ht != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ht[sbase + (size_t)(cb * 32 + j) * V] = __uint_as_float(f[j]);
+                }
             }
             tmem_st_wait();
             tc_fence_before();

@@ -9,8 +9,10 @@ from lina_speech_b200.codec import WavTokenizer
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 750
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+prec = sys.argv[4] if len(sys.argv) > 4 else "fp32"
 torch.manual_seed(0)
 wt = WavTokenizer.from_hparams().cuda().eval()
+wt.gemm_precision = prec
 with torch.no_grad():
     wt.feature_extractor.encodec.quantizer.vq.layers[0]._codebook.embed.normal_()
 codes = torch.randint(0, 4096, (1, B, L), device="cuda")
@@ -25,5 +27,5 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(json.dumps({"B": B, "L": L, "ms": ms, "frames_per_s": B * L / ms * 1e3, "audio_s_per_s": B * L / 75 / ms * 1e3,
+print(json.dumps({"gemm_precision": prec, "B": B, "L": L, "ms": ms, "frames_per_s": B * L / ms * 1e3, "audio_s_per_s": B * L / 75 / ms * 1e3,
                   "wav_shape": list(wav.shape), "finite": bool(torch.isfinite(wav).all())}))

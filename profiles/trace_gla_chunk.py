@@ -20,7 +20,7 @@ t0 = int(t[t > 0].min())
 names = ["prep", "load", "mma", "mask", "epi", "corr"]
 ev = {"prep": ["start", "end"], "load": ["start", "issued", "landed"], "mma": ["(0)", "(1)", "(2)", "done"],
       "mask": ["start", "end"], "epi": ["start", "end"], "corr": ["start", "end"]}
-for n in list(range(0, 8)) + [16, 17, 30, 31]:
+for n in list(range(0, 4)) + list(range(14, 24)) + [30, 31]:
     parts = []
     for r, nm in enumerate(names):
         vals = [int(t[r, n, e]) - t0 for e in range(len(ev[nm]))]

@@ -67,3 +67,14 @@ def test_istft_head_alone_against_torch_irfft():
     ref = CO.istft_head(sd, x.cpu(), 320)
     err = (wav.cpu() - ref).abs().max().item()
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), f"istft max err {err:.3e} (ref absmax {ref.abs().max():.2f})"
+
+
+def test_tf32_gemm_mode_stays_close(golden_codec):
+    """gemm_precision='tf32' only changes the library GEMMs / convolutions; the waveform stays within TF32 error."""
+    wt, sd = _wt(golden_codec)
+    wt.gemm_precision = "tf32"
+    codes, bw = golden_codec["L40_codes"].to(DEV), golden_codec["L40_bw"].to(DEV)
+    wav = wt.decode(wt.codes_to_features(codes), bandwidth_id=bw)
+    ref = golden_codec["L40_wav"]
+    err = (wav.cpu() - ref).abs().max().item()
+    assert err <= 3e-2 * max(1.0, ref.abs().max().item()), f"tf32 wav max err {err:.3e}"
