@@ -247,9 +247,16 @@ def main_ours(args):
     alg_flops = B * H * T * (4 * K * V + 64 * (K + V))               # SURVEY 8(d), C = 64
     pk = peaks()
     uses_tc = bool(_lib.lib().lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, _lib.BF16))
+    traffic = None                                   # DRAM bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if uses_tc and os.path.exists(tpath) and (B, H, T, K, V) == (32, 4, 2048, 256, 512):
+        with open(tpath) as f:
+            t = json.load(f).get("gla_chunk_fwd_sm100_kernel<256>")
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roofline = {"kernel": "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)",
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["src"],
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"],
                 "launch_ms": k_ms, "launches_timed": len(kern_ms), "share_of_step": sum(kern_ms) / ms,
                 "algorithmic_bytes": alg_bytes, "tensor_achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
                 "tensor_frac_of_sustained": alg_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}

@@ -100,6 +100,14 @@ int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk
                   int B, int H, int K, int V, int W, int dtype, int state_dtype,
                   float scale, float gate_normalizer, float eps, void *stream);
 
+/* Same, reading xq, xk, xv, g as column slices of ONE projection buffer with row stride `ldx` elements (the
+ * output of a single [q;k;v;g;..] GEMM) and gk_raw with row stride `ldg`; 0 = dense.  Saves the split copies. */
+int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                     const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                     void *S, const void *norm_w, void *out, void *ws,
+                     int B, int H, int K, int V, int W, int dtype, int state_dtype,
+                     float scale, float gate_normalizer, float eps, int ldx, int ldg, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.
  * Replaces causal_conv1d_fn / causal_conv1d_update (causal-conv1d 1.3.0.post1, call sites

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "lina_gla_chunk_fwd_uses_tensor_cores": (_i, [_i] * 6),
     "lina_gla_step_workspace_bytes": (_sz, [_i] * 4),
     "lina_gla_step": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_p]),
+    "lina_gla_step_ld": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_i, _i, _p]),
     "lina_short_conv_fwd": (_i, [_p] * 4 + [_i] * 7 + [_p]),
     "lina_short_conv_bwd": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "lina_short_conv_update": (_i, [_p, _p, _i, _p, _p] + [_i] * 5 + [_p]),

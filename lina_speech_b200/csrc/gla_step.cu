@@ -21,7 +21,7 @@ __global__ void gla_step_prep_kernel(const T *__restrict__ xq, const T *__restri
                                      const T *__restrict__ wk, const T *__restrict__ wv, CT *__restrict__ cq,
                                      CT *__restrict__ ck, CT *__restrict__ cv, float *__restrict__ qf,
                                      float *__restrict__ kf, float *__restrict__ ef, float *__restrict__ vf,
-                                     int B, int HK, int HV, int W, float scale, float inv_norm) {
+                                     int B, int HK, int HV, int W, float scale, float inv_norm, int ld_qk, int ld_v, int ldg) {
     const int per_b = 3 * HK + HV;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * per_b) return;
@@ -29,15 +29,15 @@ __global__ void gla_step_prep_kernel(const T *__restrict__ xq, const T *__restri
     int c = (int)(i - (long long)b * per_b);
     if (c >= 2 * HK + HV) {                         // gate channel
         c -= 2 * HK + HV;
-        const float x = to_f(gk_raw[(size_t)b * HK + c]);
+        const float x = to_f(gk_raw[(size_t)b * ldg + c]);
         ef[(size_t)b * HK + c] = expf(logsigmoidf_(x) * inv_norm);
         return;
     }
-    const T *x; const T *w; CT *cache; float *out; int D; float mul = 1.f;
-    if (c < HK) { x = xq; w = wq; cache = cq; out = qf; D = HK; mul = scale; }
-    else if (c < 2 * HK) { c -= HK; x = xk; w = wk; cache = ck; out = kf; D = HK; }
-    else { c -= 2 * HK; x = xv; w = wv; cache = cv; out = vf; D = HV; }
-    float y = to_f(x[(size_t)b * D + c]);
+    const T *x; const T *w; CT *cache; float *out; int D, ld; float mul = 1.f;
+    if (c < HK) { x = xq; w = wq; cache = cq; out = qf; D = HK; ld = ld_qk; mul = scale; }
+    else if (c < 2 * HK) { c -= HK; x = xk; w = wk; cache = ck; out = kf; D = HK; ld = ld_qk; }
+    else { c -= 2 * HK; x = xv; w = wv; cache = cv; out = vf; D = HV; ld = ld_v; }
+    float y = to_f(x[(size_t)b * ld + c]);
     if (w != nullptr) {
         // cache <- roll(cache, -1); cache[-1] = x; y = silu(sum_j cache[j] * w[j])   (convolution.py:197-204)
         CT *cp = cache + ((size_t)b * D + c) * W;
@@ -147,27 +147,42 @@ gla_step_state_kernel(ST *__restrict__ S, const float *__restrict__ qf, const fl
     }
 }
 
-// RMSNorm over V of o (fp32 scratch) * w * swish(g); one warp per (b,h) row.
+// RMSNorm over V of o (fp32 scratch) * w * swish(g); one CTA per (b,h) row, 4 consecutive columns per thread.
 template <typename T>
-__global__ void gla_step_norm_kernel(const float *__restrict__ of, const T *__restrict__ g,
-                                     const T *__restrict__ w, T *__restrict__ out, int rows, int V, float eps) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+__global__ void __launch_bounds__(256)
+gla_step_norm_kernel(const float *__restrict__ of, const T *__restrict__ g, const T *__restrict__ w,
+                     T *__restrict__ out, int V, float eps, int H, int ld_v) {
+    __shared__ float red[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const int b = row / H, h = row - b * H;
     const float *x = of + (size_t)row * V;
+    const T *gr = g + (size_t)b * ld_v + (size_t)h * V;
+    T *orow = out + (size_t)row * V;
+    float xv[4][4];
     float ss = 0.f;
-    for (int i = lane; i < V; i += 32) {
+    int nblk = 0;
+    for (int c0 = tid * 4; c0 < V && nblk < 4; c0 += blockDim.x * 4, ++nblk) {
+        const float4 t = *reinterpret_cast<const float4 *>(x + c0);
         // the reference's GLA op returns o in the activation dtype before the norm
-        const float xv = to_f(from_f<T>(x[i]));
-        ss = fmaf(xv, xv, ss);
+        xv[nblk][0] = to_f(from_f<T>(t.x)); xv[nblk][1] = to_f(from_f<T>(t.y));
+        xv[nblk][2] = to_f(from_f<T>(t.z)); xv[nblk][3] = to_f(from_f<T>(t.w));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ss = fmaf(xv[nblk][i], xv[nblk][i], ss);
     }
     ss = warp_sum(ss);
-    const float rstd = rsqrtf(ss / (float)V + eps);
-    for (int i = lane; i < V; i += 32) {
-        const float xv = to_f(from_f<T>(x[i]));
-        const float gv = to_f(g[(size_t)row * V + i]);
-        const float wv = w != nullptr ? to_f(w[i]) : 1.f;
-        out[(size_t)row * V + i] = from_f<T>(xv * rstd * wv * gv * sigmoidf_(gv));
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    const float rstd = rsqrtf(tot / (float)V + eps);
+    nblk = 0;
+    for (int c0 = tid * 4; c0 < V && nblk < 4; c0 += blockDim.x * 4, ++nblk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float gv = to_f(gr[c0 + i]);
+            const float wv = w != nullptr ? to_f(w[c0 + i]) : 1.f;
+            orow[c0 + i] = from_f<T>(xv[nblk][i] * rstd * wv * gv * sigmoidf_(gv));
+        }
     }
 }
 
@@ -175,21 +190,24 @@ template <typename T, typename CT>
 int launch_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g, const void *wq,
                 const void *wk, const void *wv, void *cq, void *ck, void *cv, void *S, const void *norm_w,
                 void *out, float *ws, int B, int H, int K, int V, int W, float scale, float gate_normalizer,
-                float eps, cudaStream_t st) {
+                float eps, int ld_qk, int ld_v, int ldg, cudaStream_t st) {
     const int HK = H * K, HV = H * V;
     float *qf = ws, *kf = qf + (size_t)B * HK, *ef = kf + (size_t)B * HK, *vf = ef + (size_t)B * HK,
           *of = vf + (size_t)B * HV;
     const long long n1 = (long long)B * (3 * HK + HV);
     gla_step_prep_kernel<T, CT><<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(
         (const T *)xq, (const T *)xk, (const T *)xv, (const T *)gk_raw, (const T *)wq, (const T *)wk,
-        (const T *)wv, (CT *)cq, (CT *)ck, (CT *)cv, qf, kf, ef, vf, B, HK, HV, W, scale, 1.f / gate_normalizer);
+        (const T *)wv, (CT *)cq, (CT *)ck, (CT *)cv, qf, kf, ef, vf, B, HK, HV, W, scale, 1.f / gate_normalizer,
+        ld_qk, ld_v, ldg);
     LINA_LAUNCH_OK("gla_step_prep_kernel");
     constexpr int VEC = sizeof(CT) == 4 ? 4 : 8;
     dim3 grid((V + 32 * VEC - 1) / (32 * VEC), B * H);
     gla_step_state_kernel<CT, VEC><<<grid, SW * 32, 0, st>>>((CT *)S, qf, kf, ef, vf, of, K, V);
     LINA_LAUNCH_OK("gla_step_state_kernel");
     const int rows = B * H;
-    gla_step_norm_kernel<T><<<(rows + 7) / 8, 256, 0, st>>>(of, (const T *)g, (const T *)norm_w, (T *)out, rows, V, eps);
+    int nt = ((V / 4 + 31) / 32) * 32;           // V % 4 == 0 (checked); up to 4 float4 per thread -> V <= 4096
+    if (nt > 256) nt = 256;
+    gla_step_norm_kernel<T><<<rows, nt, 0, st>>>(of, (const T *)g, (const T *)norm_w, (T *)out, V, eps, H, ld_v);
     LINA_LAUNCH_OK("gla_step_norm_kernel");
     return LINA_OK;
 }
@@ -200,11 +218,13 @@ extern "C" size_t lina_gla_step_workspace_bytes(int B, int H, int K, int V) {
     return ((size_t)3 * B * H * K + (size_t)2 * B * H * V) * sizeof(float);
 }
 
-extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
-                             const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
-                             void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
-                             int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
-                             void *stream) {
+// ldx: common row stride (elements) of xq, xk, xv, g when they are column slices of ONE projection buffer
+// (0 = each tensor dense); ldg: row stride of gk_raw (0 = dense).
+extern "C" int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                                const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                                void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
+                                int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
+                                int ldx, int ldg, void *stream) {
     LINA_REQUIRE(B > 0 && H > 0 && K > 0 && V > 0, LINA_ERR_BAD_ARG, "gla_step: non-positive size");
     LINA_REQUIRE(xq && xk && xv && gk_raw && g && S && out && ws, LINA_ERR_BAD_ARG, "gla_step: null pointer");
     const bool conv = wq != nullptr;
@@ -217,9 +237,13 @@ extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, con
     LINA_REQUIRE(V % (state_dtype == LINA_F32 ? 4 : 8) == 0, LINA_ERR_UNSUPPORTED,
                  "gla_step: V=%d must be a multiple of %d", V, state_dtype == LINA_F32 ? 4 : 8);
     LINA_REQUIRE(gate_normalizer != 0.f, LINA_ERR_BAD_ARG, "gla_step: zero gate normalizer");
+    LINA_REQUIRE(V <= 4096, LINA_ERR_UNSUPPORTED, "gla_step: V=%d > 4096 not implemented", V);
+    LINA_REQUIRE(ldx == 0 || ldx >= H * V, LINA_ERR_BAD_ARG, "gla_step: ldx=%d smaller than a row", ldx);
+    LINA_REQUIRE(ldg == 0 || ldg >= H * K, LINA_ERR_BAD_ARG, "gla_step: ldg=%d smaller than a row", ldg);
+    const int ld_qk = ldx ? ldx : H * K, ld_v = ldx ? ldx : H * V, lg = ldg ? ldg : H * K;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO_(T, CT) return launch_step<T, CT>(xq, xk, xv, gk_raw, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, \
-                                             (float *)ws, B, H, K, V, W, scale, gate_normalizer, eps, st)
+                                             (float *)ws, B, H, K, V, W, scale, gate_normalizer, eps, ld_qk, ld_v, lg, st)
     if (dtype == LINA_F32 && state_dtype == LINA_F32) GO_(float, float);
     if (dtype == LINA_BF16 && state_dtype == LINA_BF16) GO_(bf16, bf16);
     if (dtype == LINA_BF16 && state_dtype == LINA_F32) GO_(bf16, float);
@@ -227,4 +251,13 @@ extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, con
 #undef GO_
     lina_set_error("gla_step: dtype %d / state dtype %d combination not implemented", dtype, state_dtype);
     return LINA_ERR_UNSUPPORTED;
+}
+
+extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                             const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                             void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
+                             int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
+                             void *stream) {
+    return lina_gla_step_ld(xq, xk, xv, gk_raw, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, ws, B, H, K, V, W, dtype,
+                            state_dtype, scale, gate_normalizer, eps, 0, 0, stream);
 }

@@ -101,7 +101,7 @@ class GatedLinearAttention(nn.Module):
         proj = F.linear(x.view(B, -1), self._cat_weight())
         xq, xk, xv, g, lo = torch.split(proj, [kd, kd, vd, vd, proj.shape[1] - 2 * kd - 2 * vd], dim=1)
         gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
-        xq, xk, xv, g = xq.contiguous(), xk.contiguous(), xv.contiguous(), g.contiguous()
+        ldx = proj.shape[1]                            # the four slices are read in place with this row stride
         if self.use_short_conv:
             cq, ck, cv, S = state
             W = self.conv_size
@@ -119,10 +119,11 @@ class GatedLinearAttention(nn.Module):
         ws = torch.empty(int(lib.lina_gla_step_workspace_bytes(B, H, K, V)), dtype=torch.uint8, device=x.device)
         nw = self.g_norm_swish_gate.weight
         nw = nw.to(x.dtype) if nw is not None else None
-        rc = lib.lina_gla_step(L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(gk_raw), L.ptr(g), L.ptr(wq), L.ptr(wk),
-                               L.ptr(wv), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.ptr(S), L.ptr(nw), L.ptr(out),
-                               L.ptr(ws), B, H, K, V, W, L.dt(x), L.dt(S), float(K) ** -0.5,
-                               float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), L.stream(x))
+        rc = lib.lina_gla_step_ld(L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(gk_raw), L.ptr(g), L.ptr(wq), L.ptr(wk),
+                                  L.ptr(wv), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.ptr(S), L.ptr(nw), L.ptr(out),
+                                  L.ptr(ws), B, H, K, V, W, L.dt(x), L.dt(S), float(K) ** -0.5,
+                                  float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), ldx,
+                                  gk_raw.stride(0), L.stream(x))
         L.count_launches(3)
         L.check(rc, "lina_gla_step")
         return self.o_proj(out).view(B, 1, -1)
