@@ -59,6 +59,14 @@ int lina_gla_recurrent_bwd(const void *q, const void *k, const void *v, const vo
                            void *dq, void *dk, void *dv, void *dgk, float *dh0, void *ws,
                            int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
 
+/* RWKV6 variant of the recurrence, forward only (secondary row a13: reachable only from the reference's stale
+ * model/rwkv6.py).  o_t = scale * r_t (S_{t-1} + diag(u) k_t^T v_t) ; S_t = diag(exp(w_t)) S_{t-1} + k_t^T v_t, u [H,K].
+ * Replaces fla.ops.rwkv6.fused_recurrent_rwkv6 / chunk_rwkv6 forward (FLA/fla/ops/rwkv6/recurrent_fuse.py:335-368,
+ * FLA/fla/ops/rwkv6/chunk.py:803-); spec FLA/fla/ops/rwkv6/recurrent_naive.py:8-42. */
+int lina_rwkv6_recurrent_fwd(const void *r, const void *k, const void *v, const void *w, const void *u,
+                             const void *h0, int h0_dtype, void *o, float *ht,
+                             int B, int H, int T, int K, int V, int dtype, float scale, void *stream);
+
 /* Chunkwise-parallel forward of the same function -- the tensor-core path.
  * Replaces fla.ops.gla.fused_chunk_gla (FLA/fla/ops/gla/chunk_fuse.py:518-536) and
  * fla.ops.gla.chunk_gla (FLA/fla/ops/gla/chunk.py:453-491); same contract as

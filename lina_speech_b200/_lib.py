@@ -24,6 +24,7 @@ PROTOTYPES = {
     "lina_abi_version": (_i, []),
     "lina_last_error_string": (C.c_char_p, []),
     "lina_gla_recurrent_fwd": (_i, [_p] * 5 + [_i, _p, _p] + [_i] * 6 + [_f, _p]),
+    "lina_rwkv6_recurrent_fwd": (_i, [_p] * 6 + [_i, _p, _p] + [_i] * 6 + [_f, _p]),
     "lina_gla_recurrent_bwd_workspace_bytes": (_sz, [_i] * 5),
     "lina_gla_recurrent_bwd": (_i, [_p] * 5 + [_i] + [_p] * 8 + [_i] * 6 + [_f, _p]),
     "lina_gla_chunk_fwd_workspace_bytes": (_sz, [_i] * 6),

@@ -77,47 +77,64 @@ groupnorm_swish_kernel(const float *__restrict__ x, const float *__restrict__ ga
 
 // ------------------------------------------------------------------------------------------------
 // depthwise conv k=7 (optional) + transpose [B,C,L]->[B,L,C] + LayerNorm(no affine)*scale+shift.
-constexpr int TL = 16;     // time steps per CTA
-constexpr int CCH = 64;    // channels staged per round
-__global__ void __launch_bounds__(256)
+// One CTA = one (batch, tile of TL time steps) x ALL channels.  Every channel row of the tile is one 128-byte
+// warp load (32 floats: TL = 26 outputs + 6 halo with the conv, TL = 32 without), all rows are requested before
+// any is used, the conv runs out of shared memory, the transposed tile is normalised by one warp per time step
+// and written as full contiguous rows of [B,L,C].
+constexpr int DW_THREADS = 512;
+template <bool CONV>
+__global__ void __launch_bounds__(DW_THREADS)
 dwconv_adaln_kernel(const float *__restrict__ x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
                     const float *__restrict__ scale, const float *__restrict__ shift, float *__restrict__ y,
                     int C, int L, float eps) {
+    constexpr int TL = CONV ? 26 : 32;
     extern __shared__ float smem[];
-    float *outs = smem;                         // [TL][C + 1]
-    float *ins = smem + TL * (C + 1);           // [CCH][TL + 6]
-    const int b = blockIdx.y, l0 = blockIdx.x * TL;
-    const int tid = threadIdx.x;
     const int CP = C + 1;
-    for (int c0 = 0; c0 < C; c0 += CCH) {
-        const int nc = min(CCH, C - c0);
-        if (dw_w != nullptr) {
-            for (int i = tid; i < nc * (TL + 6); i += 256) {
-                const int ci = i / (TL + 6), j = i - ci * (TL + 6);
-                const int l = l0 - 3 + j;
-                ins[ci * (TL + 6) + j] = (l >= 0 && l < L) ? x[((size_t)b * C + c0 + ci) * L + l] : 0.f;
-            }
-            __syncthreads();
-            for (int i = tid; i < nc * TL; i += 256) {
-                const int ci = i / TL, lt = i - ci * TL;
-                const float *w = dw_w + (size_t)(c0 + ci) * 7;
-                float acc = dw_b != nullptr ? dw_b[c0 + ci] : 0.f;
+    float *outs = smem;                         // [TL][C + 1]   (transposed tile)
+    float *ins = outs + TL * CP;                // [C][33]       (CONV only: raw rows incl. halo)
+    float *wts = ins + (CONV ? C * 33 : 0);     // [C][8]        (CONV only: 7 taps + bias)
+    const int b = blockIdx.y, l0 = blockIdx.x * TL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *xb = x + (size_t)b * C * L;
+    if (CONV) {
+        {   // 8 independent 128-byte row loads in flight per warp
+            constexpr int NW = DW_THREADS / 32, U = 8;
+            const int l = l0 - 3 + lane;
+            const bool ok = l >= 0 && l < L;
+            for (int c = warp; c < C; c += NW * U) {
+                float v[U];
 #pragma unroll
-                for (int j = 0; j < 7; ++j) acc = fmaf(w[j], ins[ci * (TL + 6) + lt + j], acc);
-                outs[lt * CP + c0 + ci] = acc;
+                for (int u = 0; u < U; ++u) { const int cc = c + u * NW; v[u] = (ok && cc < C) ? xb[(size_t)cc * L + l] : 0.f; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int cc = c + u * NW; if (cc < C) ins[cc * 33 + lane] = v[u]; }
             }
-            __syncthreads();
-        } else {
-            for (int i = tid; i < nc * TL; i += 256) {
-                const int ci = i / TL, lt = i - ci * TL;
-                const int l = l0 + lt;
-                outs[lt * CP + c0 + ci] = l < L ? x[((size_t)b * C + c0 + ci) * L + l] : 0.f;
-            }
+        }
+        for (int i = tid; i < C * 8; i += DW_THREADS) {
+            const int c = i >> 3, j = i & 7;
+            wts[i] = j < 7 ? dw_w[c * 7 + j] : (dw_b != nullptr ? dw_b[c] : 0.f);
+        }
+        __syncthreads();
+        for (int e = tid; e < C * TL; e += DW_THREADS) {
+            const int c = e / TL, lt = e - c * TL;
+            const float *w = wts + c * 8, *in = ins + c * 33 + lt;
+            float acc = w[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc = fmaf(w[j], in[j], acc);
+            outs[lt * CP + c] = acc;
+        }
+    } else {
+        constexpr int NW = DW_THREADS / 32, U = 8;
+        const int l = l0 + lane;
+        for (int c = warp; c < C; c += NW * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int cc = c + u * NW; v[u] = (l < L && cc < C) ? xb[(size_t)cc * L + l] : 0.f; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int cc = c + u * NW; if (cc < C) outs[lane * CP + cc] = v[u]; }
         }
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int lt = warp; lt < TL; lt += 8) {
+    for (int lt = warp; lt < TL; lt += DW_THREADS / 32) {
         const int l = l0 + lt;
         if (l >= L) continue;
         const float *row = outs + lt * CP;
@@ -304,15 +321,19 @@ static int launch_dwconv_adaln(const float *x, const float *dw_w, const float *d
     LINA_REQUIRE(x && scale && shift && y, LINA_ERR_BAD_ARG, "dwconv_adaln: null pointer");
     LINA_REQUIRE(B > 0 && C > 0 && L > 0, LINA_ERR_BAD_ARG, "dwconv_adaln: bad size");
     LINA_REQUIRE(B <= 65535, LINA_ERR_UNSUPPORTED, "dwconv_adaln: B > 65535");
-    const size_t smem = ((size_t)TL * (C + 1) + (size_t)CCH * (TL + 6)) * sizeof(float);
-    LINA_REQUIRE(smem <= 200 * 1024, LINA_ERR_UNSUPPORTED, "dwconv_adaln: C=%d too large for shared memory", C);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const bool conv = dw_w != nullptr;
+    const int TL = conv ? 26 : 32;
+    const size_t smem = ((size_t)TL * (C + 1) + (conv ? (size_t)C * 41 : 0)) * sizeof(float);
+    LINA_REQUIRE(smem <= 227 * 1024, LINA_ERR_UNSUPPORTED, "dwconv_adaln: C=%d too large for shared memory", C);
+    static thread_local size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[conv]) {
+        if (conv) LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[conv] = smem;
     }
     dim3 grid((L + TL - 1) / TL, B);
-    dwconv_adaln_kernel<<<grid, 256, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
+    if (conv) dwconv_adaln_kernel<true><<<grid, DW_THREADS, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
+    else dwconv_adaln_kernel<false><<<grid, DW_THREADS, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
     LINA_LAUNCH_OK("dwconv_adaln_kernel");
     return LINA_OK;
 }

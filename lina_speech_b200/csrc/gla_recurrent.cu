@@ -61,7 +61,11 @@ template <typename T, int KPW>
 __global__ void __launch_bounds__(NWARP * 32)
 gla_rec_fwd_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
                    const T *__restrict__ gk, const void *__restrict__ h0, int h0_dtype,
-                   T *__restrict__ o, float *__restrict__ ht, int Tn, int K, int V, float scale) {
+                   T *__restrict__ o, float *__restrict__ ht, int Tn, int K, int V, float scale,
+                   const T *__restrict__ u, int H) {
+    // u != nullptr selects the RWKV6 form (FLA/fla/ops/rwkv6/recurrent_naive.py:30-39): the output is taken
+    // BEFORE the state update and the current token enters through the bonus u[h,k]:
+    //     o_t = scale * q_t (S_{t-1} + diag(u) k_t^T v_t) ;  S_t = diag(exp(w_t)) S_{t-1} + k_t^T v_t
     constexpr int KP = NWARP * KPW;
     __shared__ __align__(16) float sq[TS][KP];
     __shared__ __align__(16) float sk[TS][KP];
@@ -77,12 +81,14 @@ gla_rec_fwd_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__
     const T *qb = q + qoff, *kb = k + qoff, *gb = gk + qoff, *vb = v + voff;
     T *ob = o + voff;
 
-    float S[KPW];
+    float S[KPW], ub[KPW];
 #pragma unroll
     for (int j = 0; j < KPW; ++j) {
         const int kk = warp * KPW + j;
         S[j] = (h0 != nullptr && kk < K && vok) ? load_dyn(h0, h0_dtype, soff + (size_t)kk * V + vcol) : 0.f;
+        ub[j] = (u != nullptr && kk < K) ? to_f(u[(size_t)(bh % H) * K + kk]) : 0.f;
     }
+    const bool rwkv = u != nullptr;
 
     for (int t0 = 0; t0 < Tn; t0 += TS) {
         for (int i = tid; i < TS * KP; i += NWARP * 32) {
@@ -111,10 +117,18 @@ gla_rec_fwd_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__
                 const float4 e4 = *reinterpret_cast<const float4 *>(&se[s][kk]);
                 const float4 k4 = *reinterpret_cast<const float4 *>(&sk[s][kk]);
                 const float4 q4 = *reinterpret_cast<const float4 *>(&sq[s][kk]);
-                S[j + 0] = fmaf(S[j + 0], e4.x, k4.x * vv); acc = fmaf(q4.x, S[j + 0], acc);
-                S[j + 1] = fmaf(S[j + 1], e4.y, k4.y * vv); acc = fmaf(q4.y, S[j + 1], acc);
-                S[j + 2] = fmaf(S[j + 2], e4.z, k4.z * vv); acc = fmaf(q4.z, S[j + 2], acc);
-                S[j + 3] = fmaf(S[j + 3], e4.w, k4.w * vv); acc = fmaf(q4.w, S[j + 3], acc);
+                if (!rwkv) {
+                    S[j + 0] = fmaf(S[j + 0], e4.x, k4.x * vv); acc = fmaf(q4.x, S[j + 0], acc);
+                    S[j + 1] = fmaf(S[j + 1], e4.y, k4.y * vv); acc = fmaf(q4.y, S[j + 1], acc);
+                    S[j + 2] = fmaf(S[j + 2], e4.z, k4.z * vv); acc = fmaf(q4.z, S[j + 2], acc);
+                    S[j + 3] = fmaf(S[j + 3], e4.w, k4.w * vv); acc = fmaf(q4.w, S[j + 3], acc);
+                } else {
+                    const float kv0 = k4.x * vv, kv1 = k4.y * vv, kv2 = k4.z * vv, kv3 = k4.w * vv;
+                    acc = fmaf(q4.x, fmaf(ub[j + 0], kv0, S[j + 0]), acc); S[j + 0] = fmaf(S[j + 0], e4.x, kv0);
+                    acc = fmaf(q4.y, fmaf(ub[j + 1], kv1, S[j + 1]), acc); S[j + 1] = fmaf(S[j + 1], e4.y, kv1);
+                    acc = fmaf(q4.z, fmaf(ub[j + 2], kv2, S[j + 2]), acc); S[j + 2] = fmaf(S[j + 2], e4.z, kv2);
+                    acc = fmaf(q4.w, fmaf(ub[j + 3], kv3, S[j + 3]), acc); S[j + 3] = fmaf(S[j + 3], e4.w, kv3);
+                }
             }
             so[s][warp][lane] = acc;
         }
@@ -335,10 +349,11 @@ gla_rec_bwd_finalize_kernel(const T *__restrict__ q, const T *__restrict__ k,
 
 template <typename T>
 int launch_fwd(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype,
-               void *o, float *ht, int B, int H, int Tn, int K, int V, float scale, cudaStream_t st) {
+               void *o, float *ht, int B, int H, int Tn, int K, int V, float scale, cudaStream_t st,
+               const void *u = nullptr) {
     dim3 grid((V + BV - 1) / BV, B * H), block(NWARP * 32);
 #define L_(KPW) gla_rec_fwd_kernel<T, KPW><<<grid, block, 0, st>>>((const T *)q, (const T *)k, (const T *)v, \
-        (const T *)gk, h0, h0_dtype, (T *)o, ht, Tn, K, V, scale)
+        (const T *)gk, h0, h0_dtype, (T *)o, ht, Tn, K, V, scale, (const T *)u, H)
     if (K <= 32) L_(4); else if (K <= 64) L_(8); else if (K <= 128) L_(16); else L_(32);
 #undef L_
     LINA_LAUNCH_OK("gla_rec_fwd_kernel");
@@ -394,6 +409,19 @@ extern "C" int lina_gla_recurrent_fwd(const void *q, const void *k, const void *
                                       const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T,
                                       int K, int V, int dtype, float scale, void *stream) {
     return lina_gla_recurrent_fwd_impl(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, K, V, dtype, scale, stream);
+}
+
+// RWKV6 recurrence, forward (FLA/fla/ops/rwkv6/recurrent_fuse.py:335-368 -> kernel :16-82; spec recurrent_naive.py:8-42)
+extern "C" int lina_rwkv6_recurrent_fwd(const void *r, const void *k, const void *v, const void *w, const void *u,
+                                        const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T, int K,
+                                        int V, int dtype, float scale, void *stream) {
+    int rc = check_dims(B, H, T, K, V, dtype);
+    if (rc) return rc;
+    LINA_REQUIRE(r && k && v && w && u && o, LINA_ERR_BAD_ARG, "rwkv6_recurrent_fwd: null tensor pointer");
+    LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "rwkv6_recurrent_fwd: bad h0 dtype");
+    LINA_DISPATCH_DTYPE(dtype, return launch_fwd<T_>(r, k, v, w, h0, h0_dtype, o, ht, B, H, T, K, V, scale,
+                                                      (cudaStream_t)stream, u));
+    return LINA_OK;
 }
 
 extern "C" size_t lina_gla_recurrent_bwd_workspace_bytes(int B, int H, int T, int K, int V) {

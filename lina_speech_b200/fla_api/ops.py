@@ -169,3 +169,34 @@ def chunk_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor
     cached between forward and backward here, which is level 2's behaviour)."""
     assert checkpoint_level in [0, 1, 2]
     return _GLAFunction.apply(q, k, v, g, _scale(scale, q.shape[-1]), initial_state, output_final_state, "chunk")
+
+
+def fused_recurrent_rwkv6(r: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w: torch.Tensor, u: torch.Tensor,
+                          scale: float = -1, initial_state: torch.Tensor = None, output_final_state: bool = False
+                          ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """FLA/fla/ops/rwkv6/recurrent_fuse.py:335-368, forward only (inference): ``w`` are log-space decays, ``u`` [H,K]
+    the bonus.  Gradients are not implemented (the only caller, model/rwkv6.py, is stale upstream -- SURVEY D6)."""
+    if any(t.requires_grad for t in (r, k, v, w, u)) and torch.is_grad_enabled():
+        raise NotImplementedError("lina_speech_b200.fused_recurrent_rwkv6 is forward-only")
+    L.require_cuda(r, k, v, w, u, initial_state)
+    odt = v.dtype
+    if not (r.dtype == k.dtype == v.dtype == w.dtype == u.dtype):
+        r, k, v, w, u = (x.float() for x in (r, k, v, w, u))
+    r, k, v, w, u = (x.contiguous() for x in (r, k, v, w, u))
+    B, H, T, K = r.shape
+    V = v.shape[-1]
+    h0 = initial_state.contiguous() if initial_state is not None else None
+    o = torch.empty_like(v)
+    ht = torch.empty(B, H, K, V, dtype=torch.float32, device=r.device) if output_final_state else None
+    rc = L.lib().lina_rwkv6_recurrent_fwd(L.ptr(r), L.ptr(k), L.ptr(v), L.ptr(w), L.ptr(u), L.ptr(h0),
+                                          L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V,
+                                          L.dt(r), _scale(scale, K), L.stream(r))
+    L.count_launches(1)
+    L.check(rc, "lina_rwkv6_recurrent_fwd")
+    return o.to(odt), ht
+
+
+def chunk_rwkv6(r, k, v, g, u, scale: float = -1, initial_state=None, output_final_state: bool = False,
+                checkpoint_level: Optional[int] = 0):
+    """FLA/fla/ops/rwkv6/chunk.py:803- : same function as the recurrent form; served by the same kernel."""
+    return fused_recurrent_rwkv6(r, k, v, g, u, scale, initial_state, output_final_state)

@@ -50,6 +50,27 @@ def recurrent_gla(q, k, v, gk, scale: Optional[float] = None, initial_state=None
     return o.to(odt), (S.to(torch.float32) if output_final_state else None)
 
 
+def recurrent_rwkv6(r, k, v, w, u, scale: Optional[float] = None, initial_state=None,
+                    output_final_state: bool = True, acc_dtype=torch.float32):
+    """RWKV6 form (FLA/fla/ops/rwkv6/recurrent_naive.py:8-42): output BEFORE the update, current token through the
+    bonus: o_t = scale * r_t (S_{t-1} + diag(u) k_t^T v_t) ; S_t = diag(exp(w_t)) S_{t-1} + k_t^T v_t ; u [H,K]."""
+    odt = v.dtype
+    r, k, v, w, u = (x.to(acc_dtype) for x in (r, k, v, w, u))
+    B, H, T, K = r.shape
+    V = v.shape[-1]
+    if scale is None or scale == -1:
+        scale = K ** -0.5
+    S = torch.zeros(B, H, K, V, dtype=acc_dtype)
+    if initial_state is not None:
+        S = S + initial_state.to(acc_dtype)
+    o = torch.empty(B, H, T, V, dtype=acc_dtype)
+    for t in range(T):
+        kv = k[:, :, t].unsqueeze(-1) * v[:, :, t].unsqueeze(-2)
+        o[:, :, t] = torch.einsum("bhk,bhkv->bhv", r[:, :, t] * scale, S + u[None, :, :, None] * kv)
+        S = S * w[:, :, t].exp().unsqueeze(-1) + kv
+    return o.to(odt), (S.to(torch.float32) if output_final_state else None)
+
+
 def recurrent_gla_bwd(q, k, v, gk, h0, do, dht=None, scale: Optional[float] = None,
                       acc_dtype=torch.float64):
     """Explicit backward of :func:`recurrent_gla`.

@@ -295,9 +295,32 @@ def gen_codec():
     save("codec_small.npz", **out)
 
 
+# ----------------------------------------------------------------------------
+# 5. RWKV6 recurrence (secondary row a13): FLA/fla/ops/rwkv6/recurrent_naive.py
+# ----------------------------------------------------------------------------
+def gen_rwkv6():
+    from fla.ops.rwkv6.recurrent_naive import naive_recurrent_rwkv6
+    out = {}
+    for ci, (B, H, T, K, V, use_h0) in enumerate([(2, 2, 1, 32, 64, True), (1, 3, 37, 64, 64, False), (2, 4, 70, 64, 128, True)]):
+        torch.manual_seed(77 + ci)
+        r, k, v = torch.randn(B, H, T, K), torch.randn(B, H, T, K), torch.randn(B, H, T, V)
+        w = -torch.exp(torch.randn(B, H, T, K) - 1.0)                    # RWKV6 decays: w = -exp(.)  (FLA/fla/layers/rwkv6.py)
+        u = torch.randn(H, K)
+        h0 = torch.randn(B, H, K, V) if use_h0 else None
+        o, ht = naive_recurrent_rwkv6(r, k, v, w, u, initial_state=h0.clone() if use_h0 else None, output_final_state=True)
+        o2, ht2 = GO.recurrent_rwkv6(r, k, v, w, u, initial_state=h0)
+        close(o, o2, 1e-5, f"rwkv6[{ci}].o"); close(ht, ht2, 1e-4, f"rwkv6[{ci}].ht")
+        p = f"c{ci}_"
+        out.update({p + "r": r, p + "k": k, p + "v": v, p + "w": w, p + "u": u, p + "o": o, p + "ht": ht})
+        if use_h0:
+            out[p + "h0"] = h0
+    out["n_cases"] = 3
+    save("rwkv6_ops.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["ops", "layer", "model", "codec"]
+    which = sys.argv[1:] or ["ops", "layer", "model", "codec", "rwkv6"]
     for w in which:
         print(f"[{w}]")
-        {"ops": gen_ops, "layer": gen_layer, "model": gen_model, "codec": gen_codec}[w]()
+        {"ops": gen_ops, "layer": gen_layer, "model": gen_model, "codec": gen_codec, "rwkv6": gen_rwkv6}[w]()

@@ -234,3 +234,24 @@ def test_bthd_layout_is_read_in_place():
                              output_final_state=True)
     assert o1.shape == (B, H, T, V) and o1.transpose(1, 2).is_contiguous()
     assert torch.equal(o1, o2) and torch.equal(h1, h2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rwkv6_recurrent_forward(dtype):
+    """secondary row a13: fused_recurrent_rwkv6 / chunk_rwkv6 forward vs the reference's naive_recurrent_rwkv6 goldens."""
+    from conftest import load_golden
+    from lina_speech_b200.fla_api import fused_recurrent_rwkv6, chunk_rwkv6
+    g = load_golden("rwkv6_ops.npz")
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        args = [c[n].to(dtype).to(DEV) for n in ("r", "k", "v", "w", "u")]
+        h0 = c["h0"].to(DEV) if "h0" in c else None
+        for fn in (fused_recurrent_rwkv6, chunk_rwkv6):
+            o, ht = fn(*args, initial_state=h0, output_final_state=True)
+            if dtype == torch.float32:
+                _assert_close(o, c["o"], 1e-4, what=f"rwkv6 case {ci} o")
+                _assert_close(ht, c["ht"], 1e-4, what=f"rwkv6 case {ci} ht")
+            else:
+                ro, rh = GO.recurrent_rwkv6(*[a.float().cpu() for a in args], initial_state=c.get("h0"))
+                _assert_close(o, ro, 1e-4, 2.0 ** -7, what=f"rwkv6 bf16 case {ci} o")
+                _assert_close(ht, rh, 1e-4, 1e-3, what=f"rwkv6 bf16 case {ci} ht")

@@ -95,3 +95,23 @@ def test_step_loop_equals_forward(golden_model):
         ys, atts = zip(*[rnn.step(x[:, t:t + 1], ctx, t, cache)[:2] for t in range(T)])
     _close(torch.cat(ys, 1), y, 1e-4, what="step loop y")
     _close(torch.cat(atts, 2), att, 1e-4, what="step loop att")
+
+
+def test_initial_state_tuning_loop_reduces_the_loss(golden_model):
+    """train_initial_state (initial_state.py:85-160): Adam on the rank-1 state factors only, through the dh0 path."""
+    from lina_speech_b200.initial_state import train_initial_state, speaker_state_dict
+    lm = _tiny(golden_model)
+
+    class Tok:
+        def encode(self, s):
+            return [1] + [3 + (ord(c) % 29) for c in s[5:-5]] + [2]
+
+    torch.manual_seed(0)
+    data = [{"audio_token": torch.randint(0, 64, (1, 30)), "text": "hello world"} for _ in range(2)]
+    w0 = {k: v.clone() for k, v in lm.state_dict().items()}
+    params, losses = train_initial_state(lm, data, Tok(), n_samples=48, lr=0.05, grad_acc=2, batch_size=2, rank=1)
+    assert len(losses) == 24 and all(l == l for l in losses)
+    assert sum(losses[-4:]) / 4 < sum(losses[:4]) / 4, (losses[:4], losses[-4:])       # it learns the two utterances
+    assert all(torch.equal(w0[k], v) for k, v in lm.state_dict().items())                # weights untouched
+    sd = speaker_state_dict(params)
+    assert set(sd) == {f"layer{i}_{s}" for i in range(4) for s in "kv"} and not lm.training

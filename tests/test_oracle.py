@@ -110,3 +110,12 @@ def test_codec_matches_reference(golden_codec):
         wav = CO.decode(sd, CO.codes_to_features(sd, codes), bw)
         assert wav.shape == (codes.shape[1], 320 * Ln)
         assert torch.allclose(wav, g[f"L{Ln}_wav"], atol=1e-5, rtol=1e-5)
+
+
+def test_rwkv6_recurrence_matches_reference(request):
+    from conftest import load_golden
+    g = load_golden("rwkv6_ops.npz")
+    for ci in range(int(g["n_cases"])):
+        c = _case(g, ci)
+        o, ht = GO.recurrent_rwkv6(c["r"], c["k"], c["v"], c["w"], c["u"], initial_state=c.get("h0"))
+        assert torch.allclose(o, c["o"], atol=1e-5, rtol=1e-5) and torch.allclose(ht, c["ht"], atol=1e-4, rtol=1e-5)
