@@ -149,6 +149,11 @@ int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, cons
 int lina_gate_logsigmoid(const void *x, void *y, long long n, float normalizer, float clamp_min, int use_clamp,
                          int dtype, void *stream);
 int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtype, void *stream);
+/* sum_out = a + x ; ln_out = LayerNorm(sum_out) * gamma + beta over rows of length N (nn.LayerNorm semantics).
+ * a == NULL: plain LayerNorm of x (sum_out unused).  The residual-add + pre-LN pairs of MixingBlock
+ * (model/base_blocks.py:65-68) in one pass. */
+int lina_add_layernorm(const void *a, const void *x, const void *gamma, const void *beta, void *sum_out,
+                       void *ln_out, int M, int N, float eps, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * WavTokenizer decode tail (fp32).  The dense convolutions / linears of the backbone stay library

@@ -1,6 +1,8 @@
 // Small fused element-wise passes around the GLA mixer (HBM streaming, 16-byte vectors).
 //   lina_gate_logsigmoid : gk = logsigmoid(x) / normalizer [clamped]           (model/gla.py:174-181)
 //   lina_swiglu_act      : out[m, j] = silu(h[m, j]) * h[m, Hp + j]             (model/base_blocks.py:48-50)
+//   lina_add_layernorm   : s = a + x ; y = LayerNorm(s)   (the residual add + pre-LN pairs of MixingBlock,
+//                          model/base_blocks.py:65-68)
 #include "common.cuh"
 
 namespace {
@@ -59,7 +61,85 @@ swiglu_act_kernel(const T *__restrict__ h, T *__restrict__ out, int M, int Hp) {
     *reinterpret_cast<uint4 *>(out + (size_t)m * Hp + j) = outr;
 }
 
+// sum = a + x (rounded to T like the reference's separate add), ln = LayerNorm(sum) * gamma + beta.  One warp per row,
+// the row stays in registers between the statistics and the normalisation: 2 reads + 2 writes of the row in total
+// (torch: add = 2r+1w, layer_norm = 1r+1w, in two launches).  a == nullptr: plain LayerNorm of x.
+constexpr int LN_MAXCH = 8;
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict__ gamma,
+                     const T *__restrict__ beta, T *__restrict__ sum_out, T *__restrict__ ln_out, int M, int N, float eps) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nch = N / VEC;
+    const size_t off = (size_t)row * N;
+    float v[LN_MAXCH][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            const uint4 xr = *reinterpret_cast<const uint4 *>(x + off + (size_t)ch * VEC);
+            const T *xe = reinterpret_cast<const T *>(&xr);
+            if (a != nullptr) {
+                const uint4 ar = *reinterpret_cast<const uint4 *>(a + off + (size_t)ch * VEC);
+                const T *ae = reinterpret_cast<const T *>(&ar);
+                uint4 sr;
+                T *se = reinterpret_cast<T *>(&sr);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { se[i] = from_f<T>(to_f(ae[i]) + to_f(xe[i])); v[c][i] = to_f(se[i]); }
+                *reinterpret_cast<uint4 *>(sum_out + off + (size_t)ch * VEC) = sr;
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v[c][i] = to_f(xe[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s += v[c][i];
+        }
+    }
+    const float mean = warp_sum(s) / (float)N;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+        if (lane + c * 32 < nch) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { const float d = v[c][i] - mean; ss = fmaf(d, d, ss); }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)N + eps);
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            const uint4 gr = *reinterpret_cast<const uint4 *>(gamma + (size_t)ch * VEC);
+            const uint4 br = *reinterpret_cast<const uint4 *>(beta + (size_t)ch * VEC);
+            const T *ge = reinterpret_cast<const T *>(&gr), *be = reinterpret_cast<const T *>(&br);
+            uint4 outr;
+            T *oe = reinterpret_cast<T *>(&outr);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) oe[i] = from_f<T>((v[c][i] - mean) * rstd * to_f(ge[i]) + to_f(be[i]));
+            *reinterpret_cast<uint4 *>(ln_out + off + (size_t)ch * VEC) = outr;
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int lina_add_layernorm(const void *a, const void *x, const void *gamma, const void *beta, void *sum_out,
+                                  void *ln_out, int M, int N, float eps, int dtype, void *stream) {
+    LINA_REQUIRE(x && gamma && beta && ln_out && M > 0 && N > 0, LINA_ERR_BAD_ARG, "add_layernorm: bad argument");
+    LINA_REQUIRE(a == nullptr || sum_out != nullptr, LINA_ERR_BAD_ARG, "add_layernorm: sum_out required with a");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "add_layernorm: unknown dtype");
+    const int vec = 16 / (int)lina_dtype_size(dtype);
+    LINA_REQUIRE(N % vec == 0 && N / vec <= 32 * LN_MAXCH, LINA_ERR_UNSUPPORTED,
+                 "add_layernorm: row length N=%d must be a multiple of %d and <= %d", N, vec, 32 * LN_MAXCH * vec);
+    LINA_DISPATCH_DTYPE(dtype, add_layernorm_kernel<T_><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)a, (const T_ *)x, (const T_ *)gamma, (const T_ *)beta, (T_ *)sum_out,
+                                   (T_ *)ln_out, M, N, eps));
+    LINA_LAUNCH_OK("add_layernorm_kernel");
+    return LINA_OK;
+}
 
 extern "C" int lina_gate_logsigmoid(const void *x, void *y, long long n, float normalizer, float clamp_min,
                                     int use_clamp, int dtype, void *stream) {

@@ -105,3 +105,40 @@ class MixingBlock(nn.Module):
         x = (t[0] if type(t) is tuple else t) + x
         x = self.cmix(self.norm2(x)) + x
         return self.drop(x)
+
+    # -- inference fast path: residual adds fused into the following LayerNorm -------------------------------
+    def can_fuse(self, x) -> bool:
+        n = self.norm1
+        return (not torch.is_grad_enabled() and not self.training and x.is_cuda and isinstance(n, nn.LayerNorm)
+                and n.elementwise_affine and n.bias is not None and x.dtype == n.weight.dtype
+                and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+                and x.shape[-1] % (16 // x.element_size()) == 0 and x.shape[-1] // (16 // x.element_size()) <= 256)
+
+    def forward_fused(self, x, delta=None, **kwargs):
+        """Same arithmetic as ``forward`` for the block whose input is ``x + delta`` (``delta`` None = just ``x``),
+        returned as the pair (residual, branch) with block output = residual + branch, so that the caller can hand
+        the pending add to the next block's first LayerNorm (lina_add_layernorm: one pass instead of add + LN)."""
+        x1, h = add_layernorm(delta, x, self.norm1)
+        t = self.tmix(h, **kwargs)
+        t = t[0] if type(t) is tuple else t
+        x2, h2 = add_layernorm(t, x1, self.norm2)
+        return x2, self.cmix(h2)
+
+
+def add_layernorm(a, x, norm: nn.LayerNorm):
+    """(a + x, LayerNorm(a + x)); a None -> (x, LayerNorm(x)).  CUDA, no grad."""
+    from .. import _lib as L
+    xs = x.contiguous()
+    N = xs.shape[-1]
+    M = xs.numel() // N
+    ln = torch.empty_like(xs)
+    if a is not None:
+        a = a.contiguous()
+        s = torch.empty_like(xs)
+    else:
+        s = None
+    rc = L.lib().lina_add_layernorm(L.ptr(a), L.ptr(xs), L.ptr(norm.weight), L.ptr(norm.bias), L.ptr(s), L.ptr(ln), M, N,
+                                    float(norm.eps), L.dt(xs), L.stream(xs))
+    L.count_launches(1)
+    L.check(rc, "lina_add_layernorm")
+    return (s if s is not None else xs), ln

@@ -245,6 +245,17 @@ class AttentiveGLA(AttentiveRNN):
     def forward(self, x, ctx, mask=None, pos=None, reset_mask=None, attention_only=None, forced_attention=None,
                 init_state=None, crossatt_pos=None):
         """model/gla.py:287-300.  NB the cross attention's pos_net never sees ``init_state`` here."""
+        if self.encoder[0].can_fuse(x):                       # inference: adds folded into the LayerNorms
+            kw = dict(use_cache=init_state is not None, past_key_values=init_state)
+            xr, d = x, None
+            for e in self.encoder:
+                xr, d = e.forward_fused(xr, d, **kw)
+            x = xr + d
+            v, att = self.cross_att(x, ctx, mask=mask, reset_mask=reset_mask, pos=crossatt_pos)
+            xr, d = x, v
+            for dd in self.decoder:
+                xr, d = dd.forward_fused(xr, d, **kw)
+            return xr + d, att
         for e in self.encoder:
             if self.training:
                 e = maybe_grad_ckpt(e)
@@ -303,6 +314,17 @@ class AttentiveGLA(AttentiveRNN):
 
     def step(self, y_embd, x_enc, time_step, cache):
         """model/gla.py:358-365: one token through every block, all blocks stateful."""
+        if self.encoder[0].can_fuse(y_embd):
+            kw = dict(past_key_values=cache, use_cache=True)
+            xr, d = y_embd, None
+            for e in self.encoder:
+                xr, d = e.forward_fused(xr, d, **kw)
+            y = xr + d
+            v, att = self.cross_att(y, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)
+            xr, d = y, v
+            for dd in self.decoder:
+                xr, d = dd.forward_fused(xr, d, **kw)
+            return xr + d, att, cache
         for e in self.encoder:
             y_embd = e(y_embd, past_key_values=cache, use_cache=True)
         v, att = self.cross_att(y_embd, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)

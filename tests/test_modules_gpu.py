@@ -129,3 +129,23 @@ def test_swiglu_inference_path_matches_reference_formula(dtype):
         ref = m.p_out(F.silu(gate) * u)
     lo = dtype == torch.bfloat16
     _close(y, ref, 2e-2 if lo else 1e-5, 2e-2 if lo else 1e-5, what="swiglu")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N", [64, 1024])
+def test_add_layernorm_matches_torch(dtype, N):
+    from lina_speech_b200.model.base_blocks import add_layernorm
+    torch.manual_seed(N)
+    norm = torch.nn.LayerNorm(N).to(DEV).to(dtype)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5); norm.bias.normal_()
+    a, x = (torch.randn(7, 33, N, device=DEV).to(dtype) for _ in range(2))
+    with torch.no_grad():
+        s, ln = add_layernorm(a, x, norm)
+        s0, ln0 = add_layernorm(None, x, norm)
+        ref_s = a + x
+        ref_ln, ref_ln0 = norm(ref_s), norm(x)
+    assert torch.equal(s, ref_s) and s0.data_ptr() == x.data_ptr()
+    lo = dtype == torch.bfloat16
+    _close(ln, ref_ln, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="add+ln")
+    _close(ln0, ref_ln0, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="ln")
