@@ -62,6 +62,13 @@ __device__ __forceinline__ void store_dyn(void *p, int dtype, size_t i, float x)
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// one MUFU op instead of two (ex2 + rcp): sigmoid(x) = 0.5 tanh(x/2) + 0.5 with tanh.approx (rel. error ~2^-11).
+// Used only where the result is rounded to a 16-bit type right away; fp32 I/O keeps the exact form.
+__device__ __forceinline__ float tanh_approx_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <typename T> __device__ __forceinline__ float sigmoid_io(float x) {
+    if (sizeof(T) == 2) return fmaf(0.5f, tanh_approx_(0.5f * x), 0.5f);
+    return sigmoidf_(x);
+}
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // log(sigmoid(x)) = min(x,0) - log1p(exp(-|x|))   (stable for both tails)
 __device__ __forceinline__ float logsigmoidf_(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }

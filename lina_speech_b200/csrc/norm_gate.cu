@@ -62,7 +62,7 @@ norm_gate_fwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *
 #pragma unroll
             for (int i = 0; i < n; ++i) {
                 const float yh = xv[c][i] * rstd * (w != nullptr ? wv[i] : 1.f);
-                out[i] = yh * gv[i] * sigmoidf_(gv[i]);
+                out[i] = yh * gv[i] * sigmoid_io<T>(gv[i]);
             }
             store16<T>(yr + (size_t)ch * n, out);
         }

@@ -104,7 +104,7 @@ short_conv_fwd_w4_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__
             acc = fmaf(win[1][c], wt[1][c], acc);
             acc = fmaf(win[2][c], wt[2][c], acc);
             acc = fmaf(xv[c], wt[3][c], acc);
-            e[c] = from_f<T>(silu ? siluf_(acc) : acc);
+            e[c] = from_f<T>(silu ? acc * sigmoid_io<T>(acc) : acc);
             win[0][c] = win[1][c]; win[1][c] = win[2][c]; win[2][c] = xv[c];
         }
         *reinterpret_cast<uint4 *>(yb + (size_t)l * D) = raw;
