@@ -229,12 +229,14 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, mid=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             fn()
+            if mid is not None:
+                mid()               # NVML query from the launching thread: the GPU is busy with the queued steps
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -256,12 +258,14 @@ def main_ours(args):
     sampler.start()
     ops.PROFILE = []
     l0 = _lib.launches()
-    ms = timed(step_resident, args.steps)
-    if sampler.nv is not None and not sampler.samples:
-        try:
-            sampler._sample()
-        except Exception:           # noqa: BLE001
-            pass
+    def mid_sample():
+        if sampler.nv is not None:
+            try:
+                sampler._sample()
+            except Exception:       # noqa: BLE001
+                pass
+
+    ms = timed(step_resident, args.steps, mid_sample)
     launches = _lib.launches() - l0
     prof, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.result()
