@@ -23,6 +23,10 @@ import sys
 import threading
 import time
 
+# NCCL writes its "NCCL version ..." banner (NCCL_DEBUG=VERSION/WARN on these boxes) to stdout by default; stdout
+# must carry exactly one JSON line, so NCCL's own output goes to stderr.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
