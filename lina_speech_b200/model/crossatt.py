@@ -12,6 +12,8 @@ import torch
 from torch import nn
 from einops import rearrange
 
+from .positional import ConvPos, SinPos
+
 
 def exists(x):
     return x is not None
@@ -32,31 +34,6 @@ def scaled_dot_product_attention(query, key, value, mask=None):
         w = w.masked_fill(~mask, -torch.finfo(w.dtype).max)
     w = torch.softmax(w, dim=-1)
     return w @ value, w
-
-
-class ConvPos(nn.Module):
-    """model/crossatt.py:21-33."""
-
-    def __init__(self, dim, max_seq_len=2000, kernel_size=31):
-        super().__init__()
-        self.embed = nn.Embedding(max_seq_len, dim)
-        self.dw_conv = nn.Conv1d(dim, dim, kernel_size, groups=dim, padding="same")
-
-    def forward(self, x):
-        return self.dw_conv(self.embed(x).transpose(1, 2)).transpose(1, 2)
-
-
-class SinPos(nn.Module):
-    """model/crossatt.py:36-48."""
-
-    def __init__(self, dim):
-        super().__init__()
-        self.dim = dim
-
-    def forward(self, x):
-        e = 2 * torch.arange(self.dim // 2, device=x.device) / self.dim
-        pos = x.unsqueeze(-1) * torch.pow(10000, -e).view(1, 1, -1)
-        return torch.sin(torch.cat((pos, pos + math.pi / 2), dim=2))
 
 
 class BlindCrossAttention(nn.Module):

@@ -24,7 +24,7 @@ from einops import einsum, rearrange, repeat
 from .. import _lib as L
 from ..fla_api import (Cache, FusedRMSNormSwishGate, ShortConvolution, chunk_gla, fused_chunk_gla,
                        fused_recurrent_gla)
-from .attentive_rnn import AttentiveRNN
+from .contracts import AttentiveRNN
 from .base_blocks import MixingBlock, SwiGLU
 from .crossatt import BlindCrossAttention, CrossAttention, tensor_version
 

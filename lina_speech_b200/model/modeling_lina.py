@@ -20,8 +20,8 @@ import torch.nn.functional as F
 from einops import rearrange, reduce, repeat
 from torch import Tensor, nn
 
-from .attentive_rnn import AttentiveRNN
-from .multiembed import MultiEmbedding
+from .contracts import AttentiveRNN
+from .embeddings import MultiEmbedding
 from ..parallel import gather_tokens
 from .tools import topk_sampling, undelay_rvq
 
