@@ -117,6 +117,20 @@ int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void 
                      float scale, float gate_normalizer, float eps, int ldx, int ldg, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Post-projection pass of a whole-sequence GLA mixer call in ONE launch (inference prefill):
+ *   q, k, v = SiLU(ShortConvolution(x_q | x_k | x_v))   (FLA/fla/modules/convolution.py:141-178, model/gla.py:161-163)
+ *   gk      = logsigmoid(gk_raw) / normalizer [clamped]   (model/gla.py:174-181)
+ *   xq, xk [B,L,Dk], xv [B,L,Dv] with row stride `ldx` elements (column slices of one [q;k;v;g] GEMM output);
+ *   gk_raw [B,L,Dk] with row stride `ldg`; wq, wk [Dk,4], wv [Dv,4]; outputs contiguous [B,L,D];
+ *   cq, ck [B,Dk,4], cv [B,Dv,4] receive the last 4 inputs (all three or none).  W must be 4.
+ * ------------------------------------------------------------------------------------------- */
+int lina_gla_prefill_prep(const void *xq, const void *xk, const void *xv, long long ldx,
+                          const void *wq, const void *wk, const void *wv, const void *gk_raw, long long ldg,
+                          void *q, void *k, void *v, void *gk, void *cq, void *ck, void *cv, int cache_dtype,
+                          int B, int L, int Dk, int Dv, int W, float gate_normalizer, float clamp_min, int use_clamp,
+                          int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.
  * Replaces causal_conv1d_fn / causal_conv1d_update (causal-conv1d 1.3.0.post1, call sites
  * FLA/fla/modules/convolution.py:168-173,189-195; semantics = the torch branch :175-178,197-204).
@@ -137,6 +151,10 @@ int lina_short_conv_update(const void *x, void *cache, int cache_dtype, const vo
  * ------------------------------------------------------------------------------------------- */
 int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void *y, float *rstd,
                                int M, int N, float eps, int dtype, void *stream);
+/* Same forward with the gate read in place from a wider buffer: row r of g starts at
+ * g + (r / g_group) * ldg + (r % g_group) * N  (g_group = heads, ldg = row stride of the [q;k;v;g] projection). */
+int lina_rmsnorm_swishgate_fwd_ld(const void *x, const void *g, const void *w, void *y, float *rstd,
+                                  int M, int N, float eps, int g_group, long long ldg, int dtype, void *stream);
 int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, const float *rstd,
                                const void *dy, void *dx, void *dg, float *dw,
                                int M, int N, int dtype, void *stream);
@@ -154,6 +172,14 @@ int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtype, void *st
  * (model/base_blocks.py:65-68) in one pass. */
 int lina_add_layernorm(const void *a, const void *x, const void *gamma, const void *beta, void *sum_out,
                        void *ln_out, int M, int N, float eps, int dtype, void *stream);
+
+/* Row-wise cross entropy of LinaModel.forward (model/modeling_lina.py:104-106: F.cross_entropy(logits.float(),
+ * target, ignore_index=1)) straight from the `dtype` logits, fp32 math: loss[m] = logsumexp(logits[m,:Vn]) -
+ * logits[m,target[m]], valid[m] = 1; rows with target == ignore_index or row_mask[m] == 0 give loss = valid = 0.
+ * logits rows are `ld` elements apart (>= Vn: a vocabulary-padded GEMM output is read in place); row_mask may be NULL.
+ * The caller reduces: loss.sum() / valid.sum(). */
+int lina_cross_entropy_rows(const void *logits, long long ld, const int64_t *target, const uint8_t *row_mask,
+                            float *loss, float *valid, int M, int Vn, long long ignore_index, int dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * WavTokenizer decode tail (fp32).  The dense convolutions / linears of the backbone stay library
@@ -192,6 +218,10 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * operand placements of the GLA kernel (a_mode: 0 smem K-major, 1 smem MN-major, 2 TMEM; b_mode: 0 / 1).
  * `swap` exchanges the descriptor's leading/stride byte offsets.  Not part of the reference's API.
  * ------------------------------------------------------------------------------------------- */
+/* A/B switches for kernel variants (bring-up only; process-global, not thread-safe): key 0 = rows per thread of the
+ * prep / short-conv tile kernel (8 or 16), key 1 = 1 selects the round-1 sliding-window short-conv kernel,
+ * key 2 = bit mask of tcgen05 GLA kernel options. */
+int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);
 /* Same with 128-byte-swizzled operands (a_mode / b_mode: 0 K-major, 1 MN-major); use_tma != 0 loads A from

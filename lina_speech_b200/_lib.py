@@ -34,14 +34,17 @@ PROTOTYPES = {
     "lina_gla_step_workspace_bytes": (_sz, [_i] * 4),
     "lina_gla_step": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_p]),
     "lina_gla_step_ld": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_i, _i, _p]),
+    "lina_gla_prefill_prep": (_i, [_p] * 3 + [C.c_longlong] + [_p] * 4 + [C.c_longlong] + [_p] * 7 + [_i] * 6 + [_f, _f, _i, _i, _p]),
     "lina_short_conv_fwd": (_i, [_p] * 4 + [_i] * 7 + [_p]),
     "lina_short_conv_bwd": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "lina_short_conv_update": (_i, [_p, _p, _i, _p, _p] + [_i] * 5 + [_p]),
     "lina_rmsnorm_swishgate_fwd": (_i, [_p] * 5 + [_i, _i, _f, _i, _p]),
+    "lina_rmsnorm_swishgate_fwd_ld": (_i, [_p] * 5 + [_i, _i, _f, _i, C.c_longlong, _i, _p]),
     "lina_rmsnorm_swishgate_bwd": (_i, [_p] * 8 + [_i, _i, _i, _p]),
     "lina_gate_logsigmoid": (_i, [_p, _p, C.c_longlong, _f, _f, _i, _i, _p]),
     "lina_swiglu_act": (_i, [_p, _p, _i, _i, _i, _p]),
     "lina_add_layernorm": (_i, [_p] * 6 + [_i, _i, _f, _i, _p]),
+    "lina_cross_entropy_rows": (_i, [_p, C.c_longlong, _p, _p, _p, _p, _i, _i, C.c_longlong, _i, _p]),
     "lina_codec_codes_to_features": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_codec_groupnorm_swish": (_i, [_p] * 5 + [_i] * 4 + [_f, _i, _p]),
     "lina_codec_dwconv_adaln": (_i, [_p] * 6 + [_i] * 3 + [_f, _p]),
@@ -49,6 +52,7 @@ PROTOTYPES = {
     "lina_codec_layernorm_t": (_i, [_p] * 4 + [_i] * 3 + [_f, _p]),
     "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
+    "lina_debug_set_variant": (_i, [_i, _i]),
     "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
     "lina_debug_umma_timing": (_i, [_p] + [_i] * 6 + [_p]),

@@ -65,7 +65,7 @@ swiglu_act_kernel(const T *__restrict__ h, T *__restrict__ out, int M, int Hp) {
 // the row stays in registers between the statistics and the normalisation: 2 reads + 2 writes of the row in total
 // (torch: add = 2r+1w, layer_norm = 1r+1w, in two launches).  a == nullptr: plain LayerNorm of x.
 constexpr int LN_MAXCH = 8;
-template <typename T>
+template <typename T, int LN_CH>
 __global__ void __launch_bounds__(256)
 add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *__restrict__ gamma,
                      const T *__restrict__ beta, T *__restrict__ sum_out, T *__restrict__ ln_out, int M, int N, float eps) {
@@ -74,10 +74,10 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
     if (row >= M) return;
     const int nch = N / VEC;
     const size_t off = (size_t)row * N;
-    float v[LN_MAXCH][VEC];
+    float v[LN_CH][VEC];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < LN_CH; ++c) {
         const int ch = lane + c * 32;
         if (ch < nch) {
             const uint4 xr = *reinterpret_cast<const uint4 *>(x + off + (size_t)ch * VEC);
@@ -101,7 +101,7 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
     const float mean = warp_sum(s) / (float)N;
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < LN_CH; ++c) {
         if (lane + c * 32 < nch) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { const float d = v[c][i] - mean; ss = fmaf(d, d, ss); }
@@ -109,7 +109,7 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
     }
     const float rstd = rsqrtf(warp_sum(ss) / (float)N + eps);
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < LN_CH; ++c) {
         const int ch = lane + c * 32;
         if (ch < nch) {
             const uint4 gr = *reinterpret_cast<const uint4 *>(gamma + (size_t)ch * VEC);
@@ -124,6 +124,71 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
     }
 }
 
+
+// Row-wise cross entropy on logits of the activation dtype, fp32 math (the reference casts to float first:
+// model/modeling_lina.py:104-106 F.cross_entropy(logits.float(), target, ignore_index=1)):
+//   loss[m] = logsumexp(logits[m, :Vn]) - logits[m, target[m]]   (0 and valid[m] = 0 when target == ignore or masked out)
+// One warp per row, single pass with an online (max, sum) pair per lane; rows may be strided (ld elements), e.g. the
+// first Vn columns of a vocabulary-padded GEMM output.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cross_entropy_rows_kernel(const T *__restrict__ logits, long long ld, const long long *__restrict__ target,
+                          const unsigned char *__restrict__ row_mask, float *__restrict__ loss, float *__restrict__ valid,
+                          int M, int Vn, long long ignore_index) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const long long tg = target[row];
+    const bool on = tg != ignore_index && (row_mask == nullptr || row_mask[row] != 0);
+    if (!on || tg < 0 || tg >= Vn) {        // whole warp takes the same branch
+        if (lane == 0) { loss[row] = 0.f; valid[row] = 0.f; }
+        return;
+    }
+    const T *r = logits + (size_t)row * ld;
+    const bool vec_ok = (ld % VEC == 0) && (((uintptr_t)logits & 15u) == 0);
+    constexpr float LOG2E = 1.44269504088896340736f;
+    float m = -INFINITY, s = 0.f;           // running max (natural units) and sum of exp(x - m)
+    const int nfull = vec_ok ? Vn / VEC : 0;
+    for (int ch0 = 0; ch0 < nfull; ch0 += 128) {          // 4 independent 16-byte loads per lane per iteration
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ch = ch0 + u * 32 + lane;
+            if (ch < nfull) raw[u] = *reinterpret_cast<const uint4 *>(r + (size_t)ch * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ch = ch0 + u * 32 + lane;
+            if (ch < nfull) {
+                const T *e = reinterpret_cast<const T *>(&raw[u]);
+                float f[VEC], mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { f[i] = to_f(e[i]); mx = fmaxf(mx, f[i]); }
+                if (mx > m) { s *= exp2f((m - mx) * LOG2E); m = mx; }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) s += exp2f((f[i] - m) * LOG2E);
+            }
+        }
+    }
+    for (int j = nfull * VEC + lane; j < Vn; j += 32) {   // tail (and the whole row when unaligned)
+        const float f = to_f(r[j]);
+        if (f > m) { s *= exp2f((m - f) * LOG2E); m = f; }
+        s += exp2f((f - m) * LOG2E);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mn = fmaxf(m, m2);
+        const float a = (m == -INFINITY) ? 0.f : s * exp2f((m - mn) * LOG2E);
+        const float b = (m2 == -INFINITY) ? 0.f : s2 * exp2f((m2 - mn) * LOG2E);
+        s = a + b; m = mn;
+    }
+    if (lane == 0) {
+        loss[row] = m + logf(s) - to_f(r[tg]);
+        valid[row] = 1.f;
+    }
+}
+
 }  // namespace
 
 extern "C" int lina_add_layernorm(const void *a, const void *x, const void *gamma, const void *beta, void *sum_out,
@@ -134,9 +199,15 @@ extern "C" int lina_add_layernorm(const void *a, const void *x, const void *gamm
     const int vec = 16 / (int)lina_dtype_size(dtype);
     LINA_REQUIRE(N % vec == 0 && N / vec <= 32 * LN_MAXCH, LINA_ERR_UNSUPPORTED,
                  "add_layernorm: row length N=%d must be a multiple of %d and <= %d", N, vec, 32 * LN_MAXCH * vec);
-    LINA_DISPATCH_DTYPE(dtype, add_layernorm_kernel<T_><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-                                   (const T_ *)a, (const T_ *)x, (const T_ *)gamma, (const T_ *)beta, (T_ *)sum_out,
-                                   (T_ *)ln_out, M, N, eps));
+    if (N / vec <= 32 * 4) {          // d_model 1024 in bf16: half the registers of the general case
+        LINA_DISPATCH_DTYPE(dtype, add_layernorm_kernel<T_, 4><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                       (const T_ *)a, (const T_ *)x, (const T_ *)gamma, (const T_ *)beta, (T_ *)sum_out,
+                                       (T_ *)ln_out, M, N, eps));
+    } else {
+        LINA_DISPATCH_DTYPE(dtype, add_layernorm_kernel<T_, LN_MAXCH><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                       (const T_ *)a, (const T_ *)x, (const T_ *)gamma, (const T_ *)beta, (T_ *)sum_out,
+                                       (T_ *)ln_out, M, N, eps));
+    }
     LINA_LAUNCH_OK("add_layernorm_kernel");
     return LINA_OK;
 }
@@ -165,5 +236,18 @@ extern "C" int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtyp
     LINA_DISPATCH_DTYPE(dtype, swiglu_act_kernel<T_><<<(unsigned)((nthreads + 255) / 256), 256, 0,
                                                         (cudaStream_t)stream>>>((const T_ *)h, (T_ *)out, M, Hp));
     LINA_LAUNCH_OK("swiglu_act_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_cross_entropy_rows(const void *logits, long long ld, const int64_t *target, const uint8_t *row_mask,
+                                       float *loss, float *valid, int M, int Vn, long long ignore_index, int dtype,
+                                       void *stream) {
+    LINA_REQUIRE(logits && target && loss && valid && M > 0 && Vn > 0 && ld >= Vn, LINA_ERR_BAD_ARG,
+                 "cross_entropy_rows: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "cross_entropy_rows: unknown dtype");
+    LINA_DISPATCH_DTYPE(dtype, cross_entropy_rows_kernel<T_><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)logits, ld, (const long long *)target, row_mask, loss, valid, M, Vn,
+                                   ignore_index));
+    LINA_LAUNCH_OK("cross_entropy_rows_kernel");
     return LINA_OK;
 }

@@ -39,6 +39,8 @@
 
 using namespace sm100;
 
+extern int g_lina_variant[8];
+
 int lina_gla_recurrent_fwd_impl(const void *q, const void *k, const void *v, const void *gk, const void *h0,
                                 int h0_dtype, void *o, float *ht, int B, int H, int T, int K, int V, int dtype,
                                 float scale, void *stream);
@@ -104,7 +106,11 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
 
 struct TMaps { CUtensorMap q, k, g, v; };
 
-template <int K>
+// OPT bit 0: state pass reads ST 16 columns at a time, double-buffered (the tcgen05.ld of block c+1 is in flight while
+//            block c is rescaled and stored) instead of ld32 -> wait -> compute -> store per block;
+// OPT bit 1: the gate pre-pass keeps its gk rows in registers between the column-sum pass and the rescale pass
+//            (8 fewer 16-byte shared loads per thread and item).
+template <int K, int OPT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
                            bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, int H, int bthd, float scale,
@@ -157,12 +163,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             if (p == 0) TRACE(0, n, 0);
             // pass A: column sums of gk over this thread's rows
             float csum[8];
+            uint4 graw[(OPT & 2) ? RPG : 1];
 #pragma unroll
             for (int j = 0; j < 8; ++j) csum[j] = 0.f;
 #pragma unroll
             for (int i = 0; i < RPG; ++i) {
                 float g8[8];
-                unpack8(*reinterpret_cast<const uint4 *>(g_tile + sw128_off(rg * RPG + i, c16)), g8);
+                const uint4 gr = *reinterpret_cast<const uint4 *>(g_tile + sw128_off(rg * RPG + i, c16));
+                if (OPT & 2) graw[i] = gr;
+                unpack8(gr, g8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) csum[j] += g8[j];
             }
@@ -198,7 +207,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 uint4 *qp4 = reinterpret_cast<uint4 *>(qk_tile + sw128_off(r, c16));
                 uint4 *kp4 = reinterpret_cast<uint4 *>(qk_tile + sw128_off(64 + r, c16));
                 float g8[8], q8[8], k8[8];
-                unpack8(*reinterpret_cast<const uint4 *>(g_tile + sw128_off(r, c16)), g8);
+                if (OPT & 2) unpack8(graw[i], g8);
+                else unpack8(*reinterpret_cast<const uint4 *>(g_tile + sw128_off(r, c16)), g8);
                 unpack8(*qp4, q8);
                 unpack8(*kp4, k8);
                 uint32_t qp[4], kp[4];
@@ -393,6 +403,40 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             if (r == 0) TRACE(5, n, 0);
             const float *dv = dvec + (n % 3) * K;
             const bool last = n == n_items - 1;
+            if (OPT & 1) {
+                // 16-column blocks, double-buffered: ld(c+1) is issued before block c is processed
+                auto process = [&](uint32_t (&f)[16], int c) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(dv + c * 16 + j);
+                        f[j + 0] = __float_as_uint(__uint_as_float(f[j + 0]) * d4.x);
+                        f[j + 1] = __float_as_uint(__uint_as_float(f[j + 1]) * d4.y);
+                        f[j + 2] = __float_as_uint(__uint_as_float(f[j + 2]) * d4.z);
+                        f[j + 3] = __float_as_uint(__uint_as_float(f[j + 3]) * d4.w);
+                    }
+                    if (!last) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
+                        tmem_st16(tmem + lane_addr + COL_ST + c * 16, f);
+                        tmem_st8(tmem + lane_addr + COL_SA + c * 8, pk);
+                    } else if (ht != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) ht[sbase + (size_t)(c * 16 + j) * V] = __uint_as_float(f[j]);
+                    }
+                };
+                uint32_t fa[16], fb[16];
+                tmem_ld16(tmem + lane_addr + COL_ST, fa);
+#pragma unroll 1
+                for (int c = 0; c < K / 16; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld16(tmem + lane_addr + COL_ST + (c + 1) * 16, fb);
+                    process(fa, c);
+                    tmem_ld_wait();
+                    if (c + 2 < K / 16) tmem_ld16(tmem + lane_addr + COL_ST + (c + 2) * 16, fa);
+                    process(fb, c + 1);
+                }
+            } else {
 #pragma unroll 1
             for (int cb = 0; cb < K / 32; ++cb) {
                 uint32_t f[32], pk[16];
@@ -416,6 +460,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     for (int j = 0; j < 32; ++j) ht[sbase + (size_t)(cb * 32 + j) * V] = __uint_as_float(f[j]);
                 }
             }
+            }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_SA_FULL]);
@@ -427,13 +472,13 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-template <int K>
+template <int K, int OPT = 0>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
            float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr) {
     using cfg = Cfg<K>;
     static thread_local bool configured = false;
     if (!configured) {
-        LINA_CUDA_OK(cudaFuncSetAttribute(gla_chunk_fwd_sm100_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LINA_CUDA_OK(cudaFuncSetAttribute(gla_chunk_fwd_sm100_kernel<K, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)cfg::SMEM));
         configured = true;
     }
@@ -454,7 +499,7 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
         if ((rc = lina_make_tmap_bf16(&tm.v, v, 4, vdims, sv, box))) return rc;
     }
     dim3 grid(V / BV, B * H);
-    gla_chunk_fwd_sm100_kernel<K><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
+    gla_chunk_fwd_sm100_kernel<K, OPT><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
                                                                    trace);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
@@ -483,7 +528,12 @@ static int chunk_fwd_tc(const void *q, const void *k, const void *v, const void 
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
     if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-    return launch<256>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+    switch (g_lina_variant[2] & 3) {       // A/B of the kernel options at the flagship head size
+        case 1: return launch<256, 1>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+        case 2: return launch<256, 2>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+        case 3: return launch<256, 3>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+        default: return launch<256, 0>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+    }
 }
 
 extern "C" int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, const void *gk, const void *h0,

@@ -28,41 +28,53 @@ template <typename T> __device__ __forceinline__ void store16(T *p, const float 
     *reinterpret_cast<uint4 *>(p) = raw;
 }
 
-template <typename T>
+// Forward.  Row r of x / y is contiguous; row r of g lives at g + (r / g_group) * ldg + (r % g_group) * N, so the gate can be
+// read in place as a column slice of the [q;k;v;g] projection buffer (g_group = heads, ldg = its row stride) -- dense is
+// g_group = 1, ldg = N.  Both the x and the g loads of a row are issued before the reduction (2 KB in flight per warp).
+template <typename T, int CH>
 __global__ void __launch_bounds__(256)
 norm_gate_fwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *__restrict__ w, T *__restrict__ y,
-                     float *__restrict__ rstd_out, int M, int N, float eps) {
+                     float *__restrict__ rstd_out, int M, int N, float eps, int g_group, long long ldg) {
     constexpr int n = V16<T>::n;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
-    const T *xr = x + (size_t)row * N, *gr = g + (size_t)row * N;
+    const T *xr = x + (size_t)row * N;
+    const T *gr = g + (size_t)(row / g_group) * ldg + (size_t)(row % g_group) * N;
     T *yr = y + (size_t)row * N;
-    const int nch = N / n;                 // host guarantees N % n == 0 and nch <= 32*MAXCH
-    float xv[MAXCH][n];
-    float ss = 0.f;
+    const int nch = N / n;                 // host guarantees N % n == 0 and nch <= 32*CH
+    uint4 xraw[CH], graw[CH];
 #pragma unroll
-    for (int c = 0; c < MAXCH; ++c) {
+    for (int c = 0; c < CH; ++c) {
         const int ch = lane + c * 32;
         if (ch < nch) {
-            load16<T>(xr + (size_t)ch * n, xv[c]);
+            xraw[c] = *reinterpret_cast<const uint4 *>(xr + (size_t)ch * n);
+            graw[c] = *reinterpret_cast<const uint4 *>(gr + (size_t)ch * n);
+        }
+    }
+    float ss = 0.f;
 #pragma unroll
-            for (int i = 0; i < n; ++i) ss = fmaf(xv[c][i], xv[c][i], ss);
+    for (int c = 0; c < CH; ++c) {
+        if (lane + c * 32 < nch) {
+            const T *e = reinterpret_cast<const T *>(&xraw[c]);
+#pragma unroll
+            for (int i = 0; i < n; ++i) { const float v = to_f(e[i]); ss = fmaf(v, v, ss); }
         }
     }
     ss = warp_sum(ss);
     const float rstd = rsqrtf(ss / (float)N + eps);
     if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;
 #pragma unroll
-    for (int c = 0; c < MAXCH; ++c) {
+    for (int c = 0; c < CH; ++c) {
         const int ch = lane + c * 32;
         if (ch < nch) {
-            float gv[n], wv[n], out[n];
-            load16<T>(gr + (size_t)ch * n, gv);
+            float wv[n], out[n];
             if (w != nullptr) load16<T>(w + (size_t)ch * n, wv);
+            const T *xe = reinterpret_cast<const T *>(&xraw[c]), *ge = reinterpret_cast<const T *>(&graw[c]);
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                const float yh = xv[c][i] * rstd * (w != nullptr ? wv[i] : 1.f);
-                out[i] = yh * gv[i] * sigmoid_io<T>(gv[i]);
+                const float gv = to_f(ge[i]);
+                const float yh = to_f(xe[i]) * rstd * (w != nullptr ? wv[i] : 1.f);
+                out[i] = yh * gv * sigmoid_io<T>(gv);
             }
             store16<T>(yr + (size_t)ch * n, out);
         }
@@ -149,15 +161,31 @@ int check(int M, int N, int dtype) {
 
 }  // namespace
 
-extern "C" int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void *y, float *rstd, int M,
-                                          int N, float eps, int dtype, void *stream) {
+extern "C" int lina_rmsnorm_swishgate_fwd_ld(const void *x, const void *g, const void *w, void *y, float *rstd, int M,
+                                             int N, float eps, int g_group, long long ldg, int dtype, void *stream) {
     LINA_REQUIRE(x && g && y, LINA_ERR_BAD_ARG, "rmsnorm_swishgate_fwd: null pointer");
     int rc = check(M, N, dtype);
     if (rc) return rc;
-    LINA_DISPATCH_DTYPE(dtype, norm_gate_fwd_kernel<T_><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-                                   (const T_ *)x, (const T_ *)g, (const T_ *)w, (T_ *)y, rstd, M, N, eps));
+    const int n = 16 / (int)lina_dtype_size(dtype);
+    LINA_REQUIRE(g_group >= 1 && ldg >= (long long)g_group * N && ldg % n == 0 && M % g_group == 0, LINA_ERR_BAD_ARG,
+                 "rmsnorm_swishgate_fwd: bad gate layout (g_group=%d, ldg=%lld, N=%d, M=%d)", g_group, ldg, N, M);
+    LINA_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)g % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)w % 16 == 0,
+                 LINA_ERR_UNSUPPORTED, "rmsnorm_swishgate_fwd: tensors must be 16-byte aligned");
+    const int nch = N / n;
+    if (nch <= 64) {
+        LINA_DISPATCH_DTYPE(dtype, norm_gate_fwd_kernel<T_, 2><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                       (const T_ *)x, (const T_ *)g, (const T_ *)w, (T_ *)y, rstd, M, N, eps, g_group, ldg));
+    } else {
+        LINA_DISPATCH_DTYPE(dtype, norm_gate_fwd_kernel<T_, MAXCH><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                       (const T_ *)x, (const T_ *)g, (const T_ *)w, (T_ *)y, rstd, M, N, eps, g_group, ldg));
+    }
     LINA_LAUNCH_OK("norm_gate_fwd_kernel");
     return LINA_OK;
+}
+
+extern "C" int lina_rmsnorm_swishgate_fwd(const void *x, const void *g, const void *w, void *y, float *rstd, int M,
+                                          int N, float eps, int dtype, void *stream) {
+    return lina_rmsnorm_swishgate_fwd_ld(x, g, w, y, rstd, M, N, eps, 1, N, dtype, stream);
 }
 
 extern "C" int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const void *w, const float *rstd,

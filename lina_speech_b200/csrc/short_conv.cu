@@ -8,6 +8,11 @@
 // channel dim (coalesced rows of [B,L,D]); each thread slides a W-tap window over LT time steps.
 #include "common.cuh"
 
+extern int g_lina_variant[8];
+// gla_prep.cu: TL-row tiles, all loads of a thread issued up front (the production W == 4 path)
+int lina_short_conv4_tiles(const void *x, long long ldx, const void *w, void *y, void *cache, int cache_dtype, int B,
+                           int L, int D, int silu, int dtype, void *stream);
+
 namespace {
 
 constexpr int LT = 16;      // time steps per thread
@@ -191,7 +196,10 @@ extern "C" int lina_short_conv_fwd(const void *x, const void *w, void *y, void *
     LINA_REQUIRE(cache == nullptr || lina_dtype_ok(cache_dtype), LINA_ERR_BAD_ARG, "short_conv_fwd: bad cache dtype");
     LINA_REQUIRE(B <= 65535 && (L + LT - 1) / LT <= 65535, LINA_ERR_UNSUPPORTED, "short_conv_fwd: grid too large");
     const int vec = 16 / (int)lina_dtype_size(dtype);
-    if (W == 4 && D % vec == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+    if (W == 4 && D % vec == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)w % 16 == 0) &&
+        g_lina_variant[1] == 0)
+        return lina_short_conv4_tiles(x, D, w, y, cache, cache_dtype, B, L, D, silu, dtype, stream);
+    if (W == 4 && D % vec == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {   // A/B: the round-1 sliding-window kernel
         const int nv = D / vec;
         dim3 gridv((nv + 127) / 128, (L + LTV - 1) / LTV, B);
         LINA_DISPATCH_DTYPE(dtype, short_conv_fwd_w4_kernel<T_><<<gridv, 128, 0, (cudaStream_t)stream>>>(

@@ -28,6 +28,11 @@ from .contracts import AttentiveRNN
 from .base_blocks import MixingBlock, SwiGLU
 from .crossatt import BlindCrossAttention, CrossAttention, tensor_version
 
+# bring-up switches (A/B on the GPU box): LINA_FUSED_PREFILL=0 restores the op-by-op inference path,
+# LINA_CAT5=1 folds the rank-16 gate projection into the concatenated GEMM as well (N = 6160)
+FUSED_PREFILL = os.environ.get("LINA_FUSED_PREFILL", "1") != "0"
+CAT5 = os.environ.get("LINA_CAT5", "0") == "1"
+
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):
         def wrapped(*args, **kwargs):
@@ -128,6 +133,75 @@ class GatedLinearAttention(nn.Module):
         L.check(rc, "lina_gla_step")
         return self.o_proj(out).view(B, 1, -1)
 
+    # -- whole-sequence inference fast path ----------------------------------------------------------
+    def _cat_weight4(self):
+        """[q;k;v;g] stacked (N = 2*key_dim + 2*value_dim, a multiple of 256 at the shipped size): one GEMM reads
+        the LayerNorm output once instead of four times."""
+        ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.g_proj.weight)
+        key = tuple((w.data_ptr(), tensor_version(w), w.dtype) for w in ws)
+        if getattr(self, "_wcat4", None) is None or self._wcat4[0] != key:
+            self._wcat4 = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        return self._wcat4[1]
+
+    def _can_prefill(self, x, reset_mask, attention_mask) -> bool:
+        return (FUSED_PREFILL and self.use_short_conv and self.conv_size == 4 and not torch.is_grad_enabled()
+                and reset_mask is None and attention_mask is None
+                and x.dtype in (torch.bfloat16, torch.float16, torch.float32)
+                and self.key_dim % 8 == 0 and self.head_v_dim % 8 == 0
+                and self.head_v_dim * x.element_size() // 16 <= 128
+                and self.q_proj.weight.dtype == x.dtype)
+
+    def _prefill(self, x: torch.Tensor, last_state, use_cache: bool, past_key_values) -> torch.Tensor:
+        """model/gla.py:146-225 for a whole sequence without autograd: one [q;k;v;g] GEMM, ONE pass for the three
+        short convs + the gate non-linearity (lina_gla_prefill_prep), the GLA op on the [B,T,H,D] layout, the
+        norm-gate reading g in place from the projection buffer, o_proj."""
+        B, T, _ = x.shape
+        H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
+        lib = L.lib()
+        if CAT5:
+            proj = F.linear(x, self._cat_weight())
+            lo = proj[..., 2 * kd + 2 * vd:]
+        else:
+            proj = F.linear(x, self._cat_weight4())
+            lo = self.gk_proj[0](x)
+        gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
+        ldx = proj.shape[-1]
+        xq, xk, xv, g = proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd], proj[..., 2 * kd + vd:2 * kd + 2 * vd]
+        q = torch.empty(B, T, kd, dtype=x.dtype, device=x.device)
+        k, gk = torch.empty_like(q), torch.empty_like(q)
+        v = torch.empty(B, T, vd, dtype=x.dtype, device=x.device)
+        cq = ck = cv = None
+        if use_cache and last_state is not None:
+            cq, ck, cv = last_state[0], last_state[1], last_state[2]
+            if not (cq.is_contiguous() and ck.is_contiguous() and cv.is_contiguous()):
+                raise ValueError("conv caches must be contiguous [B, D, W]")
+        wq, wk, wv = (c.weight.to(x.dtype).contiguous() for c in (self.q_conv1d, self.k_conv1d, self.v_conv1d))
+        rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
+                                       L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk),
+                                       L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0, B, T, kd, vd,
+                                       self.conv_size, float(self.gate_logit_normalizer), float(self.clamp_min or 0.0),
+                                       int(self.clamp_min is not None), L.dt(x), L.stream(x))
+        L.count_launches(1)
+        L.check(rc, "lina_gla_prefill_prep")
+        q4, k4, gk4 = (t.view(B, T, H, K).transpose(1, 2) for t in (q, k, gk))
+        v4 = v.view(B, T, H, V).transpose(1, 2)
+        recurrent_state = last_state[-1] if use_cache else None
+        op = {"fused_recurrent": fused_recurrent_gla, "fused_chunk": fused_chunk_gla, "chunk": chunk_gla}[self.mode]
+        o, recurrent_state = op(q4, k4, v4, gk4, initial_state=recurrent_state, output_final_state=use_cache)
+        if past_key_values is not None and not self.training:           # model/gla.py:205-213
+            past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
+        o = o.transpose(1, 2)
+        if not o.is_contiguous():
+            o = o.contiguous()
+        y = torch.empty_like(o)
+        nw = self.g_norm_swish_gate.weight
+        nw = nw.to(x.dtype) if nw is not None else None
+        rc = lib.lina_rmsnorm_swishgate_fwd_ld(L.ptr(o), L.ptr(g), L.ptr(nw), L.ptr(y), None, B * T * H, V,
+                                               float(self.g_norm_swish_gate.eps), H, ldx, L.dt(x), L.stream(x))
+        L.count_launches(1)
+        L.check(rc, "lina_rmsnorm_swishgate_fwd_ld")
+        return self.o_proj(y.view(B, T, vd))
+
     def _can_step(self, x, state, reset_mask, attention_mask) -> bool:
         return (x.shape[1] == 1 and state is not None and not self.training and not torch.is_grad_enabled()
                 and reset_mask is None and attention_mask is None and self.clamp_min is None
@@ -147,6 +221,9 @@ class GatedLinearAttention(nn.Module):
             o = self._step(hidden_states, last_state)
             past_key_values.update(last_state, self.layer_idx, 1)      # in place already: bumps seen_tokens only
             return o
+
+        if self._can_prefill(hidden_states, reset_mask, attention_mask) and (not use_cache or last_state is not None):
+            return self._prefill(hidden_states, last_state, use_cache, past_key_values)
 
         q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
         if self.use_short_conv:

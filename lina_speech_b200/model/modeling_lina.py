@@ -97,9 +97,35 @@ class LinaModel(nn.Module):
             masked_target = y[:, 1:][logits_mask[:, 1:], :]
         else:
             masked_logits, masked_target = logits, y[:, 1:]
-        loss = F.cross_entropy(masked_logits.reshape(-1, masked_logits.shape[-1]).float(),
-                               masked_target.reshape(-1), ignore_index=1)
+        loss = self._fused_cross_entropy(logits, y, logits_mask)
+        if loss is None:
+            loss = F.cross_entropy(masked_logits.reshape(-1, masked_logits.shape[-1]).float(),
+                                   masked_target.reshape(-1), ignore_index=1)
         return logits, loss, att, masked_logits, masked_target
+
+    @staticmethod
+    def _fused_cross_entropy(logits, y, logits_mask):
+        """Inference-only: the mean cross entropy of modeling_lina.py:104-106 in one pass over the (possibly
+        vocabulary-padded, bf16) logits -- no contiguous copy, no fp32 copy, no log-softmax tensor.  None = not
+        applicable (autograd on, several quantizers, exotic strides): the caller takes the reference's route."""
+        if torch.is_grad_enabled() or not logits.is_cuda or logits.dim() != 4 or logits.shape[2] != 1:
+            return None
+        if logits.dtype not in (torch.float32, torch.bfloat16, torch.float16) or logits.stride(-1) != 1:
+            return None
+        b, n1, _, l = logits.shape
+        ld = logits.stride(1)
+        if ld < l or (b > 1 and logits.stride(0) != n1 * ld):
+            return None
+        from .. import _lib as L
+        target = y[:, 1:, 0].long().contiguous()
+        mask = logits_mask[:, 1:].bool().contiguous().view(torch.uint8) if logits_mask is not None else None
+        rows = torch.empty(2, b * n1, dtype=torch.float32, device=logits.device)
+        rc = L.lib().lina_cross_entropy_rows(L.ptr(logits), ld, L.ptr(target), L.ptr(mask), L.ptr(rows[0]), L.ptr(rows[1]),
+                                             b * n1, l, 1, L.dt(logits), L.stream(logits))
+        L.count_launches(1)
+        L.check(rc, "lina_cross_entropy_rows")
+        tot = rows.sum(dim=1)
+        return tot[0] / tot[1]
 
     # ---------------------------------------------------------------------------------------------
     def _sample(self, logits, k, first_greedy_quant, temp):

@@ -149,3 +149,85 @@ def test_add_layernorm_matches_torch(dtype, N):
     lo = dtype == torch.bfloat16
     _close(ln, ref_ln, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="add+ln")
     _close(ln0, ref_ln0, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="ln")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Ln,kd,vd", [(2, 1, 64, 128), (3, 5, 64, 128), (2, 37, 256, 512), (2, 130, 1024, 2048)])
+@pytest.mark.parametrize("tl", [8, 16])
+def test_prefill_prep_matches_oracle(dtype, B, Ln, kd, vd, tl):
+    """lina_gla_prefill_prep (conv+SiLU on q,k,v read as column slices of one projection buffer, gate non-linearity,
+    conv caches) == the oracle's ShortConvolution and logsigmoid/normalizer, for both tile heights."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(Ln * 7 + kd)
+    lib = L.lib()
+    lib.lina_debug_set_variant(0, tl)
+    try:
+        ldx = 2 * kd + 2 * vd + 16
+        proj = torch.randn(B, Ln, ldx).to(dtype)
+        gk_raw = (torch.randn(B, Ln, kd) * 3).to(dtype)
+        wq, wk, wv = (torch.randn(d, 4).to(dtype) for d in (kd, kd, vd))
+        pd, gd = proj.to(DEV), gk_raw.to(DEV)
+        q, k, gk = (torch.empty(B, Ln, kd, dtype=dtype, device=DEV) for _ in range(3))
+        v = torch.empty(B, Ln, vd, dtype=dtype, device=DEV)
+        cq, ck = (torch.ones(B, kd, 4, dtype=dtype, device=DEV) for _ in range(2))
+        cv = torch.ones(B, vd, 4, dtype=dtype, device=DEV)
+        wqd, wkd, wvd = wq.to(DEV), wk.to(DEV), wv.to(DEV)
+        xq, xk, xv = pd[..., :kd], pd[..., kd:2 * kd], pd[..., 2 * kd:2 * kd + vd]
+        rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wqd), L.ptr(wkd), L.ptr(wvd), L.ptr(gd), kd,
+                                       L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq),
+                                       B, Ln, kd, vd, 4, 16.0, -0.1, 1, L.dt(pd), L.stream(pd))
+        L.check(rc, "lina_gla_prefill_prep")
+        lo = dtype != torch.float32
+        for got, sl, w, cache in ((q, slice(0, kd), wq, cq), (k, slice(kd, 2 * kd), wk, ck),
+                                  (v, slice(2 * kd, 2 * kd + vd), wv, cv)):
+            rc_ = torch.ones(B, w.shape[0], 4)
+            ref = GO.short_conv_prefill(proj[..., sl].float(), w.float(), rc_)
+            _close(got, ref, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="conv")
+            assert torch.equal(cache.float().cpu(), rc_), "conv cache"
+        ref_g = GO.gate_logsigmoid(gk_raw.float(), 16.0, -0.1)
+        _close(gk, ref_g, 2e-3 if lo else 1e-6, 1e-2 if lo else 1e-5, what="gate")
+    finally:
+        lib.lina_debug_set_variant(0, 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rmsnorm_swishgate_strided_gate(dtype):
+    """gate read in place from a wider buffer (g_group = heads, ldg = projection row stride)."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(3)
+    Bt, H, N, ld = 50, 4, 512, 3 * 512 + 4 * 512
+    x = torch.randn(Bt * H, N).to(dtype)
+    proj = torch.randn(Bt, ld).to(dtype)
+    w = torch.empty(N).uniform_(0.5, 1.5).to(dtype)
+    xd, pd, wd = x.to(DEV), proj.to(DEV), w.to(DEV)
+    g = pd[:, 3 * 512:]
+    y = torch.empty_like(xd)
+    rc = L.lib().lina_rmsnorm_swishgate_fwd_ld(L.ptr(xd), L.ptr(g), L.ptr(wd), L.ptr(y), None, Bt * H, N, 1e-5, H, ld,
+                                               L.dt(xd), L.stream(xd))
+    L.check(rc, "lina_rmsnorm_swishgate_fwd_ld")
+    ref = GO.rmsnorm_swish_gate(x.float(), proj[:, 3 * 512:].reshape(Bt * H, N).float(), w.float())
+    lo = dtype != torch.float32
+    _close(y, ref, 2e-2 if lo else 1e-5, 1e-2 if lo else 1e-5, what="strided norm-gate")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,Vn,ld", [(37, 67, 72), (64, 4099, 4104), (9, 4099, 4099), (5, 100, 100)])
+def test_cross_entropy_rows_matches_torch(dtype, M, Vn, ld):
+    """lina_cross_entropy_rows == F.cross_entropy(logits.float(), target, ignore_index=1) incl. the row mask."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(M + Vn)
+    buf = (torch.randn(M, ld) * 4).to(dtype)
+    target = torch.randint(0, Vn, (M,))
+    target[::5] = 1
+    mask = torch.rand(M) > 0.2
+    bd, td, md = buf.to(DEV), target.to(DEV), mask.to(DEV).view(torch.uint8)
+    rows = torch.empty(2, M, dtype=torch.float32, device=DEV)
+    rc = L.lib().lina_cross_entropy_rows(L.ptr(bd), ld, L.ptr(td), L.ptr(md), L.ptr(rows[0]), L.ptr(rows[1]), M, Vn, 1,
+                                         L.dt(bd), L.stream(bd))
+    L.check(rc, "lina_cross_entropy_rows")
+    ref_rows = F.cross_entropy(buf[:, :Vn].float(), target, ignore_index=1, reduction="none") * mask
+    _close(rows[0], ref_rows, 1e-5, 1e-5, what="row losses")
+    keep = mask & (target != 1)
+    assert torch.equal(rows[1].cpu() > 0, keep)
+    ref = F.cross_entropy(buf[:, :Vn][mask].float(), target[mask], ignore_index=1)
+    _close(rows[0].sum() / rows[1].sum(), ref, 1e-5, 1e-5, what="mean loss")
