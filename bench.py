@@ -279,7 +279,11 @@ def main_ours(args):
     H, K, V = c["heads"], c["d_model"] // c["heads"], 2 * c["d_model"] // c["heads"]
     kern_ms = [a.elapsed_time(b) for (_, a, b) in prof]
     k_ms = statistics.mean(kern_ms) if kern_ms else float("nan")
-    alg_bytes = B * H * T * (3 * K + 2 * V) * 2                      # bf16 q,k,gk + v,o per launch
+    pregated = any(kind == "chunk_pregated" for (kind, _, _) in prof)
+    if pregated:     # q~, k~, v in + o out (bf16) + the per-chunk decay vectors (fp32); gk is consumed by the prep pass
+        alg_bytes = B * H * T * (2 * K + 2 * V) * 2 + B * H * ((T + 63) // 64) * K * 4
+    else:
+        alg_bytes = B * H * T * (3 * K + 2 * V) * 2                  # bf16 q,k,gk + v,o per launch
     alg_flops = B * H * T * (4 * K * V + 64 * (K + V))               # SURVEY 8(d), C = 64
     pk = peaks()
     uses_tc = bool(_lib.lib().lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, _lib.BF16))
@@ -287,10 +291,11 @@ def main_ours(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
     if uses_tc and os.path.exists(tpath) and (B, H, T, K, V) == (32, 4, 2048, 256, 512):
         with open(tpath) as f:
-            t = json.load(f).get("gla_chunk_fwd_sm100_kernel<256>")
+            t = json.load(f).get("gla_chunk_fwd_sm100_kernel<256,4>" if pregated else "gla_chunk_fwd_sm100_kernel<256>")
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    roofline = {"kernel": "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)",
+    roofline = {"kernel": ("lina_gla_chunk_fwd_pregated_bthd (tcgen05, operands gated by lina_gla_prefill_prep_gated)" if pregated
+                           else "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)"),
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"],
                 "launch_ms": k_ms, "launches_timed": len(kern_ms), "share_of_step": sum(kern_ms) / ms,

@@ -130,6 +130,21 @@ int lina_gla_prefill_prep(const void *xq, const void *xk, const void *xv, long l
                           int B, int L, int Dk, int Dv, int W, float gate_normalizer, float clamp_min, int use_clamp,
                           int dtype, void *stream);
 
+/* Same pass with the chunk gating of the tensor-core GLA kernel folded in (bf16 only): instead of q, k, gk it writes
+ *   qg = scale * q * e^G,  kg = k * e^-G   [B,L,H*K] bf16     (G = cumsum of gk inside each 64-token chunk, fp32)
+ *   decay[b,h,n,:] = e^{G at the chunk end}  [B,H,ceil(L/64),K] fp32
+ * i.e. the MMA operands FLA/fla/ops/gla/chunk_util.py:28-65 (prepare_qg_kg) materialises, for lina_gla_chunk_fwd_pregated_bthd.
+ * v = SiLU(ShortConvolution(x_v)) as above.  The gate normalizer must be a power of two (16 in the shipped model). */
+int lina_gla_prefill_prep_gated(const void *xq, const void *xk, const void *xv, long long ldx,
+                                const void *wq, const void *wk, const void *wv, const void *gk_raw, long long ldg,
+                                void *qg, void *kg, void *v, float *decay, void *cq, void *ck, void *cv, int cache_dtype,
+                                int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale, void *stream);
+/* The chunkwise GLA forward (lina_gla_chunk_fwd_bthd) on those pre-gated operands: no in-kernel gate pre-pass, gk is
+ * never read.  Tensor-core envelope only. */
+int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
+                                     const void *h0, int h0_dtype, void *o, float *ht,
+                                     int B, int H, int T, int K, int V, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.
  * Replaces causal_conv1d_fn / causal_conv1d_update (causal-conv1d 1.3.0.post1, call sites
@@ -220,7 +235,7 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * ------------------------------------------------------------------------------------------- */
 /* A/B switches for kernel variants (bring-up only; process-global, not thread-safe): key 0 = rows per thread of the
  * prep / short-conv tile kernel (8 or 16), key 1 = 1 selects the round-1 sliding-window short-conv kernel,
- * key 2 = bit mask of tcgen05 GLA kernel options. */
+ * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16. */
 int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);

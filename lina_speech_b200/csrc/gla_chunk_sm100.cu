@@ -110,11 +110,15 @@ struct TMaps { CUtensorMap q, k, g, v; };
 //            block c is rescaled and stored) instead of ld32 -> wait -> compute -> store per block;
 // OPT bit 1: the gate pre-pass keeps its gk rows in registers between the column-sum pass and the rescale pass
 //            (8 fewer 16-byte shared loads per thread and item).
+// OPT bit 2 (PRE): the operands arrive PRE-GATED -- tm.q / tm.k map q~ = scale q e^G and k~ = k e^-G (written by
+//            lina_gla_prefill_prep_gated together with `decay` [B,H,NT,K] = e^{G_C}); TMA lands them straight in operand
+//            layout, the gate pre-pass warps idle, gk is never read, the chunk decay vector is a 1-D bulk copy.
 template <int K, int OPT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
                            bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, int H, int bthd, float scale,
-                           long long *__restrict__ trace) {
+                           long long *__restrict__ trace, const float *__restrict__ decay) {
+    constexpr bool PRE = (OPT & 4) != 0;
     using cfg = Cfg<K>;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -151,6 +155,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 8) {
+      if (!PRE) {
         // ====================== warps 0-7: gate pre-pass, in place on the landed q / k rows ======================
         const int p = tid;                         // 0..255
         const int c = p % KC, rg = p / KC;         // 16-byte column group, row group
@@ -229,21 +234,26 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             mbar_arrive(&bars[B_G_EMPTY0 + s]);
             if (p == 0) TRACE(0, n, 1);
         }
+      }
     } else if (warp == 19) {
         // ====================== TMA loader (one thread): q, k -> operand tile of the stage, gk -> side tile, v ======================
         if (lane == 0) {
-            tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.g); tma_prefetch_desc(&tm.v);
+            tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.v);
+            if (!PRE) tma_prefetch_desc(&tm.g);
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1, t0 = n * C;
                 const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
                 const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
                 wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
-                wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                if (!PRE) wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
                 TRACE(1, n, 0);
-                mbar_expect_tx(&bars[B_RAW_FULL0 + s], cfg::RAW_TX);
+                mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + K * 4u) : cfg::RAW_TX);
+                if (PRE)       // dvec ring slot n % 3 <- decay[b, h, n, :]  (safe: the loader runs at most 2 items ahead)
+                    tma_load_1d(smem_u32(dvec + (n % 3) * K), decay + ((size_t)bh * n_items + n) * K, K * 4u,
+                                &bars[B_RAW_FULL0 + s]);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                    if (!PRE) tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                     tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                     tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                 }
@@ -268,7 +278,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1;
                 const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
-                wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);
+                wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
                 TRACE(2, n, 0);
@@ -397,7 +407,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         mbar_arrive(&bars[B_SA_FULL]);
         for (int n = 0; n < n_items; ++n) {
             const int s = n & 1;
-            wait_bar(&bars[B_QK_FULL0 + s], (n >> 1) & 1);         // dvec of this item is published with it
+            wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);   // dvec of this item is published with it
             wait_bar(&bars[B_ST_FULL], n & 1);
             tc_fence_after();
             if (r == 0) TRACE(5, n, 0);
@@ -474,7 +484,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
 
 template <int K, int OPT = 0>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
-           float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr) {
+           float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr,
+           const float *decay = nullptr) {
     using cfg = Cfg<K>;
     static thread_local bool configured = false;
     if (!configured) {
@@ -500,7 +511,7 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
     }
     dim3 grid(V / BV, B * H);
     gla_chunk_fwd_sm100_kernel<K, OPT><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
-                                                                   trace);
+                                                                        trace, decay);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
 }
@@ -553,6 +564,22 @@ extern "C" int lina_gla_chunk_fwd_bthd(const void *q, const void *k, const void 
                  "gla_chunk_fwd_bthd: only the tensor-core envelope (bf16, K in {64,128,256}, V %% 128 == 0, T >= 32) "
                  "reads the [B,T,H,D] layout in place; make the tensors [B,H,T,D]-contiguous and call lina_gla_chunk_fwd");
     return chunk_fwd_tc(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, K, V, 1, scale, stream);
+}
+
+// Pre-gated operands (see OPT bit 2 of the kernel): qg = scale q e^G, kg = k e^-G [B,T,H,K] bf16, decay [B,H,NT,K] fp32
+// with NT = ceil(T / 64), as written by lina_gla_prefill_prep_gated; v, o [B,T,H,V]; h0 / ht [B,H,K,V].
+extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
+                                                const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T,
+                                                int K, int V, void *stream) {
+    LINA_REQUIRE(qg && kg && v && decay && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: null tensor pointer");
+    LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: bad h0 dtype");
+    LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16), LINA_ERR_UNSUPPORTED,
+                 "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
+    LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
 }
 
 // bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]

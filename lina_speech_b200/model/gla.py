@@ -13,6 +13,7 @@ The arithmetic between the dense projections runs in liblina_b200.so:
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Optional, Tuple
 
@@ -22,6 +23,7 @@ import torch.nn.functional as F
 from einops import einsum, rearrange, repeat
 
 from .. import _lib as L
+from ..fla_api import ops as fla_ops
 from ..fla_api import (Cache, FusedRMSNormSwishGate, ShortConvolution, chunk_gla, fused_chunk_gla,
                        fused_recurrent_gla)
 from .contracts import AttentiveRNN
@@ -32,6 +34,8 @@ from .crossatt import BlindCrossAttention, CrossAttention, tensor_version
 # LINA_CAT5=1 folds the rank-16 gate projection into the concatenated GEMM as well (N = 6160)
 FUSED_PREFILL = os.environ.get("LINA_FUSED_PREFILL", "1") != "0"
 CAT5 = os.environ.get("LINA_CAT5", "0") == "1"
+# LINA_PREGATED=0: the post-projection pass writes q, k, gk and the GLA kernel gates them itself (4x redundantly)
+PREGATED = os.environ.get("LINA_PREGATED", "1") != "0"
 
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):
@@ -167,30 +171,65 @@ class GatedLinearAttention(nn.Module):
         gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
         ldx = proj.shape[-1]
         xq, xk, xv, g = proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd], proj[..., 2 * kd + vd:2 * kd + 2 * vd]
-        q = torch.empty(B, T, kd, dtype=x.dtype, device=x.device)
-        k, gk = torch.empty_like(q), torch.empty_like(q)
-        v = torch.empty(B, T, vd, dtype=x.dtype, device=x.device)
         cq = ck = cv = None
         if use_cache and last_state is not None:
             cq, ck, cv = last_state[0], last_state[1], last_state[2]
             if not (cq.is_contiguous() and ck.is_contiguous() and cv.is_contiguous()):
                 raise ValueError("conv caches must be contiguous [B, D, W]")
         wq, wk, wv = (c.weight.to(x.dtype).contiguous() for c in (self.q_conv1d, self.k_conv1d, self.v_conv1d))
-        rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
-                                       L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk),
-                                       L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0, B, T, kd, vd,
-                                       self.conv_size, float(self.gate_logit_normalizer), float(self.clamp_min or 0.0),
-                                       int(self.clamp_min is not None), L.dt(x), L.stream(x))
-        L.count_launches(1)
-        L.check(rc, "lina_gla_prefill_prep")
-        q4, k4, gk4 = (t.view(B, T, H, K).transpose(1, 2) for t in (q, k, gk))
-        v4 = v.view(B, T, H, V).transpose(1, 2)
         recurrent_state = last_state[-1] if use_cache else None
-        op = {"fused_recurrent": fused_recurrent_gla, "fused_chunk": fused_chunk_gla, "chunk": chunk_gla}[self.mode]
-        o, recurrent_state = op(q4, k4, v4, gk4, initial_state=recurrent_state, output_final_state=use_cache)
-        if past_key_values is not None and not self.training:           # model/gla.py:205-213
-            past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
-        o = o.transpose(1, 2)
+        q = torch.empty(B, T, kd, dtype=x.dtype, device=x.device)
+        k = torch.empty_like(q)
+        v = torch.empty(B, T, vd, dtype=x.dtype, device=x.device)
+        norm = float(self.gate_logit_normalizer)
+        pregated = (PREGATED and x.dtype == torch.bfloat16 and self.mode in ("fused_chunk", "chunk")
+                    and self.clamp_min is None and norm > 0 and math.frexp(norm)[0] == 0.5
+                    and bool(lib.lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, L.BF16))
+                    and (recurrent_state is None or recurrent_state.dtype in (torch.float32, torch.bfloat16, torch.float16)))
+        if pregated:
+            # q, k hold the gated MMA operands q~ = scale q e^G, k~ = k e^-G; gk is never materialised
+            nt = (T + 63) // 64
+            decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=x.device)
+            rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
+                                                 L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay),
+                                                 L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0,
+                                                 B, T, H, K, V, self.conv_size, norm, float(K) ** -0.5, L.stream(x))
+            L.count_launches(2)
+            L.check(rc, "lina_gla_prefill_prep_gated")
+            h0 = recurrent_state.contiguous() if recurrent_state is not None else None
+            o = torch.empty(B, T, H, V, dtype=x.dtype, device=x.device)
+            ht = torch.empty(B, H, K, V, dtype=torch.float32, device=x.device) if use_cache else None
+            prof = fla_ops.PROFILE
+            if prof is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(torch.cuda.current_stream(x.device))
+            rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), L.ptr(h0),
+                                                      L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V,
+                                                      L.stream(x))
+            L.count_launches(1)
+            L.check(rc, "lina_gla_chunk_fwd_pregated_bthd")
+            if prof is not None:
+                ev1.record(torch.cuda.current_stream(x.device))
+                prof.append(("chunk_pregated", ev0, ev1))
+            recurrent_state = ht
+            if past_key_values is not None and not self.training:       # model/gla.py:205-213
+                past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
+        else:
+            gk = torch.empty_like(q)
+            rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
+                                           L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk),
+                                           L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0, B, T, kd, vd,
+                                           self.conv_size, norm, float(self.clamp_min or 0.0),
+                                           int(self.clamp_min is not None), L.dt(x), L.stream(x))
+            L.count_launches(1)
+            L.check(rc, "lina_gla_prefill_prep")
+            q4, k4, gk4 = (t.view(B, T, H, K).transpose(1, 2) for t in (q, k, gk))
+            v4 = v.view(B, T, H, V).transpose(1, 2)
+            op = {"fused_recurrent": fused_recurrent_gla, "fused_chunk": fused_chunk_gla, "chunk": chunk_gla}[self.mode]
+            o, recurrent_state = op(q4, k4, v4, gk4, initial_state=recurrent_state, output_final_state=use_cache)
+            if past_key_values is not None and not self.training:       # model/gla.py:205-213
+                past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
+            o = o.transpose(1, 2)
         if not o.is_contiguous():
             o = o.contiguous()
         y = torch.empty_like(o)

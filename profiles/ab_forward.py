@@ -41,17 +41,16 @@ def run(n=5):
 
 res = {}
 configs = [
-    ("round1_path (op by op, torch CE)", dict(fused=False, cat5=False, tl=0, opt=0, ce=False)),
-    ("fused_prefill", dict(fused=True, cat5=False, tl=0, opt=0, ce=False)),
-    ("fused_prefill + fused CE", dict(fused=True, cat5=False, tl=0, opt=0, ce=True)),
-    ("fused_prefill + CE + TL16", dict(fused=True, cat5=False, tl=16, opt=0, ce=True)),
-    ("fused_prefill + CE + cat5", dict(fused=True, cat5=True, tl=0, opt=0, ce=True)),
-    ("fused_prefill + CE + OPT1", dict(fused=True, cat5=False, tl=0, opt=1, ce=True)),
-    ("fused_prefill + CE + OPT2", dict(fused=True, cat5=False, tl=0, opt=2, ce=True)),
-    ("fused_prefill + CE + OPT3", dict(fused=True, cat5=False, tl=0, opt=3, ce=True)),
+    ("round1_path (op by op, torch CE)", dict(fused=False, cat5=False, tl=0, opt=0, ce=False, pre=False)),
+    ("op by op + fused CE", dict(fused=False, cat5=False, tl=0, opt=0, ce=True, pre=False)),
+    ("fused_prefill + CE", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=False)),
+    ("fused_prefill + CE + OPT2", dict(fused=True, cat5=False, tl=0, opt=2, ce=True, pre=False)),
+    ("fused_prefill + CE + pregated", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True)),
+    ("fused_prefill + CE + pregated + TL16", dict(fused=True, cat5=False, tl=16, opt=0, ce=True, pre=True)),
+    ("fused_prefill + CE + pregated + cat5", dict(fused=True, cat5=True, tl=0, opt=0, ce=True, pre=True)),
 ]
 for name, cf in configs:
-    G.FUSED_PREFILL, G.CAT5 = cf["fused"], cf["cat5"]
+    G.FUSED_PREFILL, G.CAT5, G.PREGATED = cf["fused"], cf["cat5"], cf["pre"]
     lib.lina_debug_set_variant(0, cf["tl"])
     lib.lina_debug_set_variant(2, cf["opt"])
     ML.LinaModel._fused_cross_entropy = staticmethod(fused_ce) if cf["ce"] else staticmethod(lambda *a: None)

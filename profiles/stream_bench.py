@@ -78,15 +78,29 @@ for tl in (8, 16):
     report(f"prefill_prep_TL{tl} (q,k,v conv + gate)", timeit(prep), prep_bytes)
 lib.lina_debug_set_variant(0, 0)
 
+# ---- the same pass with the chunk gating folded in (q~, k~, decay) ----
+nt = (T + 63) // 64
+decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=dev)
+
+
+def prep_gated():
+    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv), L.ptr(gk_raw), kd,
+                                         L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, None, None, 0, B, T, H, K, V, 4,
+                                         16.0, K ** -0.5, st())
+    assert rc == 0, lib.lina_last_error_string()
+report("prefill_prep_gated (v conv + q~,k~,decay)", timeit(prep_gated), (2 * (3 * kd + vd) + 2 * (2 * kd + vd)) * M)
+
 xq_c, xv_c = xq.contiguous(), xv.contiguous()
-for variant, name in ((0, "tiles"), (1, "round1_sliding")):
-    lib.lina_debug_set_variant(1, variant)
+for variant, name in ((0, "tiles_f32x2"), (3, "tiles_scalar"), (1, "round1_sliding")):
+    lib.lina_debug_set_variant(1, 1 if variant == 1 else 0)
+    lib.lina_debug_set_variant(3, 1 if variant == 3 else 0)
     for x_, w_, y_, d_ in ((xq_c, wq, q, kd), (xv_c, wv, v, vd)):
         def conv(x_=x_, w_=w_, y_=y_, d_=d_):
             rc = lib.lina_short_conv_fwd(L.ptr(x_), L.ptr(w_), L.ptr(y_), None, 0, B, T, d_, 4, 1, L.BF16, st())
             assert rc == 0
         report(f"short_conv_fwd_{name}_D{d_}", timeit(conv), 2 * 2 * d_ * M)
 lib.lina_debug_set_variant(1, 0)
+lib.lina_debug_set_variant(3, 0)
 
 
 def gate():
@@ -173,6 +187,19 @@ for opt in (0, 1, 2, 3):
     res[f"gla_chunk_fwd_tcgen05_OPT{opt}"].update(max_diff_o_vs_opt0=d_o, max_diff_ht_vs_opt0=d_h)
     print(f"   OPT{opt}: max|o - o_opt0| = {d_o:.3e}, max|ht - ht_opt0| = {d_h:.3e}", flush=True)
 lib.lina_debug_set_variant(2, 0)
+
+# ---- pre-gated operands: prep_gated + the tcgen05 kernel without its gate pre-pass ----
+del q4, k4, gk4
+prep_gated()
+v_bthd = v.view(B, T, H, V)
+o_b = torch.empty(B, T, H, V, dtype=bf, device=dev)
+
+
+def gla_pre():
+    rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, 0, L.ptr(o_b), None, B, H, T, K, V, st())
+    assert rc == 0, lib.lina_last_error_string()
+report("gla_chunk_fwd_pregated_bthd (tcgen05)", timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
+res["gla_chunk_fwd_pregated_bthd (tcgen05)"]["finite"] = bool(torch.isfinite(o_b.float()).all())
 
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
 with open(out_path, "w") as f:

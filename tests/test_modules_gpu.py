@@ -231,3 +231,104 @@ def test_cross_entropy_rows_matches_torch(dtype, M, Vn, ld):
     assert torch.equal(rows[1].cpu() > 0, keep)
     ref = F.cross_entropy(buf[:, :Vn][mask].float(), target[mask], ignore_index=1)
     _close(rows[0].sum() / rows[1].sum(), ref, 1e-5, 1e-5, what="mean loss")
+
+
+@pytest.mark.parametrize("B,T,H,K,V,use_h0", [(2, 150, 2, 64, 128, False), (1, 300, 4, 256, 512, True), (2, 64, 1, 128, 128, True),
+                                              (1, 33, 2, 64, 256, False)])
+def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
+    """lina_gla_prefill_prep_gated (conv + SiLU + gate + chunk cumsum -> q~, k~, decay) and the tcgen05 kernel on
+    those operands == the oracle's conv -> logsigmoid/16 -> recurrence on the same inputs (bf16 I/O tolerance)."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(T + K)
+    lib = L.lib()
+    bf = torch.bfloat16
+    kd, vd = H * K, H * V
+    ldx = 2 * kd + 2 * vd
+    proj = torch.randn(B, T, ldx).to(bf)
+    gk_raw = (torch.randn(B, T, kd) * 2).to(bf)
+    wq, wk, wv = (torch.randn(d, 4).mul(0.5).to(bf) for d in (kd, kd, vd))
+    h0 = torch.randn(B, H, K, V) if use_h0 else None
+    scale = K ** -0.5
+    # oracle: fp32 math on the bf16-valued inputs
+    cq_r, ck_r, cv_r = torch.ones(B, kd, 4), torch.ones(B, kd, 4), torch.ones(B, vd, 4)
+    q = GO.short_conv_prefill(proj[..., :kd].float(), wq.float(), cq_r)
+    k = GO.short_conv_prefill(proj[..., kd:2 * kd].float(), wk.float(), ck_r)
+    v = GO.short_conv_prefill(proj[..., 2 * kd:2 * kd + vd].float(), wv.float(), cv_r)
+    gk = GO.gate_logsigmoid(gk_raw.float()).to(bf).float()                       # the reference's gk is a bf16 tensor
+    hd = lambda t, d: t.view(B, T, H, d).transpose(1, 2)
+    ro, rht = GO.recurrent_gla(hd(q, K), hd(k, K), hd(v, V), hd(gk, K), scale=scale, initial_state=h0)
+    # ours
+    pd, gd = proj.to(DEV), gk_raw.to(DEV)
+    qg, kg = (torch.empty(B, T, kd, dtype=bf, device=DEV) for _ in range(2))
+    vv = torch.empty(B, T, vd, dtype=bf, device=DEV)
+    nt = (T + 63) // 64
+    decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=DEV)
+    cq, ck = (torch.ones(B, kd, 4, dtype=bf, device=DEV) for _ in range(2))
+    cv = torch.ones(B, vd, 4, dtype=bf, device=DEV)
+    wqd, wkd, wvd = wq.to(DEV), wk.to(DEV), wv.to(DEV)
+    xq, xk, xv = pd[..., :kd], pd[..., kd:2 * kd], pd[..., 2 * kd:2 * kd + vd]
+    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wqd), L.ptr(wkd), L.ptr(wvd), L.ptr(gd), kd,
+                                         L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(cq), L.ptr(ck), L.ptr(cv),
+                                         L.dt(cq), B, T, H, K, V, 4, 16.0, scale, L.stream(pd))
+    L.check(rc, "lina_gla_prefill_prep_gated")
+    for got, ref in ((cq, cq_r), (ck, ck_r), (cv, cv_r)):
+        assert torch.equal(got.float().cpu(), ref), "conv cache"
+    _close(vv, v, 2e-2, 1e-2, what="v conv")
+    # gated operands against the oracle's chunk-local cumsum
+    G = torch.cat([gk[:, c:c + 64].cumsum(1) for c in range(0, T, 64)], 1)
+    _close(qg, q * G.exp() * scale, 2e-2, 1e-2, what="q~")
+    _close(kg, k * (-G).exp(), 2e-2, 1e-2, what="k~")
+    GC = torch.stack([gk[:, c:c + 64].sum(1) for c in range(0, T, 64)], 1)         # [B, NT, kd]
+    _close(decay, GC.exp().view(B, nt, H, K).transpose(1, 2), 1e-5, 1e-4, what="decay")
+    o = torch.empty(B, T, H, V, dtype=bf, device=DEV)
+    ht = torch.empty(B, H, K, V, dtype=torch.float32, device=DEV)
+    h0d = h0.to(DEV) if h0 is not None else None
+    rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(h0d),
+                                              L.dt(h0d) if h0d is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V,
+                                              L.stream(pd))
+    L.check(rc, "lina_gla_chunk_fwd_pregated_bthd")
+    torch.cuda.synchronize()
+    _close(o.transpose(1, 2), ro, 3e-2 * ro.abs().max().item(), 0.0, what="o (pregated tcgen05)")
+    _close(ht, rht, 3e-2 * rht.abs().max().item(), 0.0, what="final state")
+
+
+def test_bf16_layer_prefill_pregated_matches_op_by_op_and_oracle():
+    """GatedLinearAttention at the flagship head size (d1024, H4, K256, V512) in bf16: the pregated inference path ==
+    the same layer with LINA_PREGATED / LINA_FUSED_PREFILL off (within bf16 rounding) == the oracle layer in fp32;
+    prefill with a cache then continues with the fused decode step."""
+    import lina_speech_b200.model.gla as G
+    from lina_speech_b200.fla_api import Cache
+    from oracle import lina_oracle as LO
+    torch.manual_seed(5)
+    B, T, d, H = 2, 200, 1024, 4
+    layer = G.GatedLinearAttention(hidden_size=d, num_heads=H, use_short_conv=True, layer_idx=0).eval()
+    with torch.no_grad():
+        layer.g_norm_swish_gate.weight.uniform_(0.5, 1.5)
+        layer.gk_proj[1].bias.normal_()
+        for p in layer.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    sd = {"l." + k: v.detach().clone() for k, v in layer.state_dict().items()}
+    layer = layer.to(DEV).to(torch.bfloat16)
+    x = torch.randn(B, T, d).to(torch.bfloat16)
+    ref = LO.gla_layer(sd, "l", x.float(), H)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    outs = {}
+    saved = (G.FUSED_PREFILL, G.PREGATED)
+    try:
+        for name, fp, pg in (("op_by_op", False, False), ("fused", True, False), ("pregated", True, True)):
+            G.FUSED_PREFILL, G.PREGATED = fp, pg
+            cache = Cache()
+            cache.update(layer.init_state(B), 0, offset=0)
+            with torch.inference_mode():
+                y = layer(x.to(DEV), past_key_values=cache, use_cache=True)
+                y1 = layer(x[:, :1].to(DEV), past_key_values=cache, use_cache=True)
+            outs[name] = (y.float().cpu(), y1.float().cpu(), [s.float().cpu() for s in cache.states[0]])
+    finally:
+        G.FUSED_PREFILL, G.PREGATED = saved
+    scale = ref.abs().max().item()
+    for name, (y, y1, st) in outs.items():
+        _close(y, ref, 3e-2 * scale, 0.0, what=f"{name} vs oracle")
+        _close(y, outs["op_by_op"][0], 2e-2 * scale, 0.0, what=f"{name} vs op-by-op")
+        _close(y1, outs["op_by_op"][1], 3e-2 * outs["op_by_op"][1].abs().max().item(), 0.0, what=f"{name} next step")
+        for a, b in zip(st, outs["op_by_op"][2]):
+            _close(a, b, 2e-2 * max(b.abs().max().item(), 1e-3), 0.0, what=f"{name} cache state")
