@@ -134,8 +134,9 @@ int lina_gla_prefill_prep(const void *xq, const void *xk, const void *xv, long l
  *   qg = scale * q * e^G,  kg = k * e^-G   [B,L,H*K] bf16     (G = cumsum of gk inside each 64-token chunk, fp32)
  *   decay[b,h,n,:] = e^{G at the chunk end}  [B,H,ceil(L/64),K] fp32
  * i.e. the MMA operands FLA/fla/ops/gla/chunk_util.py:28-65 (prepare_qg_kg) materialises, for lina_gla_chunk_fwd_pregated_bthd.
- * v = SiLU(ShortConvolution(x_v)) as above.  The gate normalizer must be a power of two (16 in the shipped model). */
-int lina_gla_prefill_prep_gated(const void *xq, const void *xk, const void *xv, long long ldx,
+ * v = SiLU(ShortConvolution(x_v)) as above; xq / xk / xv have their own row strides (separate or concatenated GEMMs).
+ * The gate normalizer must be a power of two (16 in the shipped model). */
+int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const void *xk, long long ldk, const void *xv, long long ldv,
                                 const void *wq, const void *wk, const void *wv, const void *gk_raw, long long ldg,
                                 void *qg, void *kg, void *v, float *decay, void *cq, void *ck, void *cv, int cache_dtype,
                                 int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale, void *stream);
@@ -144,6 +145,14 @@ int lina_gla_prefill_prep_gated(const void *xq, const void *xk, const void *xv, 
 int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
                                      const void *h0, int h0_dtype, void *o, float *ht,
                                      int B, int H, int T, int K, int V, void *stream);
+
+/* General form of the same kernel: [B,H,T,D] (bthd = 0) or [B,T,H,D] (bthd = 1) operands; row_decay != 0: `decay` is
+ * [B,H,NT,V] and scales the VALUE dim of the state, out_f32 != 0: o is fp32 (only (0,0) and (1,1) are instantiated).
+ * The chunked BACKWARD of the GLA op (replacing FLA/fla/ops/gla/chunk.py:140-341 + FLA/fla/ops/common/chunk_h.py:111-189)
+ * is five runs of this kernel on role-swapped, time-reversed operands -- see lina_speech_b200/fla_api/ops.py:_bwd_tc. */
+int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, const float *decay,
+                                const void *h0, int h0_dtype, void *o, float *ht,
+                                int B, int H, int T, int K, int V, int bthd, int row_decay, int out_f32, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.

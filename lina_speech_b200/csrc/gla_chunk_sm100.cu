@@ -119,6 +119,11 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                            bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, int H, int bthd, float scale,
                            long long *__restrict__ trace, const float *__restrict__ decay) {
     constexpr bool PRE = (OPT & 4) != 0;
+    // OPT bit 3 (ROW, with PRE): the chunk decay scales the VALUE dim (rows of the transposed state = TMEM lanes) instead of
+    //            the key dim: decay is [B,H,NT,V].  This is the form the backward needs (contraction over V, state S^T).
+    // OPT bit 4 (OUT32): o is written as fp32 (the backward's dq~ / dk~ partial sums feed a cumsum).
+    constexpr bool ROW = (OPT & 8) != 0, OUT32 = (OPT & 16) != 0;
+    static_assert(!ROW || PRE, "row decay needs pre-gated operands");
     using cfg = Cfg<K>;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -247,8 +252,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
                 if (!PRE) wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
                 TRACE(1, n, 0);
-                mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + K * 4u) : cfg::RAW_TX);
-                if (PRE)       // dvec ring slot n % 3 <- decay[b, h, n, :]  (safe: the loader runs at most 2 items ahead)
+                mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + (ROW ? 0u : K * 4u)) : cfg::RAW_TX);
+                if (PRE && !ROW)   // dvec ring slot n % 3 <- decay[b, h, n, :]  (safe: the loader runs at most 2 items ahead)
                     tma_load_1d(smem_u32(dvec + (n % 3) * K), decay + ((size_t)bh * n_items + n) * K, K * 4u,
                                 &bars[B_RAW_FULL0 + s]);
 #pragma unroll
@@ -370,8 +375,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_O_EMPTY]);
-            bf16 *ob = o + obase + (size_t)t0 * o_tstride + v0 + r;
             const int nrow = min(C, T - t0);
+            if (OUT32) {
+                float *ob = reinterpret_cast<float *>(o) + obase + (size_t)t0 * o_tstride + v0 + r;
+#pragma unroll
+                for (int t = 0; t < C; ++t) {
+                    if (t < nrow) ob[(size_t)t * o_tstride] = __uint_as_float(orr[t >> 5][t & 31]);
+                }
+            } else {
+            bf16 *ob = o + obase + (size_t)t0 * o_tstride + v0 + r;
             if (nrow == C) {
 #pragma unroll
                 for (int t = 0; t < C; ++t) { *ob = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31])); ob += o_tstride; }
@@ -380,6 +392,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 for (int t = 0; t < C; ++t) {
                     if (t < nrow) ob[(size_t)t * o_tstride] = __float2bfloat16_rn(__uint_as_float(orr[t >> 5][t & 31]));
                 }
+            }
             }
             if (r == 0) TRACE(4, n, 1);
         }
@@ -413,6 +426,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             if (r == 0) TRACE(5, n, 0);
             const float *dv = dvec + (n % 3) * K;
             const bool last = n == n_items - 1;
+            float rd = 1.f;
+            if (ROW) rd = decay[((size_t)bh * n_items + n) * V + v0 + r];
             if (OPT & 1) {
                 // 16-column blocks, double-buffered: ld(c+1) is issued before block c is processed
                 auto process = [&](uint32_t (&f)[16], int c) {
@@ -454,7 +469,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 d4 = *reinterpret_cast<const float4 *>(dv + cb * 32 + j);
+                    const float4 d4 = ROW ? make_float4(rd, rd, rd, rd) : *reinterpret_cast<const float4 *>(dv + cb * 32 + j);
                     f[j + 0] = __float_as_uint(__uint_as_float(f[j + 0]) * d4.x);
                     f[j + 1] = __float_as_uint(__uint_as_float(f[j + 1]) * d4.y);
                     f[j + 2] = __float_as_uint(__uint_as_float(f[j + 2]) * d4.z);
@@ -580,6 +595,31 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
     if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+}
+
+// General pre-gated entry: layout [B,H,T,D] (bthd = 0) or [B,T,H,D] (bthd = 1); row_decay != 0: decay is [B,H,NT,V] and scales
+// the value dim (the state's rows), out_f32 != 0: o is fp32.  Used by the backward (lina_speech_b200/fla_api/ops.py), which
+// is five runs of this kernel on role-swapped / time-reversed operands.
+extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, const float *decay,
+                                           const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T, int K,
+                                           int V, int bthd, int row_decay, int out_f32, void *stream) {
+    LINA_REQUIRE(qg && kg && v && decay && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: null tensor pointer");
+    LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: bad h0 dtype");
+    LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16), LINA_ERR_UNSUPPORTED,
+                 "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
+    LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
+    LINA_REQUIRE((row_decay != 0) == (out_f32 != 0), LINA_ERR_UNSUPPORTED,
+                 "gla_chunk_fwd_pregated: only (column decay, bf16 out) and (row decay, fp32 out) are instantiated");
+    cudaStream_t st = (cudaStream_t)stream;
+    bthd = bthd ? 1 : 0;
+    if (row_decay) {
+        if (K == 64) return launch<64, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+        if (K == 128) return launch<128, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+        return launch<256, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+    }
+    if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+    if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+    return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
 }
 
 // bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]

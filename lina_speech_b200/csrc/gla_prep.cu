@@ -270,7 +270,7 @@ struct GateArgs {
     bf16 *qg, *kg;
     float *decay;
     void *cq, *ck;
-    long long ldx, ldg;
+    long long ldq, ldk, ldg;
     int B, L, Dk, K, NT, cache_dtype;
     float log2_scale, gate_c;        // gate_c = log2(e) / normalizer
 };
@@ -292,7 +292,7 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
     const long long b = rest / a.NT;
     if (b >= a.B) return;
     const int L = a.L, d0 = cg * 4, t0 = n * GC;
-    const bf16 *xq = a.xq + (size_t)b * L * a.ldx + d0, *xk = a.xk + (size_t)b * L * a.ldx + d0;
+    const bf16 *xq = a.xq + (size_t)b * L * a.ldq + d0, *xk = a.xk + (size_t)b * L * a.ldk + d0;
     const bf16 *gr = a.graw + (size_t)b * L * a.ldg + d0;
     bf16 *qo = a.qg + (size_t)b * L * a.Dk + d0, *ko = a.kg + (size_t)b * L * a.Dk + d0;
     float2 wq[2][4], wk[2][4];
@@ -304,8 +304,8 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
         const int l = t0 - 3 + i;
         uint2 rq = make_uint2(0, 0), rk = make_uint2(0, 0);
         if (l >= 0) {
-            rq = *reinterpret_cast<const uint2 *>(xq + (size_t)l * a.ldx);
-            rk = *reinterpret_cast<const uint2 *>(xk + (size_t)l * a.ldx);
+            rq = *reinterpret_cast<const uint2 *>(xq + (size_t)l * a.ldq);
+            rk = *reinterpret_cast<const uint2 *>(xk + (size_t)l * a.ldk);
         }
         winq[0][i] = bf2_to_f2(rq.x); winq[1][i] = bf2_to_f2(rq.y);
         wink[0][i] = bf2_to_f2(rk.x); wink[1][i] = bf2_to_f2(rk.y);
@@ -319,8 +319,8 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
         for (int i = 0; i < GRB; ++i) {
             const int l = t0 + r0 + i;
             if (r0 + i < nrow) {
-                rq[i] = *reinterpret_cast<const uint2 *>(xq + (size_t)l * a.ldx);
-                rk[i] = *reinterpret_cast<const uint2 *>(xk + (size_t)l * a.ldx);
+                rq[i] = *reinterpret_cast<const uint2 *>(xq + (size_t)l * a.ldq);
+                rk[i] = *reinterpret_cast<const uint2 *>(xk + (size_t)l * a.ldk);
                 rg[i] = *reinterpret_cast<const uint2 *>(gr + (size_t)l * a.ldg);
             } else {
                 rq[i] = rk[i] = rg[i] = make_uint2(0, 0);
@@ -361,8 +361,8 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
             const int l = L - 4 + j;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float vq = l >= 0 ? __bfloat162float(xq[(size_t)l * a.ldx + c]) : 0.f;
-                const float vk = l >= 0 ? __bfloat162float(xk[(size_t)l * a.ldx + c]) : 0.f;
+                const float vq = l >= 0 ? __bfloat162float(xq[(size_t)l * a.ldq + c]) : 0.f;
+                const float vk = l >= 0 ? __bfloat162float(xk[(size_t)l * a.ldk + c]) : 0.f;
                 store_dyn(a.cq, a.cache_dtype, ((size_t)b * a.Dk + d0 + c) * 4 + j, vq);
                 store_dyn(a.ck, a.cache_dtype, ((size_t)b * a.Dk + d0 + c) * 4 + j, vk);
             }
@@ -453,7 +453,8 @@ extern "C" int lina_gla_prefill_prep(const void *xq, const void *xk, const void 
 }
 
 // q/k/v short convs with the chunk gating folded in (bf16, the tensor-core GLA kernel's operands): see qk_gate_bf16_kernel.
-extern "C" int lina_gla_prefill_prep_gated(const void *xq, const void *xk, const void *xv, long long ldx, const void *wq,
+extern "C" int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const void *xk, long long ldk, const void *xv,
+                                           long long ldv, const void *wq,
                                            const void *wk, const void *wv, const void *gk_raw, long long ldg, void *qg,
                                            void *kg, void *v, float *decay, void *cq, void *ck, void *cv, int cache_dtype,
                                            int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale,
@@ -467,18 +468,19 @@ extern "C" int lina_gla_prefill_prep_gated(const void *xq, const void *xk, const
                  "gla_prefill_prep_gated: pass all three conv caches or none");
     LINA_REQUIRE(cq == nullptr || lina_dtype_ok(cache_dtype), LINA_ERR_BAD_ARG, "gla_prefill_prep_gated: bad cache dtype");
     const int Dk = H * K, Dv = H * V;
-    LINA_REQUIRE(K % 4 == 0 && Dv % 8 == 0 && ldx % 8 == 0 && ldg % 4 == 0 && ldx >= Dk && ldg >= Dk, LINA_ERR_UNSUPPORTED,
+    LINA_REQUIRE(K % 4 == 0 && Dv % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldg % 4 == 0 && ldq >= Dk &&
+                     ldk >= Dk && ldv >= Dv && ldg >= Dk, LINA_ERR_UNSUPPORTED,
                  "gla_prefill_prep_gated: K %% 4, H*V %% 8 and 16-byte row strides required");
     LINA_REQUIRE(aligned16(xq) && aligned16(xk) && aligned16(xv) && aligned16(gk_raw) && aligned16(qg) && aligned16(kg) &&
                      aligned16(v) && aligned16(decay) && aligned16(wq) && aligned16(wk) && aligned16(wv),
                  LINA_ERR_UNSUPPORTED, "gla_prefill_prep_gated: tensors must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_conv4_bf16(xv, ldx, wv, v, cv, cache_dtype, B, L, Dv, 1, st);
+    int rc = launch_conv4_bf16(xv, ldv, wv, v, cv, cache_dtype, B, L, Dv, 1, st);
     if (rc) return rc;
     GateArgs a{};
     a.xq = (const bf16 *)xq; a.xk = (const bf16 *)xk; a.graw = (const bf16 *)gk_raw;
     a.wq = (const bf16 *)wq; a.wk = (const bf16 *)wk; a.qg = (bf16 *)qg; a.kg = (bf16 *)kg; a.decay = decay;
-    a.cq = cq; a.ck = ck; a.ldx = ldx; a.ldg = ldg; a.B = B; a.L = L; a.Dk = Dk; a.K = K; a.NT = (L + GC - 1) / GC;
+    a.cq = cq; a.ck = ck; a.ldq = ldq; a.ldk = ldk; a.ldg = ldg; a.B = B; a.L = L; a.Dk = Dk; a.K = K; a.NT = (L + GC - 1) / GC;
     a.cache_dtype = cache_dtype;
     a.log2_scale = log2f(scale);
     a.gate_c = 1.44269504088896340736f / gate_normalizer;

@@ -16,6 +16,7 @@ or None; ``scale`` None / -1 means K**-0.5; gates are log-space (<= 0).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -84,8 +85,107 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool, bthd: bool = F
     return o, ht
 
 
+TC_BWD = os.environ.get("LINA_TC_BWD", "1") != "0"
+
+
+def _tc_bwd_eligible(q, v) -> bool:
+    """The backward-through-the-forward-kernel path: bf16, K a multiple of 128 (it becomes the value dim of the dq / dk
+    runs), V split into pieces of 64 / 128 / 256 (the key dim of those runs), T long enough for the tensor-core kernel."""
+    if not TC_BWD or q.dtype != torch.bfloat16:
+        return False
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    ns = (V + 255) // 256
+    return (K in (128, 256) and V % 128 == 0 and V % ns == 0 and (V // ns) in (64, 128, 256) and T >= 64
+            and B * H <= 65535)
+
+
+def _run_pregated(qg, kg, v, decay, h0, o, ht, row_decay: bool):
+    """One launch of the pre-gated tensor-core kernel on [B,H,T,D] operands (the unit the backward is built from)."""
+    B, H, T, K = qg.shape
+    V = v.shape[-1]
+    for t in (qg, kg, v, decay, o):
+        assert t.is_contiguous()
+    rc = L.lib().lina_gla_chunk_fwd_pregated(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(h0),
+                                            L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V, 0,
+                                            int(row_decay), int(o.dtype == torch.float32), L.stream(qg))
+    L.count_launches(1)
+    L.check(rc, "lina_gla_chunk_fwd_pregated")
+
+
+def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=_run_pregated):
+    """Chunked backward (dq, dk, dv, dgk, dh0) as FIVE runs of the pre-gated forward kernel (C = 64; G = in-chunk cumsum of
+    gk, D = e^{G_C}; q^ = scale q e^{G-G_C}, k^ = k e^{G_C-G}, k~ = k e^{-G}; "rev" = time-reversed):
+
+      dv, dh0 = kernel(qg = rev k^, kg = rev q^, v = rev do, decay = rev D, h0 = dht)                     (key-dim decay)
+      dq~    += kernel(qg = do[:, Vj], kg = v[:, Vj], v = k~, decay = D as ROW decay, h0 = h0[:, :, :, Vj]^T)   per V piece j
+      dk^    += kernel(qg = rev v[:, Vj], kg = rev do[:, Vj], v = rev q^, decay = rev D (ROW), h0 = dht[..., Vj]^T)
+      dq = dq~ * scale e^G ;  dk = rev(dk^) * e^{G_C-G} ;  dgk = reversed cumsum_T(dq q - dk k) [+ sum_v dht S_T]
+
+    (the identities of FLA/fla/ops/gla/chunk.py:140-341 / FLA/fla/ops/common/chunk_h.py:111-189 regrouped so that every
+    contraction is the forward kernel's; verified against the recurrence's explicit backward in tests/test_host.py with the
+    oracle's restatement of the kernel contract as ``run``).  Element-wise glue is torch (plumbing); all MMA work is ours."""
+    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    C = 64
+    NT = (T + C - 1) // C
+    Tp, pad = NT * C, NT * C - T
+    lo = q.dtype
+
+    def padT(x):
+        return torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x
+
+    qf, kf, gf = (padT(x.float()) for x in (q, k, gk))
+    vb, dob = padT(v).contiguous(), padT(do).contiguous()
+    G = gf.view(B, H, NT, C, K).cumsum(3)
+    GC = G[:, :, :, -1:, :]
+    D = GC.squeeze(3).exp().contiguous()                                   # [B,H,NT,K]
+    Dr = D.flip(2).contiguous()
+    kt = (kf.view(B, H, NT, C, K) * (-G).exp()).to(lo).view(B, H, Tp, K)
+    qh = (qf.view(B, H, NT, C, K) * ((G - GC).exp() * scale)).to(lo).view(B, H, Tp, K)
+    e_gc_g = (GC - G).exp()
+    kh = (kf.view(B, H, NT, C, K) * e_gc_g).to(lo).view(B, H, Tp, K)
+    qh_r = qh.flip(2).contiguous()
+    dht32 = dht.float().contiguous() if dht is not None else None
+
+    dv_r = torch.empty(B, H, Tp, V, dtype=lo, device=q.device)
+    dh0 = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_dh0 else None
+    run(kh.flip(2).contiguous(), qh_r, dob.flip(2).contiguous(), Dr, dht32, dv_r, dh0, False)
+    dv = dv_r.flip(2)[:, :, :T]
+
+    ns = (V + 255) // 256
+    Vp = V // ns
+    dqt = dkr = None
+    ST = []
+    for j in range(ns):
+        sl = slice(j * Vp, (j + 1) * Vp)
+        do_j, v_j = dob[..., sl].contiguous(), vb[..., sl].contiguous()
+        h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
+        o = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
+        ht = torch.empty(B, H, Vp, K, dtype=torch.float32, device=q.device) if dht is not None else None
+        run(do_j, v_j, kt, D, h0_j, o, ht, True)
+        dqt = o if dqt is None else dqt.add_(o)
+        if ht is not None:
+            ST.append(ht.transpose(-1, -2))
+        dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
+        o2 = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
+        run(v_j.flip(2).contiguous(), do_j.flip(2).contiguous(), qh_r, Dr, dht_j, o2, None, True)
+        dkr = o2 if dkr is None else dkr.add_(o2)
+    dq = (dqt.view(B, H, NT, C, K) * (G.exp() * scale)).view(B, H, Tp, K)[:, :, :T]
+    dk = (dkr.flip(2).view(B, H, NT, C, K) * e_gc_g).view(B, H, Tp, K)[:, :, :T]
+    dgk = (dq * q.float() - dk * k.float()).flip(2).cumsum(2).flip(2)
+    if dht32 is not None:
+        dgk = dgk + (dht32 * torch.cat(ST, dim=-1)).sum(-1).unsqueeze(2)
+    return dq.to(lo), dk.to(lo), dv, dgk.to(lo), dh0
+
+
 def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     lib = L.lib()
+    if _tc_bwd_eligible(q, v):
+        if do.dtype != q.dtype:
+            do = do.to(q.dtype)
+        return _bwd_tc(q, k, v, gk, h0, do, dht, scale, want_dh0)
     q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))     # the backward kernels read [B,H,T,D]
     B, H, T, K, V = q.shape[0], q.shape[1], q.shape[2], q.shape[3], v.shape[3]
     do = do.contiguous()

@@ -36,6 +36,8 @@ FUSED_PREFILL = os.environ.get("LINA_FUSED_PREFILL", "1") != "0"
 CAT5 = os.environ.get("LINA_CAT5", "0") == "1"
 # LINA_PREGATED=0: the post-projection pass writes q, k, gk and the GLA kernel gates them itself (4x redundantly)
 PREGATED = os.environ.get("LINA_PREGATED", "1") != "0"
+# "cat4": one [q;k;v;g] GEMM; "split": four GEMMs (the pre-gated pass and the norm-gate read each output in place)
+GEMM_GROUPING = os.environ.get("LINA_GEMM_GROUPING", "cat4")
 
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):
@@ -162,15 +164,27 @@ class GatedLinearAttention(nn.Module):
         B, T, _ = x.shape
         H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
         lib = L.lib()
-        if CAT5:
-            proj = F.linear(x, self._cat_weight())
-            lo = proj[..., 2 * kd + 2 * vd:]
-        else:
-            proj = F.linear(x, self._cat_weight4())
+        norm = float(self.gate_logit_normalizer)
+        state_in = last_state[-1] if use_cache and last_state is not None else None
+        pregated = (PREGATED and x.dtype == torch.bfloat16 and self.mode in ("fused_chunk", "chunk")
+                    and self.clamp_min is None and norm > 0 and math.frexp(norm)[0] == 0.5
+                    and bool(lib.lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, L.BF16))
+                    and (state_in is None or state_in.dtype in (torch.float32, torch.bfloat16, torch.float16)))
+        if GEMM_GROUPING == "split" and not CAT5 and pregated:
+            # four GEMMs, each output read in place with its own row stride (measured faster in-stream than one N=6144 GEMM)
+            xq, xk, xv, g = self.q_proj(x), self.k_proj(x), self.v_proj(x), self.g_proj(x)
             lo = self.gk_proj[0](x)
+        else:
+            if CAT5:
+                proj = F.linear(x, self._cat_weight())
+                lo = proj[..., 2 * kd + 2 * vd:]
+            else:
+                proj = F.linear(x, self._cat_weight4())
+                lo = self.gk_proj[0](x)
+            xq, xk, xv, g = (proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd],
+                             proj[..., 2 * kd + vd:2 * kd + 2 * vd])
         gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
-        ldx = proj.shape[-1]
-        xq, xk, xv, g = proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd], proj[..., 2 * kd + vd:2 * kd + 2 * vd]
+        ldq, ldk, ldv, ldgate = xq.stride(1), xk.stride(1), xv.stride(1), g.stride(1)
         cq = ck = cv = None
         if use_cache and last_state is not None:
             cq, ck, cv = last_state[0], last_state[1], last_state[2]
@@ -181,16 +195,11 @@ class GatedLinearAttention(nn.Module):
         q = torch.empty(B, T, kd, dtype=x.dtype, device=x.device)
         k = torch.empty_like(q)
         v = torch.empty(B, T, vd, dtype=x.dtype, device=x.device)
-        norm = float(self.gate_logit_normalizer)
-        pregated = (PREGATED and x.dtype == torch.bfloat16 and self.mode in ("fused_chunk", "chunk")
-                    and self.clamp_min is None and norm > 0 and math.frexp(norm)[0] == 0.5
-                    and bool(lib.lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, L.BF16))
-                    and (recurrent_state is None or recurrent_state.dtype in (torch.float32, torch.bfloat16, torch.float16)))
         if pregated:
             # q, k hold the gated MMA operands q~ = scale q e^G, k~ = k e^-G; gk is never materialised
             nt = (T + 63) // 64
             decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=x.device)
-            rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
+            rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldq, L.ptr(xk), ldk, L.ptr(xv), ldv, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                                  L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay),
                                                  L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0,
                                                  B, T, H, K, V, self.conv_size, norm, float(K) ** -0.5, L.stream(x))
@@ -216,6 +225,7 @@ class GatedLinearAttention(nn.Module):
                 past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
         else:
             gk = torch.empty_like(q)
+            ldx = ldq                                     # this entry takes one row stride: always the concatenated GEMM
             rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                            L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk),
                                            L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0, B, T, kd, vd,
@@ -236,7 +246,7 @@ class GatedLinearAttention(nn.Module):
         nw = self.g_norm_swish_gate.weight
         nw = nw.to(x.dtype) if nw is not None else None
         rc = lib.lina_rmsnorm_swishgate_fwd_ld(L.ptr(o), L.ptr(g), L.ptr(nw), L.ptr(y), None, B * T * H, V,
-                                               float(self.g_norm_swish_gate.eps), H, ldx, L.dt(x), L.stream(x))
+                                               float(self.g_norm_swish_gate.eps), H, ldgate, L.dt(x), L.stream(x))
         L.count_launches(1)
         L.check(rc, "lina_rmsnorm_swishgate_fwd_ld")
         return self.o_proj(y.view(B, T, vd))
@@ -288,6 +298,8 @@ class GatedLinearAttention(nn.Module):
             gk = F.logsigmoid(gk) / self.gate_logit_normalizer
             if self.clamp_min is not None:
                 gk = torch.clamp_min(gk, self.clamp_min)
+        if gk.dtype != q.dtype:          # autocast may leave the gate in fp32: keep one dtype so the tensor-core kernels apply
+            gk = gk.to(q.dtype)
         if reset_mask is not None:
             gk = gk.masked_fill(reset_mask.unsqueeze(1).unsqueeze(3), reset_val)
 

@@ -145,6 +145,28 @@ def chunk_gla(q, k, v, gk, scale: Optional[float] = None, initial_state=None, ch
     return o.to(odt), S.to(torch.float32)
 
 
+def pregated_chunk_fwd(qg, kg, v, decay, h0=None, row_decay: bool = False, chunk: int = 64, acc_dtype=torch.float32):
+    """Contract of the pre-gated tensor-core kernel (lina_gla_chunk_fwd_pregated) restated in torch, for CPU tests of the
+    host-side backward that is built from it: per 64-token chunk  o = qg S + tril(qg kg^T) v ;  S' = decay (.) (S + kg^T v),
+    decay [B,H,NT,K] scaling the key dim (rows of S) or, with ``row_decay``, [B,H,NT,V] scaling the value dim.
+    With qg = scale q e^G, kg = k e^-G, decay = e^{G_C} this is the chunk form of FLA/fla/ops/gla/chunk.py:110-136 +
+    FLA/fla/ops/common/chunk_h.py:74-94.  T must be a multiple of ``chunk``.  Returns (o, final state), both acc_dtype."""
+    qg, kg, v = (x.to(acc_dtype) for x in (qg, kg, v))
+    B, H, T, K = qg.shape
+    V = v.shape[-1]
+    assert T % chunk == 0
+    S = torch.zeros(B, H, K, V, dtype=acc_dtype) if h0 is None else h0.to(acc_dtype).clone()
+    o = torch.empty(B, H, T, V, dtype=acc_dtype)
+    for n in range(T // chunk):
+        sl = slice(n * chunk, (n + 1) * chunk)
+        P = torch.einsum("bhtk,bhsk->bhts", qg[:, :, sl], kg[:, :, sl]).tril()
+        o[:, :, sl] = torch.einsum("bhtk,bhkv->bhtv", qg[:, :, sl], S) + torch.einsum("bhts,bhsv->bhtv", P, v[:, :, sl])
+        S = S + torch.einsum("bhsk,bhsv->bhkv", kg[:, :, sl], v[:, :, sl])
+        d = decay[:, :, n].to(acc_dtype)
+        S = S * (d.unsqueeze(-2) if row_decay else d.unsqueeze(-1))
+    return o, S
+
+
 # ----------------------------------------------------------------------------
 # a5: ShortConvolution  (FLA/fla/modules/convolution.py:141-205, torch branch)
 # ----------------------------------------------------------------------------

@@ -44,13 +44,12 @@ configs = [
     ("round1_path (op by op, torch CE)", dict(fused=False, cat5=False, tl=0, opt=0, ce=False, pre=False)),
     ("op by op + fused CE", dict(fused=False, cat5=False, tl=0, opt=0, ce=True, pre=False)),
     ("fused_prefill + CE", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=False)),
-    ("fused_prefill + CE + OPT2", dict(fused=True, cat5=False, tl=0, opt=2, ce=True, pre=False)),
     ("fused_prefill + CE + pregated", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True)),
-    ("fused_prefill + CE + pregated + TL16", dict(fused=True, cat5=False, tl=16, opt=0, ce=True, pre=True)),
-    ("fused_prefill + CE + pregated + cat5", dict(fused=True, cat5=True, tl=0, opt=0, ce=True, pre=True)),
+    ("fused_prefill + CE + pregated + split GEMMs", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split")),
 ]
 for name, cf in configs:
     G.FUSED_PREFILL, G.CAT5, G.PREGATED = cf["fused"], cf["cat5"], cf["pre"]
+    G.GEMM_GROUPING = cf.get("group", "cat4")
     lib.lina_debug_set_variant(0, cf["tl"])
     lib.lina_debug_set_variant(2, cf["opt"])
     ML.LinaModel._fused_cross_entropy = staticmethod(fused_ce) if cf["ce"] else staticmethod(lambda *a: None)

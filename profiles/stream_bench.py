@@ -84,7 +84,7 @@ decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=dev)
 
 
 def prep_gated():
-    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv), L.ptr(gk_raw), kd,
+    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldx, L.ptr(xk), ldx, L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv), L.ptr(gk_raw), kd,
                                          L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, None, None, 0, B, T, H, K, V, 4,
                                          16.0, K ** -0.5, st())
     assert rc == 0, lib.lina_last_error_string()

@@ -255,3 +255,36 @@ def test_rwkv6_recurrent_forward(dtype):
                 ro, rh = GO.recurrent_rwkv6(*[a.float().cpu() for a in args], initial_state=c.get("h0"))
                 _assert_close(o, ro, 1e-4, 2.0 ** -7, what=f"rwkv6 bf16 case {ci} o")
                 _assert_close(ht, rh, 1e-4, 1e-3, what=f"rwkv6 bf16 case {ci} ht")
+
+
+@pytest.mark.parametrize("K,V", [(128, 256), (256, 512)])
+@pytest.mark.parametrize("T", [64, 200, 512])
+@pytest.mark.parametrize("with_state", [False, True])
+def test_tensor_core_backward(K, V, T, with_state):
+    """bf16 backward at tensor-core head sizes = five runs of the pre-gated tcgen05 kernel (fla_api.ops._bwd_tc):
+    dq, dk, dv, dgk, dh0 (incl. a gradient flowing into the final state) against the explicit fp64 backward of the
+    recurrence on the same bf16-valued inputs; tolerance = the forward's (3e-2 of the max, the reference's own bf16
+    bound is atol 1e-1, FLA/tests/ops/test_gla.py:51)."""
+    from lina_speech_b200.fla_api import chunk_gla, ops
+    assert ops.TC_BWD
+    torch.manual_seed(K + T)
+    B, H = 2, 2
+    bf = torch.bfloat16
+    q, k = (torch.randn(B, H, T, K).to(bf) for _ in range(2))
+    v, do = (torch.randn(B, H, T, V).to(bf) for _ in range(2))
+    gk = (F.logsigmoid(torch.randn(B, H, T, K)) / 16).to(bf)
+    h0 = torch.randn(B, H, K, V) if with_state else None
+    dht = torch.randn(B, H, K, V) if with_state else None
+    ref = GO.recurrent_gla_bwd(q.float(), k.float(), v.float(), gk.float(), h0, do.float(), dht)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (q, k, v, gk)]
+    h0d = h0.to(DEV).requires_grad_(True) if with_state else None
+    assert ops._tc_bwd_eligible(leaves[0], leaves[2])
+    o, ht = chunk_gla(*leaves, initial_state=h0d, output_final_state=with_state)
+    loss = (o.float() * do.to(DEV).float()).sum()
+    if with_state:
+        loss = loss + (ht * dht.to(DEV)).sum()
+    loss.backward()
+    for name, leaf, r in zip(("dq", "dk", "dv", "dgk"), leaves, ref[:4]):
+        _assert_close(leaf.grad, r, 0.0, 3e-2, what=f"{name} K={K} T={T}")
+    if with_state:
+        _assert_close(h0d.grad, ref[4], 0.0, 2e-2, what="dh0")

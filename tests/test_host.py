@@ -1,4 +1,5 @@
 """CPU: host-side logic that needs no kernel -- token tools, the state cache, module / state-dict layout."""
+import pytest
 import torch
 
 from lina_speech_b200.fla_api import Cache
@@ -67,3 +68,33 @@ def test_codec_module_tree_has_reference_key_names():
               "backbone.convnext.0.gamma", "backbone.final_layer_norm.weight", "head.out.weight",
               "head.istft.window", "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"):
         assert k in keys, k
+
+
+@pytest.mark.parametrize("B,H,T,K,V,with_state", [(1, 2, 128, 16, 32, True), (2, 1, 150, 16, 600, False), (1, 1, 200, 8, 512, True)])
+def test_backward_through_the_forward_kernel_host_logic(B, H, T, K, V, with_state):
+    """fla_api.ops._bwd_tc regroups the chunked GLA backward into five runs of the pre-gated forward kernel (role swaps,
+    time reversal, V split, row decay).  With the oracle's restatement of that kernel's contract plugged in as ``run`` the
+    result must equal the explicit backward of the recurrence (FLA/fla/ops/common/fused_recurrent.py:172-257,335-342),
+    incl. dh0, the dht terms and a ragged last chunk.  (CPU: host logic only; the kernel itself is checked on the GPU.)"""
+    import torch.nn.functional as F
+    from oracle import gla_oracle as GO
+    from lina_speech_b200.fla_api import ops
+
+    def run(qg, kg, v, decay, h0, o, ht, row):
+        oo, S = GO.pregated_chunk_fwd(qg, kg, v, decay, h0, row, acc_dtype=torch.float64)
+        o.copy_(oo)
+        if ht is not None:
+            ht.copy_(S)
+
+    torch.manual_seed(T)
+    f64 = torch.float64
+    q, k = (torch.randn(B, H, T, K, dtype=f64) for _ in range(2))
+    v, do = (torch.randn(B, H, T, V, dtype=f64) for _ in range(2))
+    gk = F.logsigmoid(torch.randn(B, H, T, K, dtype=f64)) / 4
+    h0 = torch.randn(B, H, K, V, dtype=f64) if with_state else None
+    dht = torch.randn(B, H, K, V, dtype=f64) if with_state else None
+    ref = GO.recurrent_gla_bwd(q, k, v, gk, h0, do, dht)
+    got = ops._bwd_tc(q, k, v, gk, h0, do, dht, K ** -0.5, True, run=run)
+    for name, a, b in zip(("dq", "dk", "dv", "dgk", "dh0"), got, ref):
+        err = (a.double() - b).abs().max().item() / b.abs().max().item()
+        assert err < 5e-6, f"{name}: relative error {err:.2e}"       # fp32 intermediates inside _bwd_tc

@@ -267,7 +267,7 @@ def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
     cv = torch.ones(B, vd, 4, dtype=bf, device=DEV)
     wqd, wkd, wvd = wq.to(DEV), wk.to(DEV), wv.to(DEV)
     xq, xk, xv = pd[..., :kd], pd[..., kd:2 * kd], pd[..., 2 * kd:2 * kd + vd]
-    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wqd), L.ptr(wkd), L.ptr(wvd), L.ptr(gd), kd,
+    rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldx, L.ptr(xk), ldx, L.ptr(xv), ldx, L.ptr(wqd), L.ptr(wkd), L.ptr(wvd), L.ptr(gd), kd,
                                          L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(cq), L.ptr(ck), L.ptr(cv),
                                          L.dt(cq), B, T, H, K, V, 4, 16.0, scale, L.stream(pd))
     L.check(rc, "lina_gla_prefill_prep_gated")
