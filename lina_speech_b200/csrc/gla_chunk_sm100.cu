@@ -123,6 +123,10 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     //            the key dim: decay is [B,H,NT,V].  This is the form the backward needs (contraction over V, state S^T).
     // OPT bit 4 (OUT32): o is written as fp32 (the backward's dq~ / dk~ partial sums feed a cumsum).
     constexpr bool ROW = (OPT & 8) != 0, OUT32 = (OPT & 16) != 0;
+    // OPT bit 5 (STATE2, with PRE): the idle pre-pass warps 0-3 take the upper half of the state columns in the state pass
+    //            (a warp may touch TMEM lanes 32*(warp%4)..+31 only, so warps 0-3 mirror warps 12-15 lane for lane).
+    constexpr bool STATE2 = (OPT & 32) != 0;
+    static_assert(!STATE2 || PRE, "the second state-pass warpgroup are the pre-pass warps");
     static_assert(!ROW || PRE, "row decay needs pre-gated operands");
     using cfg = Cfg<K>;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
@@ -147,7 +151,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
         mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
-        mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], 128);
+        mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], STATE2 ? 256 : 128);
         mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1);
         mbar_init(&bars[B_G_EMPTY0], NPREP); mbar_init(&bars[B_G_EMPTY1], NPREP);
         mbar_init(&bars[B_V_FULL], 1); mbar_init(&bars[B_V_EMPTY], 1);
@@ -159,7 +163,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
+    const bool st2 = STATE2 && warp < 4;
+    if (warp < 8 && !st2) {
       if (!PRE) {
         // ====================== warps 0-7: gate pre-pass, in place on the landed q / k rows ======================
         const int p = tid;                         // 0..255
@@ -396,14 +401,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             }
             if (r == 0) TRACE(4, n, 1);
         }
-    } else if (warp >= 12 && warp < 16) {
-        // ====================== warps 12-15: state pass ======================
-        const int qd = warp - 12, r = qd * 32 + lane;
+    } else if ((warp >= 12 && warp < 16) || st2) {
+        // ====================== warps 12-15 (+ 0-3 with STATE2): state pass ======================
+        const int qd = st2 ? warp : warp - 12, r = qd * 32 + lane;
+        const int cb_lo = st2 ? K / 64 : 0, cb_hi = (STATE2 && !st2) ? K / 64 : K / 32;   // 32-column blocks of this group
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         const size_t sbase = (size_t)bh * K * V + v0 + r;          // + kappa * V
         // initial state -> ST (fp32) and SA (bf16)
 #pragma unroll 1
-        for (int cb = 0; cb < K / 32; ++cb) {
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
             uint32_t f[32], pk[16];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -423,7 +429,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);   // dvec of this item is published with it
             wait_bar(&bars[B_ST_FULL], n & 1);
             tc_fence_after();
-            if (r == 0) TRACE(5, n, 0);
+            if (r == 0 && !st2) TRACE(5, n, 0);
             const float *dv = dvec + (n % 3) * K;
             const bool last = n == n_items - 1;
             float rd = 1.f;
@@ -463,7 +469,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 }
             } else {
 #pragma unroll 1
-            for (int cb = 0; cb < K / 32; ++cb) {
+            for (int cb = cb_lo; cb < cb_hi; ++cb) {
                 uint32_t f[32], pk[16];
                 tmem_ld32(tmem + lane_addr + COL_ST + cb * 32, f);
                 tmem_ld_wait();
@@ -489,7 +495,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[B_SA_FULL]);
-            if (r == 0) TRACE(5, n, 1);
+            if (r == 0 && !st2) TRACE(5, n, 1);
         }
     }
     tc_fence_before();
@@ -592,6 +598,11 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
                  "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
     LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_lina_variant[4] == 1) {            // A/B: two warpgroups share the state pass
+        if (K == 64) return launch<64, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        if (K == 128) return launch<128, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        return launch<256, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    }
     if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);

@@ -37,7 +37,7 @@ CAT5 = os.environ.get("LINA_CAT5", "0") == "1"
 # LINA_PREGATED=0: the post-projection pass writes q, k, gk and the GLA kernel gates them itself (4x redundantly)
 PREGATED = os.environ.get("LINA_PREGATED", "1") != "0"
 # "cat4": one [q;k;v;g] GEMM; "split": four GEMMs (the pre-gated pass and the norm-gate read each output in place)
-GEMM_GROUPING = os.environ.get("LINA_GEMM_GROUPING", "cat4")
+GEMM_GROUPING = os.environ.get("LINA_GEMM_GROUPING", "split")
 
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):

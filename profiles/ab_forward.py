@@ -46,12 +46,14 @@ configs = [
     ("fused_prefill + CE", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=False)),
     ("fused_prefill + CE + pregated", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True)),
     ("fused_prefill + CE + pregated + split GEMMs", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split")),
+    ("... + split + STATE2 kernel", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split", state2=1)),
 ]
 for name, cf in configs:
     G.FUSED_PREFILL, G.CAT5, G.PREGATED = cf["fused"], cf["cat5"], cf["pre"]
     G.GEMM_GROUPING = cf.get("group", "cat4")
     lib.lina_debug_set_variant(0, cf["tl"])
     lib.lina_debug_set_variant(2, cf["opt"])
+    lib.lina_debug_set_variant(4, cf.get("state2", 0))
     ML.LinaModel._fused_cross_entropy = staticmethod(fused_ce) if cf["ce"] else staticmethod(lambda *a: None)
     try:
         ms, loss = run()

@@ -57,3 +57,16 @@ for name, tc, n in (("tensor_core_backward", True, 3), ("recurrence_backward", F
         print(name, "FAILED", repr(e)[:500], flush=True)
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
 json.dump(res, open(out_path, "w"), indent=1)
+
+# kernel-level breakdown of one step (CUPTI through torch.profiler; never a timing source for the numbers above)
+if os.environ.get("LINA_TRAIN_PROFILE", "1") != "0":
+    ops.TC_BWD = True
+    from torch.profiler import profile, ProfilerActivity
+    step(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90)
+    with open(os.path.splitext(out_path)[0] + "_profile.txt", "w") as f:
+        f.write(tab)
+    print(tab[:6000])
