@@ -152,7 +152,23 @@ int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void 
  * is five runs of this kernel on role-swapped, time-reversed operands -- see lina_speech_b200/fla_api/ops.py:_bwd_tc. */
 int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, const float *decay,
                                 const void *h0, int h0_dtype, void *o, float *ht,
-                                int B, int H, int T, int K, int V, int bthd, int row_decay, int out_f32, void *stream);
+                                int B, int H, int T, int K, int V, int bthd, int row_decay, int out_f32,
+                                int ldq, int ldk, int ldv, void *stream);
+/* Element-wise passes of that backward (bf16, [B,H,T,K] contiguous, chunk 64; Tp = T rounded up to whole chunks):
+ *   prep  : kt [B,H,T,K] = k e^-G ; qh_r, kh_r [B,H,Tp,K] = scale q e^{G-G_C}, k e^{G_C-G} time-reversed (zero rows first when
+ *           T is ragged) ; D, Dr [B,H,NT,K] fp32 = e^{G_C} in forward / reversed chunk order.
+ *   time_reverse_pad2 : a_r[bh, Tp-1-t] = a[bh, t] (zero rows for t >= T), same for b; rows of Dm elements.
+ *   post  : dq = (dqa + dqb) scale e^G, dk = (dka + dkb)[reversed] e^{G_C-G} (dqb / dkb may be NULL), dgk_local = in-chunk
+ *           reversed cumsum of dq q - dk k (fp32), totals [B,H,NT,K] its chunk sums.
+ *   dgk_finish : dgk = bf16(dgk_local + carry[b,h,t/64,:]). */
+int lina_gla_bwd_prep(const void *q, const void *k, const void *gk, void *kt, void *qh_r, void *kh_r, float *D, float *Dr,
+                      int B, int H, int T, int K, float scale, void *stream);
+int lina_time_reverse_pad2(const void *a, const void *b, void *a_r, void *b_r, long long BH, int T, int Tp, int Dm,
+                           void *stream);
+int lina_gla_bwd_post(const float *dqa, const float *dqb, const float *dka, const float *dkb, const void *q, const void *k,
+                      const void *gk, void *dq, void *dk, float *dgk_local, float *totals,
+                      int B, int H, int T, int K, float scale, void *stream);
+int lina_gla_bwd_dgk_finish(const float *dgk_local, const float *carry, void *dgk, int B, int H, int T, int K, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.
@@ -244,7 +260,8 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * ------------------------------------------------------------------------------------------- */
 /* A/B switches for kernel variants (bring-up only; process-global, not thread-safe): key 0 = rows per thread of the
  * prep / short-conv tile kernel (8 or 16), key 1 = 1 selects the round-1 sliding-window short-conv kernel,
- * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16. */
+ * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16,
+ * key 4 = 1 runs the pre-gated GLA kernel's state pass on one warpgroup, key 5 = 1 selects the round-1 short-conv backward. */
 int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);

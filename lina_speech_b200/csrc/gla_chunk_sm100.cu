@@ -506,7 +506,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
 template <int K, int OPT = 0>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
            float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr,
-           const float *decay = nullptr) {
+           const float *decay = nullptr, int ldq = 0, int ldk = 0, int ldv = 0) {
     using cfg = Cfg<K>;
     static thread_local bool configured = false;
     if (!configured) {
@@ -525,10 +525,22 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
         const uint32_t box[4] = {64, 64, 1, 1};
         const uint64_t *sk = bthd ? str_bthd : str_bhtd, *sv = bthd ? vstr_bthd : vstr_bhtd;
         int rc;
+        if (!bthd && (ldq || ldk || ldv)) {
+            // [B,H,T,D] operands that are column slices of wider tensors (row stride ld elements): the backward reads
+            // V pieces of do / v in place
+            const uint64_t lq = ldq ? ldq : kd, lk = ldk ? ldk : kd, lv = ldv ? ldv : vd;
+            const uint64_t sq[4] = {2, lq * 2, t * lq * 2, h * t * lq * 2}, sk2[4] = {2, lk * 2, t * lk * 2, h * t * lk * 2};
+            const uint64_t sv2[4] = {2, lv * 2, t * lv * 2, h * t * lv * 2};
+            if ((rc = lina_make_tmap_bf16(&tm.q, q, 4, dims, sq, box))) return rc;
+            if ((rc = lina_make_tmap_bf16(&tm.k, k, 4, dims, sk2, box))) return rc;
+            if ((rc = lina_make_tmap_bf16(&tm.g, q, 4, dims, sq, box))) return rc;
+            if ((rc = lina_make_tmap_bf16(&tm.v, v, 4, vdims, sv2, box))) return rc;
+        } else {
         if ((rc = lina_make_tmap_bf16(&tm.q, q, 4, dims, sk, box))) return rc;
         if ((rc = lina_make_tmap_bf16(&tm.k, k, 4, dims, sk, box))) return rc;
         if ((rc = lina_make_tmap_bf16(&tm.g, gk, 4, dims, sk, box))) return rc;
         if ((rc = lina_make_tmap_bf16(&tm.v, v, 4, vdims, sv, box))) return rc;
+        }
     }
     dim3 grid(V / BV, B * H);
     gla_chunk_fwd_sm100_kernel<K, OPT><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
@@ -598,7 +610,7 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
                  "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
     LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_lina_variant[4] == 1) {            // A/B: two warpgroups share the state pass
+    if (g_lina_variant[4] == 0) {            // two warpgroups share the state pass (variant 4 = 1: one warpgroup)
         if (K == 64) return launch<64, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
         if (K == 128) return launch<128, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
         return launch<256, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
@@ -613,7 +625,8 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
 // is five runs of this kernel on role-swapped / time-reversed operands.
 extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, const float *decay,
                                            const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T, int K,
-                                           int V, int bthd, int row_decay, int out_f32, void *stream) {
+                                           int V, int bthd, int row_decay, int out_f32, int ldq, int ldk, int ldv,
+                                           void *stream) {
     LINA_REQUIRE(qg && kg && v && decay && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: null tensor pointer");
     LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: bad h0 dtype");
     LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16), LINA_ERR_UNSUPPORTED,
@@ -621,16 +634,20 @@ extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const
     LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
     LINA_REQUIRE((row_decay != 0) == (out_f32 != 0), LINA_ERR_UNSUPPORTED,
                  "gla_chunk_fwd_pregated: only (column decay, bf16 out) and (row decay, fp32 out) are instantiated");
+    LINA_REQUIRE(ldq >= 0 && ldk >= 0 && ldv >= 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+                     (ldq == 0 || ldq >= K) && (ldk == 0 || ldk >= K) && (ldv == 0 || ldv >= V) &&
+                     (!bthd || (ldq == 0 && ldk == 0 && ldv == 0)),
+                 LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: row strides must be 0 (dense) or multiples of 8 >= the width, [B,H,T,D] only");
     cudaStream_t st = (cudaStream_t)stream;
     bthd = bthd ? 1 : 0;
     if (row_decay) {
-        if (K == 64) return launch<64, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
-        if (K == 128) return launch<128, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
-        return launch<256, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+        if (K == 64) return launch<64, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+        if (K == 128) return launch<128, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+        return launch<256, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
     }
-    if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
-    if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
-    return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay);
+    if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+    if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+    return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
 }
 
 // bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]

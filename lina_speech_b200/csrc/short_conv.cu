@@ -7,6 +7,8 @@
 // Pure HBM streaming: x is read once (+ (W-1)/LT halo), y written once.  Threads run along the
 // channel dim (coalesced rows of [B,L,D]); each thread slides a W-tap window over LT time steps.
 #include "common.cuh"
+#include "sm100.cuh"
+#include "packed.cuh"
 
 extern int g_lina_variant[8];
 // gla_prep.cu: TL-row tiles, all loads of a thread issued up front (the production W == 4 path)
@@ -165,6 +167,109 @@ short_conv_bwd_kernel(const T *__restrict__ x, const T *__restrict__ w, const T 
     for (int j = 0; j < W; ++j) atomicAdd(&dw[(size_t)d * W + j], dwl[j]);
 }
 
+
+// Backward for the shipped configuration (bf16, W = 4), packed math, one pass:
+//   pre[m] = sum_j w[j] x[m-3+j] ;  dpre[m] = dy[m] * act'(pre[m]) ;  dx[l] = sum_j w[j] dpre[l+3-j] ;  dw[j] += dpre[m] x[m-3+j]
+// One thread = 4 channels x BRT consecutive rows, walked once with a 3-row x window and a 3-row dpre window (dx[m-3] is
+// emitted when dpre[m] is known); rows l0+BRT .. l0+BRT+2 are recomputed as a tail halo.  dw is reduced in registers
+// over the thread's rows and then with one fp32 atomic per (channel, tap).  The round-1 kernel recomputed pre four times
+// per output with scalar loads (1.7 ms per call at bs8 x seq4096: 22 % of a training step).
+constexpr int BRT = 64;      // rows per thread
+constexpr int BRB = 4;       // rows per load batch
+__global__ void __launch_bounds__(128, 4)
+short_conv4_bwd_bf16_kernel(const bf16 *__restrict__ x, const bf16 *__restrict__ w, const bf16 *__restrict__ dy,
+                            bf16 *__restrict__ dx, float *__restrict__ dw, int B, int L, int D, int silu) {
+    const int ng = D / 4;
+    const int tiles = (L + BRT - 1) / BRT;
+    const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int cg = (int)(idx % ng);
+    const long long rest = idx / ng;
+    const int tile = (int)(rest % tiles);
+    const long long b = rest / tiles;
+    if (b >= B) return;
+    const int d0 = cg * 4, l0 = tile * BRT;
+    const bf16 *xb = x + (size_t)b * L * D + d0, *dyb = dy + (size_t)b * L * D + d0;
+    bf16 *dxb = dx + (size_t)b * L * D + d0;
+    float2 wt[2][4];
+    load_taps2(w + (size_t)d0 * 4, wt[0]);
+    load_taps2(w + (size_t)(d0 + 2) * 4, wt[1]);
+    float2 xw[2][3], dp[2][3], dwa[2][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dwa[p][j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dp[p][j] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int l = l0 - 3 + i;
+        const uint2 r = l >= 0 ? *reinterpret_cast<const uint2 *>(xb + (size_t)l * D) : make_uint2(0, 0);
+        xw[0][i] = bf2_to_f2(r.x); xw[1][i] = bf2_to_f2(r.y);
+    }
+    const int mend = min(L + 3, l0 + BRT + 3);            // exclusive; rows >= L contribute dpre = 0
+#pragma unroll 1
+    for (int m0 = l0; m0 < mend; m0 += BRB) {
+        uint2 rx[BRB], rd[BRB];
+#pragma unroll
+        for (int i = 0; i < BRB; ++i) {
+            const int m = m0 + i;
+            const bool ok = m < L && m < mend;
+            rx[i] = ok ? *reinterpret_cast<const uint2 *>(xb + (size_t)m * D) : make_uint2(0, 0);
+            rd[i] = ok ? *reinterpret_cast<const uint2 *>(dyb + (size_t)m * D) : make_uint2(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < BRB; ++i) {
+            const int m = m0 + i;
+            if (m >= mend) break;
+            const bool own = m < l0 + BRT;                // rows of this tile (dw counted once); later rows are halo
+            uint32_t ow[2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const float2 xv = bf2_to_f2(p == 0 ? rx[i].x : rx[i].y);
+                const float2 g = bf2_to_f2(p == 0 ? rd[i].x : rd[i].y);
+                // pre[m] from the window (x[m-3], x[m-2], x[m-1]) and x[m]
+                float2 pre = __fmul2_rn(xw[p][0], wt[p][0]);
+                pre = __ffma2_rn(xw[p][1], wt[p][1], pre);
+                pre = __ffma2_rn(xw[p][2], wt[p][2], pre);
+                pre = __ffma2_rn(xv, wt[p][3], pre);
+                float2 d = g;
+                if (silu) {                               // act'(pre) = s (1 + pre (1 - s)), s = sigmoid(pre)
+                    const float2 hh = __fmul2_rn(pre, make_float2(0.5f, 0.5f));
+                    const float2 t = make_float2(tanh_approx_(hh.x), tanh_approx_(hh.y));
+                    const float2 sg = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+                    const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+                    const float2 u = __ffma2_rn(pre, om, make_float2(1.f, 1.f));
+                    d = __fmul2_rn(g, __fmul2_rn(sg, u));
+                }
+                if (own) {                                // dw[j] += dpre[m] * x[m-3+j]
+                    dwa[p][0] = __ffma2_rn(d, xw[p][0], dwa[p][0]);
+                    dwa[p][1] = __ffma2_rn(d, xw[p][1], dwa[p][1]);
+                    dwa[p][2] = __ffma2_rn(d, xw[p][2], dwa[p][2]);
+                    dwa[p][3] = __ffma2_rn(d, xv, dwa[p][3]);
+                }
+                // dx[m-3] = w0 dpre[m] + w1 dpre[m-1] + w2 dpre[m-2] + w3 dpre[m-3]
+                float2 o = __fmul2_rn(dp[p][0], wt[p][3]);
+                o = __ffma2_rn(dp[p][1], wt[p][2], o);
+                o = __ffma2_rn(dp[p][2], wt[p][1], o);
+                o = __ffma2_rn(d, wt[p][0], o);
+                ow[p] = sm100::pack_bf16(o.x, o.y);
+                xw[p][0] = xw[p][1]; xw[p][1] = xw[p][2]; xw[p][2] = xv;
+                dp[p][0] = dp[p][1]; dp[p][1] = dp[p][2]; dp[p][2] = d;
+            }
+            const int l = m - 3;
+            if (l >= l0 && l < L) *reinterpret_cast<uint2 *>(dxb + (size_t)l * D) = make_uint2(ow[0], ow[1]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&dw[(size_t)(d0 + 2 * p) * 4 + j], dwa[p][j].x);
+            atomicAdd(&dw[(size_t)(d0 + 2 * p + 1) * 4 + j], dwa[p][j].y);
+        }
+}
+
 template <typename T>
 __global__ void short_conv_update_kernel(const T *__restrict__ x, void *__restrict__ cache, int cache_dtype,
                                          const T *__restrict__ w, T *__restrict__ y, int B, int D, int W,
@@ -219,6 +324,16 @@ extern "C" int lina_short_conv_bwd(const void *x, const void *w, const void *dy,
     LINA_REQUIRE(x && w && dy && dx && dw, LINA_ERR_BAD_ARG, "short_conv_bwd: null pointer");
     LINA_REQUIRE(B > 0 && L > 0 && D > 0, LINA_ERR_BAD_ARG, "short_conv_bwd: non-positive size");
     LINA_REQUIRE(W >= 1 && W <= MAXW, LINA_ERR_UNSUPPORTED, "short_conv_bwd: kernel size %d not in [1,%d]", W, MAXW);
+    if (dtype == LINA_BF16 && W == 4 && D % 4 == 0 && ((uintptr_t)x % 8 == 0) && ((uintptr_t)dy % 8 == 0) &&
+        ((uintptr_t)dx % 8 == 0) && ((uintptr_t)w % 16 == 0) && g_lina_variant[5] == 0) {
+        const long long nthreads = (long long)B * ((L + BRT - 1) / BRT) * (D / 4);
+        const long long nblk = (nthreads + 127) / 128;
+        LINA_REQUIRE(nblk <= 2147483647LL, LINA_ERR_UNSUPPORTED, "short_conv_bwd: grid too large");
+        short_conv4_bwd_bf16_kernel<<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
+            (const bf16 *)x, (const bf16 *)w, (const bf16 *)dy, (bf16 *)dx, dw, B, L, D, silu);
+        LINA_LAUNCH_OK("short_conv4_bwd_bf16_kernel");
+        return LINA_OK;
+    }
     LINA_REQUIRE(B <= 65535 && (L + LT - 1) / LT <= 65535, LINA_ERR_UNSUPPORTED, "short_conv_bwd: grid too large");
     dim3 grid((D + 127) / 128, (L + LT - 1) / LT, B);
     LINA_DISPATCH_DTYPE(dtype, short_conv_bwd_kernel<T_><<<grid, 128, 0, (cudaStream_t)stream>>>(

@@ -101,19 +101,94 @@ def _tc_bwd_eligible(q, v) -> bool:
 
 
 def _run_pregated(qg, kg, v, decay, h0, o, ht, row_decay: bool):
-    """One launch of the pre-gated tensor-core kernel on [B,H,T,D] operands (the unit the backward is built from)."""
+    """One launch of the pre-gated tensor-core kernel on [B,H,T,D] operands (the unit the backward is built from).
+    qg / kg / v may be last-dim slices of wider contiguous [B,H,T,W] tensors: they are read in place (row stride W)."""
     B, H, T, K = qg.shape
     V = v.shape[-1]
-    for t in (qg, kg, v, decay, o):
-        assert t.is_contiguous()
+
+    def ld(t):
+        if t.is_contiguous():
+            return 0
+        w = t.stride(2)
+        if t.stride(3) != 1 or t.stride(1) != T * w or t.stride(0) != H * T * w:
+            raise ValueError("operand must be a last-dim slice of a contiguous [B,H,T,W] tensor")
+        return w
+
+    assert decay.is_contiguous() and o.is_contiguous()
     rc = L.lib().lina_gla_chunk_fwd_pregated(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(h0),
                                             L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V, 0,
-                                            int(row_decay), int(o.dtype == torch.float32), L.stream(qg))
+                                            int(row_decay), int(o.dtype == torch.float32), ld(qg), ld(kg), ld(v),
+                                            L.stream(qg))
     L.count_launches(1)
     L.check(rc, "lina_gla_chunk_fwd_pregated")
 
 
-def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=_run_pregated):
+def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
+    """Product path of the tensor-core backward: same scheme as ``_bwd_tc_reference`` with fused element-wise kernels.
+    9 launches of ours per call at V <= 512: prep, flip, 5 x tcgen05, post, finish (+ a tiny torch scan over the chunk
+    totals and the transposes of the [K,V] states)."""
+    lib = L.lib()
+    q, k, v, gk, do = (x.contiguous() for x in (q, k, v, gk, do))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    C = 64
+    NT = (T + C - 1) // C
+    Tp = NT * C
+    dev, bf, f32 = q.device, q.dtype, torch.float32
+    st = L.stream(q)
+    kt = torch.empty(B, H, T, K, dtype=bf, device=dev)
+    qh_r, kh_r = (torch.empty(B, H, Tp, K, dtype=bf, device=dev) for _ in range(2))
+    D, Dr = (torch.empty(B, H, NT, K, dtype=f32, device=dev) for _ in range(2))
+    L.check(lib.lina_gla_bwd_prep(L.ptr(q), L.ptr(k), L.ptr(gk), L.ptr(kt), L.ptr(qh_r), L.ptr(kh_r), L.ptr(D), L.ptr(Dr),
+                                  B, H, T, K, scale, st), "lina_gla_bwd_prep")
+    do_r, v_r = (torch.empty(B, H, Tp, V, dtype=bf, device=dev) for _ in range(2))
+    L.check(lib.lina_time_reverse_pad2(L.ptr(do), L.ptr(v), L.ptr(do_r), L.ptr(v_r), B * H, T, Tp, V, st),
+            "lina_time_reverse_pad2")
+    L.count_launches(2)
+    dht32 = dht.float().contiguous() if dht is not None else None
+
+    # dv (+ dh0): reversed time, key-dim decay
+    dv_r = torch.empty(B, H, Tp, V, dtype=bf, device=dev)
+    dh0 = torch.empty(B, H, K, V, dtype=f32, device=dev) if want_dh0 else None
+    _run_pregated(kh_r, qh_r, do_r, Dr, dht32, dv_r, dh0, False)
+    dv = dv_r.flip(2)[:, :, :T] if Tp != T else dv_r.flip(2)
+
+    ns = (V + 255) // 256
+    Vp = V // ns
+    dq_parts, dk_parts, ST = [], [], []
+    for j in range(ns):
+        sl = slice(j * Vp, (j + 1) * Vp)
+        h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
+        o = torch.empty(B, H, T, K, dtype=f32, device=dev)
+        ht = torch.empty(B, H, Vp, K, dtype=f32, device=dev) if dht is not None else None
+        _run_pregated(do[..., sl], v[..., sl], kt, D, h0_j, o, ht, True)            # dq~ piece (forward time, row decay)
+        dq_parts.append(o)
+        if ht is not None:
+            ST.append(ht.transpose(-1, -2))
+        dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
+        o2 = torch.empty(B, H, Tp, K, dtype=f32, device=dev)
+        _run_pregated(v_r[..., sl], do_r[..., sl], qh_r, Dr, dht_j, o2, None, True)  # dk^ piece (reversed time)
+        dk_parts.append(o2)
+    while len(dq_parts) > 2:                       # V > 512: fold the extra pieces (the post kernel sums two)
+        dq_parts[0].add_(dq_parts.pop())
+        dk_parts[0].add_(dk_parts.pop())
+    dq, dk, dgk = torch.empty_like(q), torch.empty_like(k), torch.empty_like(gk)
+    dgk_local = torch.empty(B, H, T, K, dtype=f32, device=dev)
+    totals = torch.empty(B, H, NT, K, dtype=f32, device=dev)
+    two = len(dq_parts) == 2
+    L.check(lib.lina_gla_bwd_post(L.ptr(dq_parts[0]), L.ptr(dq_parts[1]) if two else None, L.ptr(dk_parts[0]),
+                                  L.ptr(dk_parts[1]) if two else None, L.ptr(q), L.ptr(k), L.ptr(gk), L.ptr(dq), L.ptr(dk),
+                                  L.ptr(dgk_local), L.ptr(totals), B, H, T, K, scale, st), "lina_gla_bwd_post")
+    carry = totals.flip(2).cumsum(2).flip(2) - totals                     # sum over the LATER chunks, [B,H,NT,K]
+    if dht32 is not None:
+        carry = carry + (dht32 * torch.cat(ST, dim=-1)).sum(-1).unsqueeze(2)
+    carry = carry.contiguous()
+    L.check(lib.lina_gla_bwd_dgk_finish(L.ptr(dgk_local), L.ptr(carry), L.ptr(dgk), B, H, T, K, st), "lina_gla_bwd_dgk_finish")
+    L.count_launches(2)
+    return dq, dk, dv, dgk, dh0
+
+
+def _bwd_tc_reference(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=None):
     """Chunked backward (dq, dk, dv, dgk, dh0) as FIVE runs of the pre-gated forward kernel (C = 64; G = in-chunk cumsum of
     gk, D = e^{G_C}; q^ = scale q e^{G-G_C}, k^ = k e^{G_C-G}, k~ = k e^{-G}; "rev" = time-reversed):
 
@@ -124,7 +199,12 @@ def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=_run_pre
 
     (the identities of FLA/fla/ops/gla/chunk.py:140-341 / FLA/fla/ops/common/chunk_h.py:111-189 regrouped so that every
     contraction is the forward kernel's; verified against the recurrence's explicit backward in tests/test_host.py with the
-    oracle's restatement of the kernel contract as ``run``).  Element-wise glue is torch (plumbing); all MMA work is ours."""
+    oracle's restatement of the kernel contract as ``run``).
+
+    This torch-glue version is the readable statement of the scheme and what the CPU host-logic test exercises (with
+    ``run`` = the oracle's restatement of the kernel contract); the product path is ``_bwd_tc`` below, which does the same
+    with four fused element-wise kernels (csrc/gla_bwd_glue.cu) and strided operand reads instead of ~25 torch ops."""
+    run = run or _run_pregated
     q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
     B, H, T, K = q.shape
     V = v.shape[-1]

@@ -85,6 +85,17 @@ class SwiGLU(nn.Module):
             L.count_launches(1)
             L.check(rc, "lina_swiglu_act")
             return F.linear(a.view(*x.shape[:-1], hp), wo_p, self.p_out.bias)
+        hid = self.p_out.in_features
+        if x.is_cuda and hid % 8:
+            # training / autograd path: the same zero padding, applied differentiably on the fly -- with hidden = 1365 the
+            # unpadded GEMMs (N = 2730, K = 1365) run on cuBLAS' unaligned sm75/sm80 kernels, ~5x slower (56 ms of a
+            # 300 ms training step at bs8 x seq4096)
+            hp, padn = (hid + 7) // 8 * 8, (hid + 7) // 8 * 8 - hid
+            wi, bi = self.p_in.weight, self.p_in.bias
+            wi_p = torch.cat([F.pad(wi[:hid], (0, 0, 0, padn)), F.pad(wi[hid:], (0, 0, 0, padn))], dim=0)
+            bi_p = torch.cat([F.pad(bi[:hid], (0, padn)), F.pad(bi[hid:], (0, padn))], dim=0)
+            gate, u = F.linear(x, wi_p, bi_p).chunk(2, dim=-1)
+            return F.linear(F.silu(gate) * u, F.pad(self.p_out.weight, (0, padn)), self.p_out.bias)
         gate, u = self.p_in(x).chunk(2, dim=-1)
         return self.p_out(F.silu(gate) * u)
 

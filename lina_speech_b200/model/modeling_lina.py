@@ -52,6 +52,8 @@ class LogitsHead(nn.Module):
                 wp[:l] = self.weight.detach()[0]
                 self._wpad = (key, wp)
             return F.linear(x, self._wpad[1])[..., :l].unsqueeze(-2)
+        if q == 1 and l % 8 and x.is_cuda:      # autograd path: pad differentiably (aligned GEMM kernels), slice the logits
+            return F.linear(x, F.pad(self.weight[0], (0, 0, 0, (l + 7) // 8 * 8 - l)))[..., :l].unsqueeze(-2)
         return F.linear(x, self.weight.view(q * l, d)).view(*x.shape[:-1], q, l)
 
 

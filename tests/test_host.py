@@ -72,7 +72,7 @@ def test_codec_module_tree_has_reference_key_names():
 
 @pytest.mark.parametrize("B,H,T,K,V,with_state", [(1, 2, 128, 16, 32, True), (2, 1, 150, 16, 600, False), (1, 1, 200, 8, 512, True)])
 def test_backward_through_the_forward_kernel_host_logic(B, H, T, K, V, with_state):
-    """fla_api.ops._bwd_tc regroups the chunked GLA backward into five runs of the pre-gated forward kernel (role swaps,
+    """fla_api.ops._bwd_tc_reference (the scheme of the product's _bwd_tc) regroups the chunked GLA backward into five runs of the pre-gated forward kernel (role swaps,
     time reversal, V split, row decay).  With the oracle's restatement of that kernel's contract plugged in as ``run`` the
     result must equal the explicit backward of the recurrence (FLA/fla/ops/common/fused_recurrent.py:172-257,335-342),
     incl. dh0, the dht terms and a ragged last chunk.  (CPU: host logic only; the kernel itself is checked on the GPU.)"""
@@ -94,7 +94,7 @@ def test_backward_through_the_forward_kernel_host_logic(B, H, T, K, V, with_stat
     h0 = torch.randn(B, H, K, V, dtype=f64) if with_state else None
     dht = torch.randn(B, H, K, V, dtype=f64) if with_state else None
     ref = GO.recurrent_gla_bwd(q, k, v, gk, h0, do, dht)
-    got = ops._bwd_tc(q, k, v, gk, h0, do, dht, K ** -0.5, True, run=run)
+    got = ops._bwd_tc_reference(q, k, v, gk, h0, do, dht, K ** -0.5, True, run=run)
     for name, a, b in zip(("dq", "dk", "dv", "dgk", "dh0"), got, ref):
         err = (a.double() - b).abs().max().item() / b.abs().max().item()
         assert err < 5e-6, f"{name}: relative error {err:.2e}"       # fp32 intermediates inside _bwd_tc

@@ -344,3 +344,27 @@ def test_bf16_layer_prefill_pregated_matches_op_by_op_and_oracle():
         _close(y1, outs["op_by_op"][1], 3e-2 * outs["op_by_op"][1].abs().max().item(), 0.0, what=f"{name} next step")
         for a, b in zip(st, outs["op_by_op"][2]):
             _close(a, b, 2e-2 * max(b.abs().max().item(), 1e-3), 0.0, what=f"{name} cache state")
+
+
+@pytest.mark.parametrize("B,Ln,D", [(2, 150, 256), (1, 64, 1024), (3, 5, 64), (2, 67, 128)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_short_conv_bf16_backward_packed_kernel(B, Ln, D, silu):
+    """bf16 / W = 4 backward (short_conv4_bwd_bf16_kernel: one pass, packed fp32x2 math, tail-halo rows, atomics for dw)
+    against autograd through the fp32 torch restatement on the same bf16-valued inputs."""
+    from lina_speech_b200.fla_api import ShortConvolution
+    torch.manual_seed(Ln + D)
+    bf = torch.bfloat16
+    conv = ShortConvolution(D, 4, activation="silu" if silu else None).to(DEV).to(bf)
+    x = torch.randn(B, Ln, D).to(bf)
+    dy = torch.randn(B, Ln, D).to(bf)
+    xr = x.float().requires_grad_(True)
+    wr = conv.weight.detach().float().cpu()[:, 0].clone().requires_grad_(True)
+    pre = F.conv1d(F.pad(xr.transpose(1, 2), (3, 0)), wr.unsqueeze(1), groups=D).transpose(1, 2)
+    yr = F.silu(pre) if silu else pre
+    (yr * dy.float()).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    y = conv(xg)
+    _close(y, yr, 2e-2, 1e-2, what="conv y (bf16)")
+    (y.float() * dy.to(DEV).float()).sum().backward()
+    _close(xg.grad, xr.grad, 2e-2, 1e-2, what="conv dx (bf16)")
+    _close(conv.weight.grad[:, 0], wr.grad, 5e-2, 2e-2, what="conv dw (bf16)")
