@@ -102,9 +102,8 @@ norm_gate_bwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *
         for (int i = 0; i < n; ++i) { dwl[c][i] = 0.f; wv[c][i] = 1.f; }
         if (w != nullptr && ch < nch) load16<T>(w + (size_t)ch * n, wv[c]);
     }
-    for (int rr = 0; rr < rows_per_warp; ++rr) {
-        const int row = wid * rows_per_warp + rr;
-        if (row >= M) break;
+    (void)rows_per_warp;
+    for (int row = wid; row < M; row += gridDim.x * 8) {       // persistent: rows strided over all warps of the grid
         const size_t off = (size_t)row * N;
         const float rstd = rstd_in[row];
         uint4 xr[CH], gr[CH], dr[CH];
@@ -153,13 +152,21 @@ norm_gate_bwd_kernel(const T *__restrict__ x, const T *__restrict__ g, const T *
         }
     }
     if (dw != nullptr) {
+        // block-level reduction over the 8 warps in shared memory, then ONE atomic per column per block (the grid is
+        // 2 blocks per SM: ~150 k atomics in total; per-warp atomics onto N addresses serialised in L2 and cost more than
+        // the streaming itself)
+        __shared__ float red[8][32 * CH * n + 1];
+        const int wl = threadIdx.x >> 5;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int ch = lane + c * 32;
-            if (ch < nch) {
+        for (int c = 0; c < CH; ++c)
 #pragma unroll
-                for (int i = 0; i < n; ++i) atomicAdd(&dw[(size_t)ch * n + i], dwl[c][i]);
-            }
+            for (int i = 0; i < n; ++i) red[wl][(lane + c * 32) * n + i] = dwl[c][i];
+        __syncthreads();
+        for (int col = threadIdx.x; col < N; col += 256) {
+            float a = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) a += red[w8][col];
+            atomicAdd(&dw[col], a);
         }
     }
 }
@@ -208,10 +215,10 @@ extern "C" int lina_rmsnorm_swishgate_bwd(const void *x, const void *g, const vo
     LINA_REQUIRE(x && g && rstd && dy && dx && dg, LINA_ERR_BAD_ARG, "rmsnorm_swishgate_bwd: null pointer");
     int rc = check(M, N, dtype);
     if (rc) return rc;
-    // ~16 warps per SM-slot: O(19000 * N / 32) atomics for dw, enough warps to keep HBM busy
-    int rows_per_warp = (M + 148 * 8 * 16 - 1) / (148 * 8 * 16);
-    if (rows_per_warp < 1) rows_per_warp = 1;
-    const int nwarps = (M + rows_per_warp - 1) / rows_per_warp;
+    // persistent grid: 2 blocks of 8 warps per SM, rows strided over the warps
+    const int rows_per_warp = 0;
+    int nwarps = (M + 7) / 8 * 8;
+    if (nwarps > 148 * 2 * 8) nwarps = 148 * 2 * 8;
     const int nch = N / (16 / (int)lina_dtype_size(dtype));
     if (nch <= 64) {
         LINA_DISPATCH_DTYPE(dtype, norm_gate_bwd_kernel<T_, 2><<<(nwarps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
