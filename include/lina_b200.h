@@ -154,7 +154,7 @@ int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, c
                                 const void *h0, int h0_dtype, void *o, float *ht,
                                 int B, int H, int T, int K, int V, int bthd, int row_decay, int out_f32,
                                 int ldq, int ldk, int ldv, void *stream);
-/* Element-wise passes of that backward (bf16, [B,H,T,K] contiguous, chunk 64; Tp = T rounded up to whole chunks):
+/* Element-wise passes of that backward (bf16; [B,H,T,K] contiguous or, with bthd != 0, [B,T,H,K]; chunk 64; Tp = T rounded up to whole chunks):
  *   prep  : kt [B,H,T,K] = k e^-G ; qh_r, kh_r [B,H,Tp,K] = scale q e^{G-G_C}, k e^{G_C-G} time-reversed (zero rows first when
  *           T is ragged) ; D, Dr [B,H,NT,K] fp32 = e^{G_C} in forward / reversed chunk order.
  *   time_reverse_pad2 : a_r[bh, Tp-1-t] = a[bh, t] (zero rows for t >= T), same for b; rows of Dm elements.
@@ -162,13 +162,14 @@ int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const void *v, c
  *           reversed cumsum of dq q - dk k (fp32), totals [B,H,NT,K] its chunk sums.
  *   dgk_finish : dgk = bf16(dgk_local + carry[b,h,t/64,:]). */
 int lina_gla_bwd_prep(const void *q, const void *k, const void *gk, void *kt, void *qh_r, void *kh_r, float *D, float *Dr,
-                      int B, int H, int T, int K, float scale, void *stream);
+                      int B, int H, int T, int K, int bthd, float scale, void *stream);
 int lina_time_reverse_pad2(const void *a, const void *b, void *a_r, void *b_r, long long BH, int T, int Tp, int Dm,
                            void *stream);
 int lina_gla_bwd_post(const float *dqa, const float *dqb, const float *dka, const float *dkb, const void *q, const void *k,
                       const void *gk, void *dq, void *dk, float *dgk_local, float *totals,
-                      int B, int H, int T, int K, float scale, void *stream);
-int lina_gla_bwd_dgk_finish(const float *dgk_local, const float *carry, void *dgk, int B, int H, int T, int K, void *stream);
+                      int B, int H, int T, int K, int bthd, float scale, void *stream);
+int lina_gla_bwd_dgk_finish(const float *dgk_local, const float *carry, void *dgk, int B, int H, int T, int K, int bthd,
+                            void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ShortConvolution: y[b,l,d] = act(sum_j w[d,j] * x[b, l-(W-1)+j, d]), act = SiLU or identity.

@@ -38,10 +38,10 @@ PROTOTYPES = {
     "lina_gla_prefill_prep_gated": (_i, [_p, C.c_longlong] * 3 + [_p] * 4 + [C.c_longlong] + [_p] * 7 + [_i] * 7 + [_f, _f, _p]),
     "lina_gla_chunk_fwd_pregated_bthd": (_i, [_p] * 5 + [_i, _p, _p] + [_i] * 5 + [_p]),
     "lina_gla_chunk_fwd_pregated": (_i, [_p] * 5 + [_i, _p, _p] + [_i] * 11 + [_p]),
-    "lina_gla_bwd_prep": (_i, [_p] * 8 + [_i] * 4 + [_f, _p]),
+    "lina_gla_bwd_prep": (_i, [_p] * 8 + [_i] * 5 + [_f, _p]),
     "lina_time_reverse_pad2": (_i, [_p] * 4 + [C.c_longlong, _i, _i, _i, _p]),
-    "lina_gla_bwd_post": (_i, [_p] * 11 + [_i] * 4 + [_f, _p]),
-    "lina_gla_bwd_dgk_finish": (_i, [_p] * 3 + [_i] * 4 + [_p]),
+    "lina_gla_bwd_post": (_i, [_p] * 11 + [_i] * 5 + [_f, _p]),
+    "lina_gla_bwd_dgk_finish": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_short_conv_fwd": (_i, [_p] * 4 + [_i] * 7 + [_p]),
     "lina_short_conv_bwd": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "lina_short_conv_update": (_i, [_p, _p, _i, _p, _p] + [_i] * 5 + [_p]),

@@ -24,6 +24,15 @@ constexpr int C = 64;
 constexpr int RB = 8;                                   // rows per load batch
 constexpr float LOG2E = 1.44269504088896340736f;
 
+// element strides (batch, head, time) of a [B,H,T,K] (bthd = 0) or [B,T,H,K] (bthd = 1) tensor; channels are contiguous
+struct Lay { size_t sb, sh, st; };
+Lay make_lay(int bthd, int H, int Tn, int K) {
+    Lay l;
+    if (bthd) { l.sb = (size_t)Tn * H * K; l.sh = (size_t)K; l.st = (size_t)H * K; }
+    else { l.sb = (size_t)H * Tn * K; l.sh = (size_t)Tn * K; l.st = (size_t)K; }
+    return l;
+}
+
 struct ChunkIdx { int cg, n; long long bh; bool ok; };
 __device__ __forceinline__ ChunkIdx chunk_index(int ng, int NT, long long BH) {
     const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
@@ -37,7 +46,7 @@ __device__ __forceinline__ ChunkIdx chunk_index(int ng, int NT, long long BH) {
 }
 
 // sum of gk over the valid rows of the chunk, in log2 units
-__device__ __forceinline__ void chunk_gate_total(const bf16 *g, int K, int nrow, float2 (&GC)[2]) {
+__device__ __forceinline__ void chunk_gate_total(const bf16 *g, size_t K, int nrow, float2 (&GC)[2]) {
     GC[0] = GC[1] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int r0 = 0; r0 < nrow; r0 += RB) {
@@ -58,18 +67,19 @@ __device__ __forceinline__ void chunk_gate_total(const bf16 *g, int K, int nrow,
 __global__ void __launch_bounds__(128, 4)
 gla_bwd_prep_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, const bf16 *__restrict__ gk,
                     bf16 *__restrict__ kt, bf16 *__restrict__ qh_r, bf16 *__restrict__ kh_r, float *__restrict__ D,
-                    float *__restrict__ Dr, long long BH, int T, int K, float log2_scale) {
+                    float *__restrict__ Dr, long long BH, int H, int T, int K, float log2_scale, Lay lt, Lay lp) {
     const int NT = (T + C - 1) / C, Tp = NT * C;
     const ChunkIdx ci = chunk_index(K / 4, NT, BH);
     if (!ci.ok) return;
     const int d0 = ci.cg * 4, t0 = ci.n * C;
     const int nrow = min(C, T - t0);
-    const size_t in0 = ((size_t)ci.bh * T + t0) * K + d0;
+    const size_t bb = (size_t)(ci.bh / H), hh = (size_t)(ci.bh % H);
+    const size_t in0 = bb * lt.sb + hh * lt.sh + (size_t)t0 * lt.st + d0;
     const bf16 *qp = q + in0, *kp = k + in0, *gp = gk + in0;
     bf16 *ktp = kt + in0;
-    const size_t rbase = (size_t)ci.bh * Tp * K + d0;          // reversed arrays: row Tp-1-t
+    const size_t rbase = bb * lp.sb + hh * lp.sh + d0;          // reversed arrays: row Tp-1-t
     float2 GC[2];
-    chunk_gate_total(gp, K, nrow, GC);
+    chunk_gate_total(gp, lt.st, nrow, GC);
     const float4 dec = make_float4(ex2_approx(GC[0].x), ex2_approx(GC[0].y), ex2_approx(GC[1].x), ex2_approx(GC[1].y));
     *reinterpret_cast<float4 *>(D + ((size_t)ci.bh * NT + ci.n) * K + d0) = dec;
     *reinterpret_cast<float4 *>(Dr + ((size_t)ci.bh * NT + (NT - 1 - ci.n)) * K + d0) = dec;
@@ -80,7 +90,7 @@ gla_bwd_prep_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, cons
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
             const bool ok = r0 + i < nrow;
-            const size_t off = (size_t)(r0 + i) * K;
+            const size_t off = (size_t)(r0 + i) * lt.st;
             rq[i] = ok ? *reinterpret_cast<const uint2 *>(qp + off) : make_uint2(0, 0);
             rk[i] = ok ? *reinterpret_cast<const uint2 *>(kp + off) : make_uint2(0, 0);
             rg[i] = ok ? *reinterpret_cast<const uint2 *>(gp + off) : make_uint2(0, 0);
@@ -103,10 +113,10 @@ gla_bwd_prep_kernel(const bf16 *__restrict__ q, const bf16 *__restrict__ k, cons
             // rows past the end of the sequence (ragged last chunk) are zero rows of the padded, reversed operands
             const uint2 zq = ok ? make_uint2(oqh[0], oqh[1]) : make_uint2(0, 0);
             const uint2 zk = ok ? make_uint2(okh[0], okh[1]) : make_uint2(0, 0);
-            const size_t roff = rbase + (size_t)(Tp - 1 - t) * K;
+            const size_t roff = rbase + (size_t)(Tp - 1 - t) * lp.st;
             *reinterpret_cast<uint2 *>(qh_r + roff) = zq;
             *reinterpret_cast<uint2 *>(kh_r + roff) = zk;
-            if (ok) *reinterpret_cast<uint2 *>(ktp + (size_t)(r0 + i) * K) = make_uint2(okt[0], okt[1]);
+            if (ok) *reinterpret_cast<uint2 *>(ktp + (size_t)(r0 + i) * lt.st) = make_uint2(okt[0], okt[1]);
         }
     }
 }
@@ -149,16 +159,18 @@ __global__ void __launch_bounds__(128, 4)
 gla_bwd_post_kernel(const float *__restrict__ dqa, const float *__restrict__ dqb, const float *__restrict__ dka,
                     const float *__restrict__ dkb, const bf16 *__restrict__ q, const bf16 *__restrict__ k,
                     const bf16 *__restrict__ gk, bf16 *__restrict__ dq, bf16 *__restrict__ dk,
-                    float *__restrict__ dgk_local, float *__restrict__ totals, long long BH, int T, int K, float log2_scale) {
+                    float *__restrict__ dgk_local, float *__restrict__ totals, long long BH, int H, int T, int K,
+                    float log2_scale, Lay lt, Lay lp) {
     const int NT = (T + C - 1) / C, Tp = NT * C;
     const ChunkIdx ci = chunk_index(K / 4, NT, BH);
     if (!ci.ok) return;
     const int d0 = ci.cg * 4, t0 = ci.n * C;
     const int nrow = min(C, T - t0);
-    const size_t in0 = ((size_t)ci.bh * T + t0) * K + d0;
-    const size_t rbase = (size_t)ci.bh * Tp * K + d0;
+    const size_t bb = (size_t)(ci.bh / H), hh = (size_t)(ci.bh % H);
+    const size_t in0 = bb * lt.sb + hh * lt.sh + (size_t)t0 * lt.st + d0;
+    const size_t rbase = bb * lp.sb + hh * lp.sh + d0;
     float2 GC[2];
-    chunk_gate_total(gk + in0, K, nrow, GC);
+    chunk_gate_total(gk + in0, lt.st, nrow, GC);
     float2 G[2] = {GC[0], GC[1]};                                // inclusive cumsum at the last valid row
     float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll 1
@@ -169,8 +181,8 @@ gla_bwd_post_kernel(const float *__restrict__ dqa, const float *__restrict__ dqb
         for (int i = 0; i < RBP; ++i) {
             const int r = r1 - 1 - i;
             const bool ok = r >= 0;
-            const size_t off = in0 + (size_t)(ok ? r : 0) * K;
-            const size_t roff = rbase + (size_t)(Tp - 1 - (t0 + (ok ? r : 0))) * K;
+            const size_t off = in0 + (size_t)(ok ? r : 0) * lt.st;
+            const size_t roff = rbase + (size_t)(Tp - 1 - (t0 + (ok ? r : 0))) * lp.st;
             rq[i] = ok ? *reinterpret_cast<const uint2 *>(q + off) : make_uint2(0, 0);
             rk[i] = ok ? *reinterpret_cast<const uint2 *>(k + off) : make_uint2(0, 0);
             rg[i] = ok ? *reinterpret_cast<const uint2 *>(gk + off) : make_uint2(0, 0);
@@ -203,7 +215,7 @@ gla_bwd_post_kernel(const float *__restrict__ dqa, const float *__restrict__ dqb
                 ok_[p] = pack_bf16(dkv.x, dkv.y);
                 G[p] = __ffma2_rn(bf2_to_f2(p == 0 ? rg[i].x : rg[i].y), make_float2(-LOG2E, -LOG2E), G[p]);   // -> G_{t-1}
             }
-            const size_t off = in0 + (size_t)r * K;
+            const size_t off = in0 + (size_t)r * lt.st;
             *reinterpret_cast<uint2 *>(dq + off) = make_uint2(oq[0], oq[1]);
             *reinterpret_cast<uint2 *>(dk + off) = make_uint2(ok_[0], ok_[1]);
             *reinterpret_cast<float4 *>(dgk_local + off) = make_float4(lo[0].x, lo[0].y, lo[1].x, lo[1].y);
@@ -214,15 +226,24 @@ gla_bwd_post_kernel(const float *__restrict__ dqa, const float *__restrict__ dqb
 
 __global__ void __launch_bounds__(256)
 gla_bwd_dgk_finish_kernel(const float *__restrict__ dgk_local, const float *__restrict__ carry, bf16 *__restrict__ dgk,
-                          long long BH, int T, int K) {
+                          long long BH, int H, int T, int K, Lay lt) {
     const int NT = (T + C - 1) / C, nv = K / 4;
     const long long total = BH * T * nv;
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
-    const int dv = (int)(i % nv);
+    const int dv = (int)(i % nv);                                   // enumerate in MEMORY order of the layout: (.., t|h, h|t, dv)
     const long long rest = i / nv;
-    const int t = (int)(rest % T);
-    const long long bh = rest / T;
+    long long bh;
+    int t;
+    if (lt.sh < lt.st) {                                            // [B,T,H,K]
+        const int hh = (int)(rest % H);
+        const long long r2 = rest / H;
+        t = (int)(r2 % T);
+        bh = (r2 / T) * H + hh;
+    } else {
+        t = (int)(rest % T);
+        bh = rest / T;
+    }
     const float4 a = *reinterpret_cast<const float4 *>(dgk_local + (size_t)i * 4);
     const float4 c = *reinterpret_cast<const float4 *>(carry + ((size_t)bh * NT + t / C) * K + (size_t)dv * 4);
     *reinterpret_cast<uint2 *>(dgk + (size_t)i * 4) = make_uint2(pack_bf16(a.x + c.x, a.y + c.y), pack_bf16(a.z + c.z, a.w + c.w));
@@ -233,7 +254,7 @@ bool al16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 }  // namespace
 
 extern "C" int lina_gla_bwd_prep(const void *q, const void *k, const void *gk, void *kt, void *qh_r, void *kh_r, float *D,
-                                 float *Dr, int B, int H, int T, int K, float scale, void *stream) {
+                                 float *Dr, int B, int H, int T, int K, int bthd, float scale, void *stream) {
     LINA_REQUIRE(q && k && gk && kt && qh_r && kh_r && D && Dr, LINA_ERR_BAD_ARG, "gla_bwd_prep: null pointer");
     LINA_REQUIRE(B > 0 && H > 0 && T > 0 && K > 0 && K % 4 == 0 && scale > 0.f, LINA_ERR_BAD_ARG, "gla_bwd_prep: bad size");
     LINA_REQUIRE(al16(q) && al16(k) && al16(gk) && al16(kt) && al16(qh_r) && al16(kh_r) && al16(D) && al16(Dr),
@@ -242,7 +263,7 @@ extern "C" int lina_gla_bwd_prep(const void *q, const void *k, const void *gk, v
     const long long n = (long long)B * H * NT * (K / 4);
     gla_bwd_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         (const bf16 *)q, (const bf16 *)k, (const bf16 *)gk, (bf16 *)kt, (bf16 *)qh_r, (bf16 *)kh_r, D, Dr, (long long)B * H,
-        T, K, log2f(scale));
+        H, T, K, log2f(scale), make_lay(bthd, H, T, K), make_lay(bthd, H, NT * C, K));
     LINA_LAUNCH_OK("gla_bwd_prep_kernel");
     return LINA_OK;
 }
@@ -264,7 +285,7 @@ extern "C" int lina_time_reverse_pad2(const void *a, const void *b, void *a_r, v
 
 extern "C" int lina_gla_bwd_post(const float *dqa, const float *dqb, const float *dka, const float *dkb, const void *q,
                                  const void *k, const void *gk, void *dq, void *dk, float *dgk_local, float *totals, int B,
-                                 int H, int T, int K, float scale, void *stream) {
+                                 int H, int T, int K, int bthd, float scale, void *stream) {
     LINA_REQUIRE(dqa && dka && q && k && gk && dq && dk && dgk_local && totals, LINA_ERR_BAD_ARG, "gla_bwd_post: null pointer");
     LINA_REQUIRE((dqb == nullptr) == (dkb == nullptr), LINA_ERR_BAD_ARG, "gla_bwd_post: pass both second pieces or none");
     LINA_REQUIRE(B > 0 && H > 0 && T > 0 && K > 0 && K % 4 == 0 && scale > 0.f, LINA_ERR_BAD_ARG, "gla_bwd_post: bad size");
@@ -272,18 +293,18 @@ extern "C" int lina_gla_bwd_post(const float *dqa, const float *dqb, const float
     const long long n = (long long)B * H * NT * (K / 4);
     gla_bwd_post_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         dqa, dqb, dka, dkb, (const bf16 *)q, (const bf16 *)k, (const bf16 *)gk, (bf16 *)dq, (bf16 *)dk, dgk_local, totals,
-        (long long)B * H, T, K, log2f(scale));
+        (long long)B * H, H, T, K, log2f(scale), make_lay(bthd, H, T, K), make_lay(bthd, H, NT * C, K));
     LINA_LAUNCH_OK("gla_bwd_post_kernel");
     return LINA_OK;
 }
 
 extern "C" int lina_gla_bwd_dgk_finish(const float *dgk_local, const float *carry, void *dgk, int B, int H, int T, int K,
-                                       void *stream) {
+                                       int bthd, void *stream) {
     LINA_REQUIRE(dgk_local && carry && dgk && B > 0 && H > 0 && T > 0 && K > 0 && K % 4 == 0, LINA_ERR_BAD_ARG,
                  "gla_bwd_dgk_finish: bad argument");
     const long long n = (long long)B * H * T * (K / 4);
-    gla_bwd_dgk_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dgk_local, carry, (bf16 *)dgk,
-                                                                                              (long long)B * H, T, K);
+    gla_bwd_dgk_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        dgk_local, carry, (bf16 *)dgk, (long long)B * H, H, T, K, make_lay(bthd, H, T, K));
     LINA_LAUNCH_OK("gla_bwd_dgk_finish_kernel");
     return LINA_OK;
 }

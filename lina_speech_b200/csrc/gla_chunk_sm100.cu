@@ -525,12 +525,16 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
         const uint32_t box[4] = {64, 64, 1, 1};
         const uint64_t *sk = bthd ? str_bthd : str_bhtd, *sv = bthd ? vstr_bthd : vstr_bhtd;
         int rc;
-        if (!bthd && (ldq || ldk || ldv)) {
-            // [B,H,T,D] operands that are column slices of wider tensors (row stride ld elements): the backward reads
+        if (ldq || ldk || ldv) {
+            // operands that are column slices of wider tensors (row stride ld elements per (t, h)): the backward reads
             // V pieces of do / v in place
             const uint64_t lq = ldq ? ldq : kd, lk = ldk ? ldk : kd, lv = ldv ? ldv : vd;
-            const uint64_t sq[4] = {2, lq * 2, t * lq * 2, h * t * lq * 2}, sk2[4] = {2, lk * 2, t * lk * 2, h * t * lk * 2};
-            const uint64_t sv2[4] = {2, lv * 2, t * lv * 2, h * t * lv * 2};
+            auto strides = [&](uint64_t l, uint64_t *o4) {
+                if (bthd) { o4[0] = 2; o4[1] = h * l * 2; o4[2] = l * 2; o4[3] = t * h * l * 2; }
+                else { o4[0] = 2; o4[1] = l * 2; o4[2] = t * l * 2; o4[3] = h * t * l * 2; }
+            };
+            uint64_t sq[4], sk2[4], sv2[4];
+            strides(lq, sq); strides(lk, sk2); strides(lv, sv2);
             if ((rc = lina_make_tmap_bf16(&tm.q, q, 4, dims, sq, box))) return rc;
             if ((rc = lina_make_tmap_bf16(&tm.k, k, 4, dims, sk2, box))) return rc;
             if ((rc = lina_make_tmap_bf16(&tm.g, q, 4, dims, sq, box))) return rc;
@@ -635,9 +639,8 @@ extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const
     LINA_REQUIRE((row_decay != 0) == (out_f32 != 0), LINA_ERR_UNSUPPORTED,
                  "gla_chunk_fwd_pregated: only (column decay, bf16 out) and (row decay, fp32 out) are instantiated");
     LINA_REQUIRE(ldq >= 0 && ldk >= 0 && ldv >= 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
-                     (ldq == 0 || ldq >= K) && (ldk == 0 || ldk >= K) && (ldv == 0 || ldv >= V) &&
-                     (!bthd || (ldq == 0 && ldk == 0 && ldv == 0)),
-                 LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: row strides must be 0 (dense) or multiples of 8 >= the width, [B,H,T,D] only");
+                     (ldq == 0 || ldq >= K) && (ldk == 0 || ldk >= K) && (ldv == 0 || ldv >= V),
+                 LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: row strides must be 0 (dense) or multiples of 8 >= the width");
     cudaStream_t st = (cudaStream_t)stream;
     bthd = bthd ? 1 : 0;
     if (row_decay) {

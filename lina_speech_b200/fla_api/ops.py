@@ -100,24 +100,29 @@ def _tc_bwd_eligible(q, v) -> bool:
             and B * H <= 65535)
 
 
-def _run_pregated(qg, kg, v, decay, h0, o, ht, row_decay: bool):
-    """One launch of the pre-gated tensor-core kernel on [B,H,T,D] operands (the unit the backward is built from).
-    qg / kg / v may be last-dim slices of wider contiguous [B,H,T,W] tensors: they are read in place (row stride W)."""
-    B, H, T, K = qg.shape
+def _run_pregated(qg, kg, v, decay, h0, o, ht, row_decay: bool, bthd: bool = False):
+    """One launch of the pre-gated tensor-core kernel (the unit the backward is built from).  Operands are given in their
+    MEMORY layout -- [B,H,T,D], or [B,T,H,D] with ``bthd`` -- and qg / kg / v may be last-dim slices of wider contiguous
+    tensors: they are read in place (row stride = the parent's width)."""
+    if bthd:
+        B, T, H, K = qg.shape
+    else:
+        B, H, T, K = qg.shape
     V = v.shape[-1]
 
     def ld(t):
         if t.is_contiguous():
             return 0
-        w = t.stride(2)
-        if t.stride(3) != 1 or t.stride(1) != T * w or t.stride(0) != H * T * w:
-            raise ValueError("operand must be a last-dim slice of a contiguous [B,H,T,W] tensor")
+        w = t.stride(2)                          # [B,H,T,W]: stride of T; [B,T,H,W]: stride of H -- the parent's row width
+        exp = (H * T * w, T * w, w, 1) if not bthd else (T * H * w, H * w, w, 1)
+        if tuple(t.stride()) != exp:
+            raise ValueError("operand must be a last-dim slice of a contiguous tensor")
         return w
 
     assert decay.is_contiguous() and o.is_contiguous()
     rc = L.lib().lina_gla_chunk_fwd_pregated(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(h0),
-                                            L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V, 0,
-                                            int(row_decay), int(o.dtype == torch.float32), ld(qg), ld(kg), ld(v),
+                                            L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V,
+                                            int(bthd), int(row_decay), int(o.dtype == torch.float32), ld(qg), ld(kg), ld(v),
                                             L.stream(qg))
     L.count_launches(1)
     L.check(rc, "lina_gla_chunk_fwd_pregated")
@@ -126,32 +131,44 @@ def _run_pregated(qg, kg, v, decay, h0, o, ht, row_decay: bool):
 def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     """Product path of the tensor-core backward: same scheme as ``_bwd_tc_reference`` with fused element-wise kernels.
     9 launches of ours per call at V <= 512: prep, flip, 5 x tcgen05, post, finish (+ a tiny torch scan over the chunk
-    totals and the transposes of the [K,V] states)."""
+    totals and the transposes of the [K,V] states).  Works in the memory layout the operands arrive in: when q, k, v, gk
+    are [B,H,T,D] views of [B,T,H,D] tensors (what the model passes) nothing is copied and the gradients come back as the
+    same kind of view."""
     lib = L.lib()
-    q, k, v, gk, do = (x.contiguous() for x in (q, k, v, gk, do))
+    bthd = all(_is_bthd(x) for x in (q, k, v, gk))
     B, H, T, K = q.shape
     V = v.shape[-1]
+    if bthd:                                       # memory-layout tensors [B,T,H,D]
+        q, k, v, gk = (x.transpose(1, 2) for x in (q, k, v, gk))
+        do = do.transpose(1, 2).contiguous()
+    else:
+        q, k, v, gk, do = (x.contiguous() for x in (q, k, v, gk, do))
     C = 64
     NT = (T + C - 1) // C
     Tp = NT * C
     dev, bf, f32 = q.device, q.dtype, torch.float32
     st = L.stream(q)
-    kt = torch.empty(B, H, T, K, dtype=bf, device=dev)
-    qh_r, kh_r = (torch.empty(B, H, Tp, K, dtype=bf, device=dev) for _ in range(2))
+    tdim = 1 if bthd else 2
+
+    def alloc(Tn, Dn, dtype):
+        return torch.empty((B, Tn, H, Dn) if bthd else (B, H, Tn, Dn), dtype=dtype, device=dev)
+
+    kt = alloc(T, K, bf)
+    qh_r, kh_r = alloc(Tp, K, bf), alloc(Tp, K, bf)
     D, Dr = (torch.empty(B, H, NT, K, dtype=f32, device=dev) for _ in range(2))
     L.check(lib.lina_gla_bwd_prep(L.ptr(q), L.ptr(k), L.ptr(gk), L.ptr(kt), L.ptr(qh_r), L.ptr(kh_r), L.ptr(D), L.ptr(Dr),
-                                  B, H, T, K, scale, st), "lina_gla_bwd_prep")
-    do_r, v_r = (torch.empty(B, H, Tp, V, dtype=bf, device=dev) for _ in range(2))
-    L.check(lib.lina_time_reverse_pad2(L.ptr(do), L.ptr(v), L.ptr(do_r), L.ptr(v_r), B * H, T, Tp, V, st),
-            "lina_time_reverse_pad2")
+                                  B, H, T, K, int(bthd), scale, st), "lina_gla_bwd_prep")
+    do_r, v_r = alloc(Tp, V, bf), alloc(Tp, V, bf)
+    L.check(lib.lina_time_reverse_pad2(L.ptr(do), L.ptr(v), L.ptr(do_r), L.ptr(v_r), B if bthd else B * H, T, Tp,
+                                       H * V if bthd else V, st), "lina_time_reverse_pad2")
     L.count_launches(2)
     dht32 = dht.float().contiguous() if dht is not None else None
 
     # dv (+ dh0): reversed time, key-dim decay
-    dv_r = torch.empty(B, H, Tp, V, dtype=bf, device=dev)
+    dv_r = alloc(Tp, V, bf)
     dh0 = torch.empty(B, H, K, V, dtype=f32, device=dev) if want_dh0 else None
-    _run_pregated(kh_r, qh_r, do_r, Dr, dht32, dv_r, dh0, False)
-    dv = dv_r.flip(2)[:, :, :T] if Tp != T else dv_r.flip(2)
+    _run_pregated(kh_r, qh_r, do_r, Dr, dht32, dv_r, dh0, False, bthd)
+    dv = dv_r.flip(tdim).narrow(tdim, 0, T)
 
     ns = (V + 255) // 256
     Vp = V // ns
@@ -159,105 +176,36 @@ def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     for j in range(ns):
         sl = slice(j * Vp, (j + 1) * Vp)
         h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
-        o = torch.empty(B, H, T, K, dtype=f32, device=dev)
+        o = alloc(T, K, f32)
         ht = torch.empty(B, H, Vp, K, dtype=f32, device=dev) if dht is not None else None
-        _run_pregated(do[..., sl], v[..., sl], kt, D, h0_j, o, ht, True)            # dq~ piece (forward time, row decay)
+        _run_pregated(do[..., sl], v[..., sl], kt, D, h0_j, o, ht, True, bthd)            # dq~ piece (forward time, row decay)
         dq_parts.append(o)
         if ht is not None:
             ST.append(ht.transpose(-1, -2))
         dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
-        o2 = torch.empty(B, H, Tp, K, dtype=f32, device=dev)
-        _run_pregated(v_r[..., sl], do_r[..., sl], qh_r, Dr, dht_j, o2, None, True)  # dk^ piece (reversed time)
+        o2 = alloc(Tp, K, f32)
+        _run_pregated(v_r[..., sl], do_r[..., sl], qh_r, Dr, dht_j, o2, None, True, bthd)  # dk^ piece (reversed time)
         dk_parts.append(o2)
     while len(dq_parts) > 2:                       # V > 512: fold the extra pieces (the post kernel sums two)
         dq_parts[0].add_(dq_parts.pop())
         dk_parts[0].add_(dk_parts.pop())
-    dq, dk, dgk = torch.empty_like(q), torch.empty_like(k), torch.empty_like(gk)
-    dgk_local = torch.empty(B, H, T, K, dtype=f32, device=dev)
+    dq, dk, dgk = alloc(T, K, bf), alloc(T, K, bf), alloc(T, K, bf)
+    dgk_local = alloc(T, K, f32)
     totals = torch.empty(B, H, NT, K, dtype=f32, device=dev)
     two = len(dq_parts) == 2
     L.check(lib.lina_gla_bwd_post(L.ptr(dq_parts[0]), L.ptr(dq_parts[1]) if two else None, L.ptr(dk_parts[0]),
                                   L.ptr(dk_parts[1]) if two else None, L.ptr(q), L.ptr(k), L.ptr(gk), L.ptr(dq), L.ptr(dk),
-                                  L.ptr(dgk_local), L.ptr(totals), B, H, T, K, scale, st), "lina_gla_bwd_post")
+                                  L.ptr(dgk_local), L.ptr(totals), B, H, T, K, int(bthd), scale, st), "lina_gla_bwd_post")
     carry = totals.flip(2).cumsum(2).flip(2) - totals                     # sum over the LATER chunks, [B,H,NT,K]
     if dht32 is not None:
         carry = carry + (dht32 * torch.cat(ST, dim=-1)).sum(-1).unsqueeze(2)
     carry = carry.contiguous()
-    L.check(lib.lina_gla_bwd_dgk_finish(L.ptr(dgk_local), L.ptr(carry), L.ptr(dgk), B, H, T, K, st), "lina_gla_bwd_dgk_finish")
+    L.check(lib.lina_gla_bwd_dgk_finish(L.ptr(dgk_local), L.ptr(carry), L.ptr(dgk), B, H, T, K, int(bthd), st),
+            "lina_gla_bwd_dgk_finish")
     L.count_launches(2)
+    if bthd:
+        dq, dk, dgk, dv = (x.transpose(1, 2) for x in (dq, dk, dgk, dv))
     return dq, dk, dv, dgk, dh0
-
-
-def _bwd_tc_reference(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=None):
-    """Chunked backward (dq, dk, dv, dgk, dh0) as FIVE runs of the pre-gated forward kernel (C = 64; G = in-chunk cumsum of
-    gk, D = e^{G_C}; q^ = scale q e^{G-G_C}, k^ = k e^{G_C-G}, k~ = k e^{-G}; "rev" = time-reversed):
-
-      dv, dh0 = kernel(qg = rev k^, kg = rev q^, v = rev do, decay = rev D, h0 = dht)                     (key-dim decay)
-      dq~    += kernel(qg = do[:, Vj], kg = v[:, Vj], v = k~, decay = D as ROW decay, h0 = h0[:, :, :, Vj]^T)   per V piece j
-      dk^    += kernel(qg = rev v[:, Vj], kg = rev do[:, Vj], v = rev q^, decay = rev D (ROW), h0 = dht[..., Vj]^T)
-      dq = dq~ * scale e^G ;  dk = rev(dk^) * e^{G_C-G} ;  dgk = reversed cumsum_T(dq q - dk k) [+ sum_v dht S_T]
-
-    (the identities of FLA/fla/ops/gla/chunk.py:140-341 / FLA/fla/ops/common/chunk_h.py:111-189 regrouped so that every
-    contraction is the forward kernel's; verified against the recurrence's explicit backward in tests/test_host.py with the
-    oracle's restatement of the kernel contract as ``run``).
-
-    This torch-glue version is the readable statement of the scheme and what the CPU host-logic test exercises (with
-    ``run`` = the oracle's restatement of the kernel contract); the product path is ``_bwd_tc`` below, which does the same
-    with four fused element-wise kernels (csrc/gla_bwd_glue.cu) and strided operand reads instead of ~25 torch ops."""
-    run = run or _run_pregated
-    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
-    B, H, T, K = q.shape
-    V = v.shape[-1]
-    C = 64
-    NT = (T + C - 1) // C
-    Tp, pad = NT * C, NT * C - T
-    lo = q.dtype
-
-    def padT(x):
-        return torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x
-
-    qf, kf, gf = (padT(x.float()) for x in (q, k, gk))
-    vb, dob = padT(v).contiguous(), padT(do).contiguous()
-    G = gf.view(B, H, NT, C, K).cumsum(3)
-    GC = G[:, :, :, -1:, :]
-    D = GC.squeeze(3).exp().contiguous()                                   # [B,H,NT,K]
-    Dr = D.flip(2).contiguous()
-    kt = (kf.view(B, H, NT, C, K) * (-G).exp()).to(lo).view(B, H, Tp, K)
-    qh = (qf.view(B, H, NT, C, K) * ((G - GC).exp() * scale)).to(lo).view(B, H, Tp, K)
-    e_gc_g = (GC - G).exp()
-    kh = (kf.view(B, H, NT, C, K) * e_gc_g).to(lo).view(B, H, Tp, K)
-    qh_r = qh.flip(2).contiguous()
-    dht32 = dht.float().contiguous() if dht is not None else None
-
-    dv_r = torch.empty(B, H, Tp, V, dtype=lo, device=q.device)
-    dh0 = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_dh0 else None
-    run(kh.flip(2).contiguous(), qh_r, dob.flip(2).contiguous(), Dr, dht32, dv_r, dh0, False)
-    dv = dv_r.flip(2)[:, :, :T]
-
-    ns = (V + 255) // 256
-    Vp = V // ns
-    dqt = dkr = None
-    ST = []
-    for j in range(ns):
-        sl = slice(j * Vp, (j + 1) * Vp)
-        do_j, v_j = dob[..., sl].contiguous(), vb[..., sl].contiguous()
-        h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
-        o = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
-        ht = torch.empty(B, H, Vp, K, dtype=torch.float32, device=q.device) if dht is not None else None
-        run(do_j, v_j, kt, D, h0_j, o, ht, True)
-        dqt = o if dqt is None else dqt.add_(o)
-        if ht is not None:
-            ST.append(ht.transpose(-1, -2))
-        dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
-        o2 = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
-        run(v_j.flip(2).contiguous(), do_j.flip(2).contiguous(), qh_r, Dr, dht_j, o2, None, True)
-        dkr = o2 if dkr is None else dkr.add_(o2)
-    dq = (dqt.view(B, H, NT, C, K) * (G.exp() * scale)).view(B, H, Tp, K)[:, :, :T]
-    dk = (dkr.flip(2).view(B, H, NT, C, K) * e_gc_g).view(B, H, Tp, K)[:, :, :T]
-    dgk = (dq * q.float() - dk * k.float()).flip(2).cumsum(2).flip(2)
-    if dht32 is not None:
-        dgk = dgk + (dht32 * torch.cat(ST, dim=-1)).sum(-1).unsqueeze(2)
-    return dq.to(lo), dk.to(lo), dv, dgk.to(lo), dh0
 
 
 def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):

@@ -260,7 +260,8 @@ def test_rwkv6_recurrent_forward(dtype):
 @pytest.mark.parametrize("K,V", [(128, 256), (256, 512)])
 @pytest.mark.parametrize("T", [64, 200, 512])
 @pytest.mark.parametrize("with_state", [False, True])
-def test_tensor_core_backward(K, V, T, with_state):
+@pytest.mark.parametrize("layout", ["bhtd", "bthd"])
+def test_tensor_core_backward(K, V, T, with_state, layout):
     """bf16 backward at tensor-core head sizes = five runs of the pre-gated tcgen05 kernel (fla_api.ops._bwd_tc):
     dq, dk, dv, dgk, dh0 (incl. a gradient flowing into the final state) against the explicit fp64 backward of the
     recurrence on the same bf16-valued inputs; tolerance = the forward's (3e-2 of the max, the reference's own bf16
@@ -276,10 +277,16 @@ def test_tensor_core_backward(K, V, T, with_state):
     h0 = torch.randn(B, H, K, V) if with_state else None
     dht = torch.randn(B, H, K, V) if with_state else None
     ref = GO.recurrent_gla_bwd(q.float(), k.float(), v.float(), gk.float(), h0, do.float(), dht)
-    leaves = [t.to(DEV).requires_grad_(True) for t in (q, k, v, gk)]
+    if layout == "bthd":        # what the model passes: [B,H,T,D] views of [B,T,H,D] memory, gradients come back the same way
+        leaves = [t.transpose(1, 2).contiguous().to(DEV).requires_grad_(True) for t in (q, k, v, gk)]
+        args = [t.transpose(1, 2) for t in leaves]
+        ref = [r.transpose(1, 2) for r in ref[:4]] + [ref[4]]
+    else:
+        leaves = [t.to(DEV).requires_grad_(True) for t in (q, k, v, gk)]
+        args = leaves
     h0d = h0.to(DEV).requires_grad_(True) if with_state else None
-    assert ops._tc_bwd_eligible(leaves[0], leaves[2])
-    o, ht = chunk_gla(*leaves, initial_state=h0d, output_final_state=with_state)
+    assert ops._tc_bwd_eligible(args[0], args[2])
+    o, ht = chunk_gla(*args, initial_state=h0d, output_final_state=with_state)
     loss = (o.float() * do.to(DEV).float()).sum()
     if with_state:
         loss = loss + (ht * dht.to(DEV)).sum()
