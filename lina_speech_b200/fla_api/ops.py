@@ -208,6 +208,78 @@ def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     return dq, dk, dv, dgk, dh0
 
 
+def _bwd_tc_reference(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, run=None):
+    """Chunked backward (dq, dk, dv, dgk, dh0) as FIVE runs of the pre-gated forward kernel (C = 64; G = in-chunk cumsum of
+    gk, D = e^{G_C}; q^ = scale q e^{G-G_C}, k^ = k e^{G_C-G}, k~ = k e^{-G}; "rev" = time-reversed):
+
+      dv, dh0 = kernel(qg = rev k^, kg = rev q^, v = rev do, decay = rev D, h0 = dht)                     (key-dim decay)
+      dq~    += kernel(qg = do[:, Vj], kg = v[:, Vj], v = k~, decay = D as ROW decay, h0 = h0[:, :, :, Vj]^T)   per V piece j
+      dk^    += kernel(qg = rev v[:, Vj], kg = rev do[:, Vj], v = rev q^, decay = rev D (ROW), h0 = dht[..., Vj]^T)
+      dq = dq~ * scale e^G ;  dk = rev(dk^) * e^{G_C-G} ;  dgk = reversed cumsum_T(dq q - dk k) [+ sum_v dht S_T]
+
+    (the identities of FLA/fla/ops/gla/chunk.py:140-341 / FLA/fla/ops/common/chunk_h.py:111-189 regrouped so that every
+    contraction is the forward kernel's; verified against the recurrence's explicit backward in tests/test_host.py with the
+    oracle's restatement of the kernel contract as ``run``).
+
+    This torch-glue version is the readable statement of the scheme and what the CPU host-logic test exercises (with
+    ``run`` = the oracle's restatement of the kernel contract); the product path is ``_bwd_tc`` below, which does the same
+    with four fused element-wise kernels (csrc/gla_bwd_glue.cu) and strided operand reads instead of ~25 torch ops."""
+    run = run or _run_pregated
+    q, k, v, gk = (x.contiguous() for x in (q, k, v, gk))
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    C = 64
+    NT = (T + C - 1) // C
+    Tp, pad = NT * C, NT * C - T
+    lo = q.dtype
+
+    def padT(x):
+        return torch.nn.functional.pad(x, (0, 0, 0, pad)) if pad else x
+
+    qf, kf, gf = (padT(x.float()) for x in (q, k, gk))
+    vb, dob = padT(v).contiguous(), padT(do).contiguous()
+    G = gf.view(B, H, NT, C, K).cumsum(3)
+    GC = G[:, :, :, -1:, :]
+    D = GC.squeeze(3).exp().contiguous()                                   # [B,H,NT,K]
+    Dr = D.flip(2).contiguous()
+    kt = (kf.view(B, H, NT, C, K) * (-G).exp()).to(lo).view(B, H, Tp, K)
+    qh = (qf.view(B, H, NT, C, K) * ((G - GC).exp() * scale)).to(lo).view(B, H, Tp, K)
+    e_gc_g = (GC - G).exp()
+    kh = (kf.view(B, H, NT, C, K) * e_gc_g).to(lo).view(B, H, Tp, K)
+    qh_r = qh.flip(2).contiguous()
+    dht32 = dht.float().contiguous() if dht is not None else None
+
+    dv_r = torch.empty(B, H, Tp, V, dtype=lo, device=q.device)
+    dh0 = torch.empty(B, H, K, V, dtype=torch.float32, device=q.device) if want_dh0 else None
+    run(kh.flip(2).contiguous(), qh_r, dob.flip(2).contiguous(), Dr, dht32, dv_r, dh0, False)
+    dv = dv_r.flip(2)[:, :, :T]
+
+    ns = (V + 255) // 256
+    Vp = V // ns
+    dqt = dkr = None
+    ST = []
+    for j in range(ns):
+        sl = slice(j * Vp, (j + 1) * Vp)
+        do_j, v_j = dob[..., sl].contiguous(), vb[..., sl].contiguous()
+        h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
+        o = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
+        ht = torch.empty(B, H, Vp, K, dtype=torch.float32, device=q.device) if dht is not None else None
+        run(do_j, v_j, kt, D, h0_j, o, ht, True)
+        dqt = o if dqt is None else dqt.add_(o)
+        if ht is not None:
+            ST.append(ht.transpose(-1, -2))
+        dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
+        o2 = torch.empty(B, H, Tp, K, dtype=torch.float32, device=q.device)
+        run(v_j.flip(2).contiguous(), do_j.flip(2).contiguous(), qh_r, Dr, dht_j, o2, None, True)
+        dkr = o2 if dkr is None else dkr.add_(o2)
+    dq = (dqt.view(B, H, NT, C, K) * (G.exp() * scale)).view(B, H, Tp, K)[:, :, :T]
+    dk = (dkr.flip(2).view(B, H, NT, C, K) * e_gc_g).view(B, H, Tp, K)[:, :, :T]
+    dgk = (dq * q.float() - dk * k.float()).flip(2).cumsum(2).flip(2)
+    if dht32 is not None:
+        dgk = dgk + (dht32 * torch.cat(ST, dim=-1)).sum(-1).unsqueeze(2)
+    return dq.to(lo), dk.to(lo), dv, dgk.to(lo), dh0
+
+
 def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     lib = L.lib()
     if _tc_bwd_eligible(q, v):

@@ -46,7 +46,7 @@ configs = [
     ("fused_prefill + CE", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=False)),
     ("fused_prefill + CE + pregated", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True)),
     ("fused_prefill + CE + pregated + split GEMMs", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split")),
-    ("... + split + STATE2 kernel", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split", state2=1)),
+    ("... + split, one state warpgroup", dict(fused=True, cat5=False, tl=0, opt=0, ce=True, pre=True, group="split", state2=1)),
 ]
 for name, cf in configs:
     G.FUSED_PREFILL, G.CAT5, G.PREGATED = cf["fused"], cf["cat5"], cf["pre"]

@@ -202,9 +202,9 @@ report("gla_chunk_fwd_pregated_bthd (tcgen05)", timeit(gla_pre), B * H * T * (2 
 res["gla_chunk_fwd_pregated_bthd (tcgen05)"]["finite"] = bool(torch.isfinite(o_b.float()).all())
 o_one = o_b.clone()
 lib.lina_debug_set_variant(4, 1)
-report("gla_chunk_fwd_pregated_bthd STATE2", timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
-res["gla_chunk_fwd_pregated_bthd STATE2"]["max_diff_vs_one_group"] = (o_b.float() - o_one.float()).abs().max().item()
-print("   STATE2 max diff", res["gla_chunk_fwd_pregated_bthd STATE2"]["max_diff_vs_one_group"])
+report("gla_chunk_fwd_pregated_bthd one state warpgroup", timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
+res["gla_chunk_fwd_pregated_bthd one state warpgroup"]["max_diff_vs_default"] = (o_b.float() - o_one.float()).abs().max().item()
+print("   STATE2 max diff", res["gla_chunk_fwd_pregated_bthd one state warpgroup"]["max_diff_vs_default"])
 lib.lina_debug_set_variant(4, 0)
 
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
