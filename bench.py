@@ -191,6 +191,40 @@ def main_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def train_step_metrics(dev, B=8, T=4096, Tx=256, steps=3):
+    torch.cuda.empty_cache()
+    lm = build_model(dev, torch.float32).train()
+    opt = torch.optim.AdamW(lm.parameters(), lr=2e-4, betas=(0.9, 0.95), weight_decay=0.1)
+    x, y, em, cm = synth_inputs(B, T, Tx, seed=7)
+    xd, yd, emd, cmd = x.to(dev), y.to(dev), em.to(dev), cm.to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = lm(xd, yd, emd, cmd)[1]
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"workload": "LinaModel d1024 l12 train step (fwd + bwd + AdamW), bf16 autocast, bs8 x seq4096 (BASELINE configs[3])",
+           "batch": B, "seq_len": T, "text_len": Tx, "steps": steps, "ms_per_step": ms, "tokens_per_s": B * T / (ms * 1e-3),
+           "loss": float(loss.detach()), "gla_backward": "tensor cores (5 runs of the pre-gated tcgen05 kernel)",
+           "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del lm, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def main_ours(args):
     import torch.distributed as dist
@@ -338,6 +372,15 @@ def main_ours(args):
                     "rtf_24khz": 75.0 * dec2_ms * 1e-3, "state_bytes_per_step": sb2,
                     "state_hbm_frac": sb2 / (dec2_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
 
+    # BASELINE configs[3]: one training step (fwd + bwd + AdamW, bf16 autocast over fp32 parameters) at bs8 x seq4096,
+    # GLA backward on the tensor-core path (five runs of the pre-gated tcgen05 kernel); rank 0 at N = 1 only
+    train = None
+    if world == 1 and not args.no_train:
+        try:
+            train = train_step_metrics(dev)
+        except Exception as e:      # noqa: BLE001  (an extra section must never take the headline line down)
+            train = {"error": repr(e)[:300]}
+
     if rank == 0:
         cpu_v, cores, sample = cpu_reference_rate(budget_s=20.0) if world == 1 else (None, None, None)
         per_step = ms / args.steps
@@ -351,6 +394,8 @@ def main_ours(args):
                        "h2d_bytes_per_step": xh.numel() * 8 + yh.numel() * 8, "d2h_bytes_per_step": 4},
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "decode": decode,
                "decode_bs128": decode_bs128}
+        if train is not None:
+            out["train_step"] = train
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out), flush=True)
@@ -365,6 +410,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work for the whole --impl reference run")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step section")
     ap.add_argument("--profile", action="store_true", help="run only W+K resident steps (for ncu); prints nothing")
     a = ap.parse_args()
     if a.impl == "reference":
