@@ -250,14 +250,13 @@ struct GateArgs {
 };
 
 constexpr int GC = 64;               // chunk length of gla_chunk_sm100.cu
-constexpr int GRB = 2;               // rows per load batch (two batches in flight)
+constexpr int GRB = 4;               // rows per load batch
 
 __device__ __forceinline__ float logsigmoid_bf16r(float x) {   // bf16-rounded like the reference's activation dtype
     return __bfloat162float(__float2bfloat16_rn(logsigmoid_fast_(x)));
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(PREP_THREADS, MINB)
+__global__ void __launch_bounds__(PREP_THREADS, 4)
 qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
     const int ng = a.Dk / 4;
     const long long idx = (long long)blockIdx.x * PREP_THREADS + threadIdx.x;
@@ -287,9 +286,9 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
     }
     float2 G[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};          // log2 units
     const int nrow = min(GC, L - t0);
-    // double-buffered: the loads of rows r+GRB.. are in flight while rows r.. are processed (the kernel is latency bound:
-    // 16 warps per SM at 128 registers, ~120 instructions per row)
-    auto load = [&](uint2 (&rq)[GRB], uint2 (&rk)[GRB], uint2 (&rg)[GRB], int r0) {
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrow; r0 += GRB) {
+        uint2 rq[GRB], rk[GRB], rg[GRB];
 #pragma unroll
         for (int i = 0; i < GRB; ++i) {
             const int l = t0 + r0 + i;
@@ -301,8 +300,6 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
                 rq[i] = rk[i] = rg[i] = make_uint2(0, 0);
             }
         }
-    };
-    auto process = [&](const uint2 (&rq)[GRB], const uint2 (&rk)[GRB], const uint2 (&rg)[GRB], int r0) {
 #pragma unroll
         for (int i = 0; i < GRB; ++i) {
             if (r0 + i >= nrow) break;                    // block-uniform: rows past the sequence end are not gated
@@ -326,15 +323,6 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
             *reinterpret_cast<uint2 *>(qo + (size_t)l * a.Dk) = make_uint2(oq[0], oq[1]);
             *reinterpret_cast<uint2 *>(ko + (size_t)l * a.Dk) = make_uint2(ok[0], ok[1]);
         }
-    };
-    uint2 aq[GRB], ak[GRB], ag[GRB], bq[GRB], bk[GRB], bg[GRB];
-    load(aq, ak, ag, 0);
-#pragma unroll 1
-    for (int r0 = 0; r0 < nrow; r0 += 2 * GRB) {
-        load(bq, bk, bg, r0 + GRB);
-        process(aq, ak, ag, r0);
-        load(aq, ak, ag, r0 + 2 * GRB);
-        process(bq, bk, bg, r0 + GRB);
     }
     // (rows past the end of a partial last chunk contribute gk = 0, like the TMA zero fill of the in-kernel pre-pass)
     const int h = d0 / a.K, kap = d0 - h * a.K;
@@ -473,8 +461,7 @@ extern "C" int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const 
     const long long nthreads = (long long)B * a.NT * (Dk / 4);
     const long long nblk = (nthreads + PREP_THREADS - 1) / PREP_THREADS;
     LINA_REQUIRE(nblk <= 2147483647LL, LINA_ERR_UNSUPPORTED, "gla_prefill_prep_gated: grid too large");
-    if (g_lina_variant[6] == 1) qk_gate_bf16_kernel<3><<<(unsigned)nblk, PREP_THREADS, 0, st>>>(a);   // A/B: 168 registers, no spills
-    else qk_gate_bf16_kernel<4><<<(unsigned)nblk, PREP_THREADS, 0, st>>>(a);
+    qk_gate_bf16_kernel<<<(unsigned)nblk, PREP_THREADS, 0, st>>>(a);
     LINA_LAUNCH_OK("qk_gate_bf16_kernel");
     return LINA_OK;
 }

@@ -89,9 +89,6 @@ def prep_gated():
                                          16.0, K ** -0.5, st())
     assert rc == 0, lib.lina_last_error_string()
 report("prefill_prep_gated (v conv + q~,k~,decay)", timeit(prep_gated), (2 * (3 * kd + vd) + 2 * (2 * kd + vd)) * M)
-lib.lina_debug_set_variant(6, 1)
-report("prefill_prep_gated, gate kernel at 3 blocks/SM", timeit(prep_gated), (2 * (3 * kd + vd) + 2 * (2 * kd + vd)) * M)
-lib.lina_debug_set_variant(6, 0)
 
 xq_c, xv_c = xq.contiguous(), xv.contiguous()
 for variant, name in ((0, "tiles_f32x2"), (3, "tiles_scalar"), (1, "round1_sliding")):
