@@ -75,6 +75,77 @@ groupnorm_swish_kernel(const float *__restrict__ x, const float *__restrict__ ga
     }
 }
 
+
+// Register-resident variant: one CTA per (b, group), NT threads, the group's cpg*L floats (a contiguous run) are loaded
+// ONCE as float4 (all loads issued before the first use), reduced, normalised from registers and stored: one read + one
+// write of the tensor, >= 256 B in flight per thread.  Used when the run fits PER float4 per thread and is 16-byte aligned.
+template <int NT, int PER>
+__global__ void __launch_bounds__(NT)
+groupnorm_swish_reg_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                           float *__restrict__ y, int C, int L, int groups, float eps, int swish) {
+    __shared__ float red[2][NT / 32];
+    __shared__ float stat[2];
+    const int bg = blockIdx.x, g = bg % groups;
+    const int cpg = C / groups;
+    const int n4 = cpg * L / 4;                              // host guarantees (cpg * L) % 4 == 0
+    const float4 *xp = reinterpret_cast<const float4 *>(x + (size_t)bg * cpg * L);
+    float4 *yp = reinterpret_cast<float4 *>(y + (size_t)bg * cpg * L);
+    float4 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int j = threadIdx.x + i * NT;
+        v[i] = j < n4 ? xp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int w = 0; w < NT / 32; ++w) a += red[0][w];
+        stat[0] = (float)(a / (double)(cpg * L));
+    }
+    __syncthreads();
+    const float mean = stat[0];
+    float ss = 0.f;                                          // centred second moment: no cancellation
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if (threadIdx.x + i * NT < n4) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int w = 0; w < NT / 32; ++w) a += red[1][w];
+        stat[1] = (float)(1.0 / sqrt(a / (double)(cpg * L) + (double)eps));
+    }
+    __syncthreads();
+    const float rstd = stat[1];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int j = threadIdx.x + i * NT;
+        if (j < n4) {
+            // the 4 elements of a float4 may straddle a channel boundary only if L % 4 != 0: resolve per element
+            const int e0 = j * 4;
+            float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = g * cpg + (e0 + q) / L;
+                float t = (o[q] - mean) * rstd * gamma[c] + beta[c];
+                if (swish) t = t * sigmoidf_(t);
+                o[q] = t;
+            }
+            yp[j] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // depthwise conv k=7 (optional) + transpose [B,C,L]->[B,L,C] + LayerNorm(no affine)*scale+shift.
 // One CTA = one (batch, tile of TL time steps) x ALL channels.  Every channel row of the tile is one 128-byte
@@ -166,6 +237,48 @@ scale_residual_t_kernel(const float *__restrict__ h, const float *__restrict__ g
         if (c < C && l < L) {
             const size_t idx = ((size_t)b * C + c) * L + l;
             out[idx] = res[idx] + (gamma != nullptr ? gamma[c] : 1.f) * tile[tx][i];
+        }
+    }
+}
+
+
+// 64 x 64 tiles: h rows [l][c0..c0+63] are read as float4 (C % 4 == 0), transposed through shared memory, and res / out rows
+// [c][l0..l0+63] are read / written as float2 (rows of [B,C,L] start on 8-byte boundaries when L is even; the shipped
+// L = 750 is not a multiple of 4).  All loads of a thread are issued before the first use.
+__global__ void __launch_bounds__(256)
+scale_residual_t64_kernel(const float *__restrict__ h, const float *__restrict__ gamma, const float *__restrict__ res,
+                          float *__restrict__ out, int C, int L) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z, l0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
+    float4 hv[4];                                          // 64 rows (l) x 16 float4 (c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * 256, r = idx >> 4, q = idx & 15;
+        const int l = l0 + r, c = c0 + q * 4;
+        hv[i] = (l < L && c < C) ? *reinterpret_cast<const float4 *>(h + ((size_t)b * L + l) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float2 rv[8];                                          // 64 rows (c) x 32 float2 (l)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * 256, r = idx >> 5, q = idx & 31;
+        const int c = c0 + r, l = l0 + q * 2;
+        rv[i] = (c < C && l < L) ? *reinterpret_cast<const float2 *>(res + ((size_t)b * C + c) * L + l) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * 256, r = idx >> 4, q = idx & 15;
+        tile[r][q * 4 + 0] = hv[i].x; tile[r][q * 4 + 1] = hv[i].y; tile[r][q * 4 + 2] = hv[i].z; tile[r][q * 4 + 3] = hv[i].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * 256, r = idx >> 5, q = idx & 31;
+        const int c = c0 + r, l = l0 + q * 2;
+        if (c < C && l < L) {                              // L even: l + 1 < L too
+            const float gm = gamma != nullptr ? gamma[c] : 1.f;
+            *reinterpret_cast<float2 *>(out + ((size_t)b * C + c) * L + l) =
+                make_float2(rv[i].x + gm * tile[q * 2][r], rv[i].y + gm * tile[q * 2 + 1][r]);
         }
     }
 }
@@ -311,7 +424,20 @@ extern "C" int lina_codec_groupnorm_swish(const float *x, const float *gamma, co
     LINA_REQUIRE(x && gamma && beta && y, LINA_ERR_BAD_ARG, "groupnorm_swish: null pointer");
     LINA_REQUIRE(B > 0 && C > 0 && L > 0 && groups > 0 && C % groups == 0, LINA_ERR_BAD_ARG,
                  "groupnorm_swish: bad size (C=%d groups=%d)", C, groups);
-    groupnorm_swish_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, C, L, groups, eps, swish);
+    const long long run = (long long)(C / groups) * L;
+    const bool al = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && run % 4 == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (al && run / 4 <= 512 * 12) {                 // <= 24576 floats per (b, group): 12 float4 per thread, 512 threads
+        groupnorm_swish_reg_kernel<512, 12><<<B * groups, 512, 0, st>>>(x, gamma, beta, y, C, L, groups, eps, swish);
+        LINA_LAUNCH_OK("groupnorm_swish_reg_kernel");
+        return LINA_OK;
+    }
+    if (al && run / 4 <= 512 * 24) {                 // <= 49152 floats (L <= 2048 at 24 channels per group)
+        groupnorm_swish_reg_kernel<512, 24><<<B * groups, 512, 0, st>>>(x, gamma, beta, y, C, L, groups, eps, swish);
+        LINA_LAUNCH_OK("groupnorm_swish_reg_kernel");
+        return LINA_OK;
+    }
+    groupnorm_swish_kernel<<<B * groups, 256, 0, st>>>(x, gamma, beta, y, C, L, groups, eps, swish);
     LINA_LAUNCH_OK("groupnorm_swish_kernel");
     return LINA_OK;
 }
@@ -353,6 +479,12 @@ extern "C" int lina_codec_scale_residual_t(const float *h, const float *gamma, c
     LINA_REQUIRE(h && res && out, LINA_ERR_BAD_ARG, "scale_residual_t: null pointer");
     LINA_REQUIRE(B > 0 && C > 0 && L > 0, LINA_ERR_BAD_ARG, "scale_residual_t: bad size");
     LINA_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, LINA_ERR_UNSUPPORTED, "scale_residual_t: grid too large");
+    if (C % 4 == 0 && L % 2 == 0 && (uintptr_t)h % 16 == 0 && (uintptr_t)res % 8 == 0 && (uintptr_t)out % 8 == 0) {
+        dim3 g64((L + 63) / 64, (C + 63) / 64, B);
+        scale_residual_t64_kernel<<<g64, 256, 0, (cudaStream_t)stream>>>(h, gamma, res, out, C, L);
+        LINA_LAUNCH_OK("scale_residual_t64_kernel");
+        return LINA_OK;
+    }
     dim3 grid((L + 31) / 32, (C + 31) / 32, B);
     scale_residual_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, gamma, res, out, C, L);
     LINA_LAUNCH_OK("scale_residual_t_kernel");
