@@ -239,6 +239,13 @@ int lina_codec_groupnorm_swish(const float *x, const float *gamma, const float *
  * dw_w NULL = skip the conv (plain transposing AdaLN, DEC/models.py:229). */
 int lina_codec_dwconv_adaln(const float *x, const float *dw_w, const float *dw_b, const float *scale,
                             const float *shift, float *y, int B, int C, int L, float eps, void *stream);
+/* Same two functions as a pair of small kernels (tile = 64 channels x 64 steps, deterministic merged statistics) instead of
+ * one kernel holding all C channels of a time tile: `ws` = lina_codec_dwconv_adaln_workspace_bytes(B, C, L). */
+size_t lina_codec_dwconv_adaln_workspace_bytes(int B, int C, int L);
+int lina_codec_dwconv_adaln_ws(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                               const float *shift, float *y, float *ws, int B, int C, int L, float eps, void *stream);
+int lina_codec_layernorm_t_ws(const float *x, const float *gamma, const float *beta, float *y, float *ws,
+                              int B, int C, int L, float eps, void *stream);
 /* ConvNeXt back half (DEC/modules.py:55-59): out[b,c,l] = res[b,c,l] + gamma[c] * h[b,l,c]. */
 int lina_codec_scale_residual_t(const float *h, const float *gamma, const float *res, float *out,
                                 int B, int C, int L, void *stream);

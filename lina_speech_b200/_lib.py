@@ -57,6 +57,9 @@ PROTOTYPES = {
     "lina_codec_dwconv_adaln": (_i, [_p] * 6 + [_i] * 3 + [_f, _p]),
     "lina_codec_scale_residual_t": (_i, [_p] * 4 + [_i] * 3 + [_p]),
     "lina_codec_layernorm_t": (_i, [_p] * 4 + [_i] * 3 + [_f, _p]),
+    "lina_codec_dwconv_adaln_workspace_bytes": (_sz, [_i] * 3),
+    "lina_codec_dwconv_adaln_ws": (_i, [_p] * 7 + [_i] * 3 + [_f, _p]),
+    "lina_codec_layernorm_t_ws": (_i, [_p] * 5 + [_i] * 3 + [_f, _p]),
     "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
     "lina_debug_set_variant": (_i, [_i, _i]),

@@ -46,10 +46,15 @@ def dwconv_adaln(x, dw_w, dw_b, scale, shift, eps: float):
     w = _f32c(dw_w).view(C, -1) if dw_w is not None else None
     if w is not None and w.shape[1] != 7:
         raise NotImplementedError("depthwise kernel size must be 7 (ConvNeXtBlock, modules.py:28)")
-    rc = L.lib().lina_codec_dwconv_adaln(L.ptr(x), L.ptr(w), L.ptr(_f32c(dw_b)) if dw_b is not None else None,
-                                         L.ptr(_f32c(scale)), L.ptr(_f32c(shift)), L.ptr(y), B, C, Ln, eps, L.stream(x))
-    L.count_launches(1)
-    L.check(rc, "lina_codec_dwconv_adaln")
+    lib = L.lib()
+    sc, sh = _f32c(scale), _f32c(shift)
+    if sc.data_ptr() % 16 or sh.data_ptr() % 16:          # rows of an embedding table: the apply kernel reads them as float4
+        sc, sh = sc.clone(), sh.clone()
+    ws = torch.empty(int(lib.lina_codec_dwconv_adaln_workspace_bytes(B, C, Ln)), dtype=torch.uint8, device=x.device)
+    rc = lib.lina_codec_dwconv_adaln_ws(L.ptr(x), L.ptr(w), L.ptr(_f32c(dw_b)) if dw_b is not None else None,
+                                        L.ptr(sc), L.ptr(sh), L.ptr(y), L.ptr(ws), B, C, Ln, eps, L.stream(x))
+    L.count_launches(2)
+    L.check(rc, "lina_codec_dwconv_adaln_ws")
     return y
 
 

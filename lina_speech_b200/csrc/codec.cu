@@ -131,14 +131,19 @@ groupnorm_swish_reg_kernel(const float *__restrict__ x, const float *__restrict_
     for (int i = 0; i < PER; ++i) {
         const int j = threadIdx.x + i * NT;
         if (j < n4) {
-            // the 4 elements of a float4 may straddle a channel boundary only if L % 4 != 0: resolve per element
+            // one division per float4; its 4 elements straddle a channel boundary only when L % 4 != 0
             const int e0 = j * 4;
+            const int cl = e0 / L, rem = e0 - cl * L;
+            const int c0 = g * cpg + cl;
+            const int c1 = min(c0 + 1, C - 1);
+            const float ga0 = gamma[c0] * rstd, be0 = beta[c0] - mean * ga0;       // (x - mean) rstd gamma + beta = x A + B
+            const float ga1 = gamma[c1] * rstd, be1 = beta[c1] - mean * ga1;
             float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int c = g * cpg + (e0 + q) / L;
-                float t = (o[q] - mean) * rstd * gamma[c] + beta[c];
-                if (swish) t = t * sigmoidf_(t);
+                const bool nxt = rem + q >= L;
+                float t = fmaf(o[q], nxt ? ga1 : ga0, nxt ? be1 : be0);
+                if (swish) t = __fdividef(t, 1.f + __expf(-t));
                 o[q] = t;
             }
             yp[j] = make_float4(o[0], o[1], o[2], o[3]);
@@ -217,6 +222,134 @@ dwconv_adaln_kernel(const float *__restrict__ x, const float *__restrict__ dw_w,
         const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
         float *yr = y + ((size_t)b * L + l) * C;
         for (int c = lane; c < C; c += 32) yr[c] = (row[c] - mean) * rstd * scale[c] + shift[c];
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Two-kernel form of dwconv + transpose + (Ada)LayerNorm (the production path; the single-kernel version above needs all C
+// channels of a time tile in one CTA -> 205 KB of shared memory, one CTA per SM, phases serialised: 0.15 of the copy rate).
+//   A: CTA = (b, 64 channels, 64 time steps): coalesced row loads (+-3 halo), 7-tap conv out of shared memory, transposed
+//      store of the UN-normalised tile into y[b, l, c0..c0+63], per-row partial statistics (count, mean, M2 of the 64
+//      channels) into ws[b, l, cblk, 2]  (35 KB smem, 6 CTAs per SM);
+//   B: one warp per (b, l) row: Chan-merges the partials in a fixed order (deterministic, no cancellation), normalises the
+//      row in place with float4 accesses.  The intermediate (73.7 MB at the shipped size) mostly lives in the 126 MB L2.
+constexpr int DT_C = 64, DT_L = 64;
+template <bool CONV>
+__global__ void __launch_bounds__(256)
+dwconv_t_stats_kernel(const float *__restrict__ x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
+                      float *__restrict__ y, float *__restrict__ ws, int C, int L, int nblk) {
+    __shared__ float ins[DT_C][DT_L + 9];                 // x[c][l0-3 .. l0+DT_L+3]  (CONV) or x[c][l0 .. l0+DT_L); odd stride: no bank conflicts
+    __shared__ float outs[DT_L][DT_C + 1];                // conv output, transposed
+    const int b = blockIdx.z, c0 = blockIdx.y * DT_C, l0 = blockIdx.x * DT_L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int HALO = CONV ? 3 : 0, ROW = DT_L + 2 * HALO;
+    const float *xb = x + ((size_t)b * C + c0) * L;
+    {   // every warp loads 8 channel rows; all its loads are issued before the first shared store
+        float v[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = warp + u * 8;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = lane + k * 32, l = l0 - HALO + i;
+                v[u][k] = (i < ROW && c0 + c < C && l >= 0 && l < L) ? xb[(size_t)c * L + l] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = lane + k * 32;
+                if (i < ROW) ins[warp + u * 8][i] = v[u][k];
+            }
+    }
+    __syncthreads();
+    {   // thread = channel (tid & 63) x 16 consecutive time steps, sliding 7-tap window (a warp = 32 channels, one time block)
+        const int c = tid & 63, lb = (tid >> 6) * 16;
+        if (CONV) {
+            float w[7], bias = 0.f;
+            const bool cok = c0 + c < C;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) w[j] = cok ? dw_w[(size_t)(c0 + c) * 7 + j] : 0.f;
+            if (cok && dw_b != nullptr) bias = dw_b[c0 + c];
+            float win[22];
+#pragma unroll
+            for (int i = 0; i < 22; ++i) win[i] = ins[c][lb + i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float acc = bias;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc = fmaf(w[j], win[i + j], acc);
+                outs[lb + i][c] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) outs[lb + i][c] = ins[c][lb + i];
+        }
+    }
+    __syncthreads();
+    const int nc = min(DT_C, C - c0);
+    for (int r = warp; r < DT_L; r += 8) {               // one warp per time step: partial stats + transposed store
+        const int l = l0 + r;
+        if (l >= L) break;
+        const float a0 = lane < nc ? outs[r][lane] : 0.f, a1 = lane + 32 < nc ? outs[r][lane + 32] : 0.f;
+        const float mean = warp_sum(a0 + a1) / (float)nc;
+        const float d0 = lane < nc ? a0 - mean : 0.f, d1 = lane + 32 < nc ? a1 - mean : 0.f;
+        const float m2 = warp_sum(d0 * d0 + d1 * d1);
+        float *yr = y + ((size_t)b * L + l) * C + c0;
+        if (lane < nc) yr[lane] = a0;
+        if (lane + 32 < nc) yr[lane + 32] = a1;
+        if (lane == 0) {
+            float *w2 = ws + (((size_t)b * L + l) * nblk + blockIdx.y) * 2;
+            w2[0] = mean; w2[1] = m2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adaln_apply_kernel(float *__restrict__ y, const float *__restrict__ ws, const float *__restrict__ scale,
+                   const float *__restrict__ shift, long long rows, int C, int nblk, float eps) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    // Chan merge of the per-block (mean, M2) partials, fixed order
+    float mean = 0.f, m2 = 0.f, n = 0.f;
+    for (int p = 0; p < nblk; ++p) {
+        const float np = (float)min(DT_C, C - p * DT_C);
+        const float mp = ws[((size_t)row * nblk + p) * 2], m2p = ws[((size_t)row * nblk + p) * 2 + 1];
+        const float nt = n + np, delta = mp - mean;
+        mean += delta * (np / nt);
+        m2 += m2p + delta * delta * (n * np / nt);
+        n = nt;
+    }
+    const float rstd = rsqrtf(m2 / (float)C + eps);
+    float *yr = y + (size_t)row * C;
+    if (C % 4 == 0 && ((uintptr_t)y % 16 == 0)) {
+        const int n4 = C / 4;
+        for (int j0 = 0; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 32 + lane;
+                if (j < n4) v[u] = reinterpret_cast<const float4 *>(yr)[j];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 32 + lane;
+                if (j < n4) {
+                    const float4 sc = reinterpret_cast<const float4 *>(scale)[j], sh = reinterpret_cast<const float4 *>(shift)[j];
+                    float4 o;
+                    o.x = (v[u].x - mean) * rstd * sc.x + sh.x;
+                    o.y = (v[u].y - mean) * rstd * sc.y + sh.y;
+                    o.z = (v[u].z - mean) * rstd * sc.z + sh.z;
+                    o.w = (v[u].w - mean) * rstd * sc.w + sh.w;
+                    reinterpret_cast<float4 *>(yr)[j] = o;
+                }
+            }
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) yr[c] = (yr[c] - mean) * rstd * scale[c] + shift[c];
     }
 }
 
@@ -462,6 +595,38 @@ static int launch_dwconv_adaln(const float *x, const float *dw_w, const float *d
     else dwconv_adaln_kernel<false><<<grid, DW_THREADS, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
     LINA_LAUNCH_OK("dwconv_adaln_kernel");
     return LINA_OK;
+}
+
+static int launch_dwconv_adaln_ws(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                                  const float *shift, float *y, float *ws, int B, int C, int L, float eps, cudaStream_t st) {
+    LINA_REQUIRE(x && scale && shift && y && ws, LINA_ERR_BAD_ARG, "dwconv_adaln: null pointer");
+    LINA_REQUIRE(B > 0 && C > 0 && L > 0, LINA_ERR_BAD_ARG, "dwconv_adaln: bad size");
+    const int nblk = (C + DT_C - 1) / DT_C;
+    LINA_REQUIRE(B <= 65535 && nblk <= 65535, LINA_ERR_UNSUPPORTED, "dwconv_adaln: grid too large");
+    LINA_REQUIRE((uintptr_t)scale % 16 == 0 && (uintptr_t)shift % 16 == 0, LINA_ERR_UNSUPPORTED, "dwconv_adaln: scale / shift alignment");
+    dim3 grid((L + DT_L - 1) / DT_L, nblk, B);
+    if (dw_w != nullptr) dwconv_t_stats_kernel<true><<<grid, 256, 0, st>>>(x, dw_w, dw_b, y, ws, C, L, nblk);
+    else dwconv_t_stats_kernel<false><<<grid, 256, 0, st>>>(x, dw_w, dw_b, y, ws, C, L, nblk);
+    LINA_LAUNCH_OK("dwconv_t_stats_kernel");
+    const long long rows = (long long)B * L;
+    adaln_apply_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(y, ws, scale, shift, rows, C, nblk, eps);
+    LINA_LAUNCH_OK("adaln_apply_kernel");
+    return LINA_OK;
+}
+
+extern "C" size_t lina_codec_dwconv_adaln_workspace_bytes(int B, int C, int L) {
+    return (size_t)B * L * ((C + DT_C - 1) / DT_C) * 2 * sizeof(float);
+}
+
+extern "C" int lina_codec_dwconv_adaln_ws(const float *x, const float *dw_w, const float *dw_b, const float *scale,
+                                          const float *shift, float *y, float *ws, int B, int C, int L, float eps,
+                                          void *stream) {
+    return launch_dwconv_adaln_ws(x, dw_w, dw_b, scale, shift, y, ws, B, C, L, eps, (cudaStream_t)stream);
+}
+
+extern "C" int lina_codec_layernorm_t_ws(const float *x, const float *gamma, const float *beta, float *y, float *ws, int B,
+                                         int C, int L, float eps, void *stream) {
+    return launch_dwconv_adaln_ws(x, nullptr, nullptr, gamma, beta, y, ws, B, C, L, eps, (cudaStream_t)stream);
 }
 
 extern "C" int lina_codec_dwconv_adaln(const float *x, const float *dw_w, const float *dw_b, const float *scale,

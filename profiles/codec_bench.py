@@ -58,8 +58,11 @@ def check(rc):
 
 
 report("groupnorm_swish", timeit(lambda: check(lib.lina_codec_groupnorm_swish(L.ptr(x), L.ptr(gam), L.ptr(bet), L.ptr(y), None, B, C, Ln, G, 1e-6, 1, st()))), 2 * nb)
-report("dwconv_adaln (dwconv7 + transpose + AdaLN)", timeit(lambda: check(lib.lina_codec_dwconv_adaln(L.ptr(x), L.ptr(dww), L.ptr(dwb), L.ptr(gam), L.ptr(bet), L.ptr(yt), B, C, Ln, 1e-6, st()))), 2 * nb)
-report("layernorm_t (transpose + LayerNorm)", timeit(lambda: check(lib.lina_codec_layernorm_t(L.ptr(x), L.ptr(gam), L.ptr(bet), L.ptr(yt), B, C, Ln, 1e-6, st()))), 2 * nb)
+wsb = torch.empty(int(lib.lina_codec_dwconv_adaln_workspace_bytes(B, C, Ln)), dtype=torch.uint8, device=dev)
+report("dwconv_adaln_ws (2 kernels: conv+T+stats, apply)", timeit(lambda: check(lib.lina_codec_dwconv_adaln_ws(L.ptr(x), L.ptr(dww), L.ptr(dwb), L.ptr(gam), L.ptr(bet), L.ptr(yt), L.ptr(wsb), B, C, Ln, 1e-6, st()))), 2 * nb)
+report("layernorm_t_ws (2 kernels)", timeit(lambda: check(lib.lina_codec_layernorm_t_ws(L.ptr(x), L.ptr(gam), L.ptr(bet), L.ptr(yt), L.ptr(wsb), B, C, Ln, 1e-6, st()))), 2 * nb)
+report("dwconv_adaln (round-1 single kernel)", timeit(lambda: check(lib.lina_codec_dwconv_adaln(L.ptr(x), L.ptr(dww), L.ptr(dwb), L.ptr(gam), L.ptr(bet), L.ptr(yt), B, C, Ln, 1e-6, st()))), 2 * nb)
+report("layernorm_t (round-1 single kernel)", timeit(lambda: check(lib.lina_codec_layernorm_t(L.ptr(x), L.ptr(gam), L.ptr(bet), L.ptr(yt), B, C, Ln, 1e-6, st()))), 2 * nb)
 report("scale_residual_t", timeit(lambda: check(lib.lina_codec_scale_residual_t(L.ptr(ht), L.ptr(gam), L.ptr(x), L.ptr(y), B, C, Ln, st()))), 3 * nb)
 hh = torch.randn(B, Ln, NFFT + 2, device=dev) * 0.5
 win = torch.hann_window(NFFT, device=dev)
