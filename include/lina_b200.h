@@ -285,6 +285,9 @@ int lina_debug_umma_timing(long long *out, int N, int a_tmem, int a_mn, int b_mn
 int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
                                int H, int T, int K, int V, float scale, long long *trace, void *stream);
 
+int lina_debug_gla_pregated_trace(const void *qg, const void *kg, const void *v, const float *decay, void *o, int B,
+                                  int H, int T, int K, int V, long long *trace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

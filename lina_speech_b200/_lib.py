@@ -67,6 +67,7 @@ PROTOTYPES = {
     "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
     "lina_debug_umma_timing": (_i, [_p] + [_i] * 6 + [_p]),
     "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
+    "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -246,8 +246,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         }
       }
     } else if (warp == 19) {
-        // ====================== TMA loader (one thread): q, k -> operand tile of the stage, gk -> side tile, v ======================
-        if (lane == 0) {
+        // ====================== TMA loader (one elected thread): q, k -> operand tile of the stage, gk -> side tile, v ======================
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.v);
             if (!PRE) tma_prefetch_desc(&tm.g);
             for (int n = 0; n < n_items; ++n) {
@@ -278,25 +278,35 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         }
         __syncwarp();
     } else if (warp == 18) {
-        // ====================== MMA issuer (one thread) ======================
-        if (lane == 0) {
+        // ====================== MMA issuer (one elected thread) ======================
+        if (elect_one_sync()) {
             const uint32_t id_p = idesc_bf16(128, 64, 0, 0);     // (0),(1): K-major x K-major, N = 64
             const uint32_t id_o = idesc_bf16(128, 64, 1, 0);     // (2): MN-major A (v^T), K-major B (P)
             const uint32_t id_s = idesc_bf16(128, K, 1, 1);      // (3): MN-major A (v^T), MN-major B (k~)
             const uint32_t p_tile = smem_u32(smem + cfg::OFF_P);
             const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
+            // Descriptors are built ONCE; inside the loops only a compile-time constant is added to their 14-bit
+            // (address >> 4) field (all operand addresses are < 256 KB, so the field never carries).  Rebuilding them per
+            // instruction cost ~10 dependent uniform-datapath ops per MMA, and the single issuing thread is the kernel's
+            // critical resource (40 MMAs per 64-token item).
+            const uint32_t qk0 = smem_u32(smem + cfg::OFF_QK);
+            const uint64_t d_q[2] = {smem_desc_sw128(qk0, 0, 1024), smem_desc_sw128(qk0 + cfg::QK_BYTES, 0, 1024)};
+            const uint64_t d_k[2] = {smem_desc_sw128(qk0 + 8192, 0, 1024), smem_desc_sw128(qk0 + cfg::QK_BYTES + 8192, 0, 1024)};
+            const uint64_t d_k3[2] = {smem_desc_sw128(qk0 + 8192, cfg::QK_BLK, 1024),
+                                      smem_desc_sw128(qk0 + cfg::QK_BYTES + 8192, cfg::QK_BLK, 1024)};
+            const uint64_t d_v = smem_desc_sw128(v_tile, 8192, 1024), d_p = smem_desc_sw128(p_tile, 0, 1024);
             for (int n = 0; n < n_items; ++n) {
                 const int s = n & 1;
-                const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
+                const uint64_t dq = d_q[s], dk = d_k[s], dk3 = d_k3[s];
                 wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
                 TRACE(2, n, 0);
                 // (0) P = [q~;k~] k~^T
-#pragma unroll 4
+#pragma unroll
                 for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint32_t a = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
-                    mma_ss(tmem + COL_P, smem_desc_sw128(a, 0, 1024), smem_desc_sw128(a + 8192, 0, 1024), id_p, ks > 0);
+                    const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
+                    mma_ss(tmem + COL_P, dq + off, dk + off, id_p, ks > 0);
                 }
                 mma_commit(&bars[B_P_FULL]);
                 wait_bar(&bars[B_SA_FULL], n & 1);
@@ -304,10 +314,10 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 tc_fence_after();
                 TRACE(2, n, 1);
                 // (1) OT = SA q~^T   (A from TMEM)
-#pragma unroll 4
+#pragma unroll
                 for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint32_t b = qk_tile + (ks >> 2) * cfg::QK_BLK + (ks & 3) * 32;
-                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, smem_desc_sw128(b, 0, 1024), id_p, ks > 0);
+                    const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
+                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, dq + off, id_p, ks > 0);
                 }
                 wait_bar(&bars[B_PS_FULL], n & 1);
                 wait_bar(&bars[B_V_FULL], n & 1);
@@ -316,15 +326,13 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 // (2) OT += v^T P^T
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks)
-                    mma_ss(tmem + COL_OT, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
-                           smem_desc_sw128(p_tile + ks * 32, 0, 1024), id_o, 1);
+                    mma_ss(tmem + COL_OT, d_v + (uint64_t)(ks * 128), d_p + (uint64_t)(ks * 2), id_o, 1);
                 mma_commit(&bars[B_O_FULL]);
                 mma_commit(&bars[B_PS_EMPTY]);
                 // (3) ST += v^T k~
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks)
-                    mma_ss(tmem + COL_ST, smem_desc_sw128(v_tile + ks * 2048, 8192, 1024),
-                           smem_desc_sw128(qk_tile + 8192 + ks * 2048, cfg::QK_BLK, 1024), id_s, 1);
+                    mma_ss(tmem + COL_ST, d_v + (uint64_t)(ks * 128), dk3 + (uint64_t)(ks * 128), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY]);
@@ -658,4 +666,11 @@ extern "C" int lina_debug_gla_chunk_trace(const void *q, const void *k, const vo
                                           int H, int T, int K, int V, float scale, long long *trace, void *stream) {
     LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16) && K == 256, LINA_ERR_UNSUPPORTED, "trace: K=256 bf16 only");
     return launch<256>(q, k, v, gk, nullptr, 0, o, nullptr, B, H, T, V, 0, scale, (cudaStream_t)stream, trace);
+}
+
+// same for the pre-gated variant (two state warpgroups): operands as for lina_gla_chunk_fwd_pregated_bthd
+extern "C" int lina_debug_gla_pregated_trace(const void *qg, const void *kg, const void *v, const float *decay, void *o, int B,
+                                             int H, int T, int K, int V, long long *trace, void *stream) {
+    LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16) && K == 256, LINA_ERR_UNSUPPORTED, "trace: K=256 bf16 only");
+    return launch<256, 36>(qg, kg, v, qg, nullptr, 0, o, nullptr, B, H, T, V, 1, 1.f, (cudaStream_t)stream, trace, decay);
 }

@@ -200,6 +200,7 @@ extern "C" int lina_debug_umma_probe_sw128(const float *A, const float *B, float
 // ---- third probe: cycles per tcgen05.mma for the shapes the GLA kernel issues (SW128 operands; data = garbage) ----
 namespace {
 
+template <bool ELECT>
 __global__ void __launch_bounds__(128)
 umma_timing_kernel(long long *__restrict__ out, int N, int a_tmem, int a_mn, int b_mn, int nmma, int same_d) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -214,7 +215,11 @@ umma_timing_kernel(long long *__restrict__ out, int N, int a_tmem, int a_mn, int
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base_s;
-    if (tid == 0) {
+    // elect != 0: the issuing thread is chosen with elect.sync (ptxas then emits bare UTCHMMAs); elect == 0: `tid == 0`, under
+    // which every MMA is wrapped in an elect / vote loop -- the ~97-cycle "issue cost" of round 1 was this loop
+    bool issuer = tid == 0;
+    if (ELECT) issuer = warp == 0 ? elect_one_sync() : false;      // compile-time choice: the region below is provably single-threaded
+    if (issuer) {
         const uint32_t idesc = idesc_bf16(128, N, a_mn, b_mn);
         const uint32_t a_tile = smem_u32(smem), b_tile = smem_u32(smem + 64 * 1024);
         const uint64_t ad0 = a_mn ? smem_desc_sw128(a_tile, 8192, 1024) : smem_desc_sw128(a_tile, 0, 1024);
@@ -251,8 +256,10 @@ extern "C" int lina_debug_umma_timing(long long *out, int N, int a_tmem, int a_m
                                       void *stream) {
     LINA_REQUIRE(out && N % 16 == 0 && N >= 16 && N <= 256 && nmma > 0 && nmma <= 4096, LINA_ERR_BAD_ARG, "umma_timing: bad argument");
     const int smem = 160 * 1024;
-    LINA_CUDA_OK(cudaFuncSetAttribute(umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, N, a_tmem, a_mn, b_mn, nmma, same_d);
+    LINA_CUDA_OK(cudaFuncSetAttribute(umma_timing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LINA_CUDA_OK(cudaFuncSetAttribute(umma_timing_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if ((same_d >> 1) & 1) umma_timing_kernel<true><<<1, 128, smem, (cudaStream_t)stream>>>(out, N, a_tmem, a_mn, b_mn, nmma, same_d & 1);
+    else umma_timing_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(out, N, a_tmem, a_mn, b_mn, nmma, same_d & 1);
     LINA_LAUNCH_OK("umma_timing_kernel");
     return LINA_OK;
 }
