@@ -72,15 +72,16 @@ template <int K> struct Cfg {
     static constexpr uint32_t OFF_DVEC = OFF_P + PT_BYTES;            // [3][K] fp32
     static constexpr uint32_t OFF_PART = OFF_DVEC + 3 * K * 4;        // [NRG-1][K] fp32
     static constexpr uint32_t OFF_BAR = OFF_PART + (NRG - 1) * K * 4; // mbarriers
-    static constexpr uint32_t SMEM = OFF_BAR + 24 * 8 + 16;
+    static constexpr uint32_t SMEM = OFF_BAR + 32 * 8 + 16;
     static constexpr uint32_t RAW_TX = 3u * K * C * 2u;               // bytes landed per stage by TMA (q, k, gk)
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(OFF_G % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
-enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_EMPTY,
-       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_SA_FULL, B_RAW_FULL0, B_RAW_FULL1, B_G_EMPTY0, B_G_EMPTY1, B_V_FULL,
-       B_V_EMPTY, B_COUNT };
+enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_QK_EMPTY2, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_EMPTY,
+       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_RAW_FULL0, B_RAW_FULL1, B_RAW_FULL2, B_G_EMPTY0, B_G_EMPTY1, B_V_FULL0, B_V_FULL1,
+       B_V_EMPTY0, B_V_EMPTY1, B_SA_BLK0 /* .. B_SA_BLK0 + K/32 - 1: one per 32-column block of the state */, B_COUNT = B_SA_BLK0 + 8 };
+static_assert(B_COUNT <= 32, "mbarrier slots");
 
 // mbarrier wait that traps instead of hanging forever (a protocol bug must not wedge the GPU)
 __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
@@ -106,8 +107,6 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
 
 struct TMaps { CUtensorMap q, k, g, v; };
 
-// OPT bit 0: state pass reads ST 16 columns at a time, double-buffered (the tcgen05.ld of block c+1 is in flight while
-//            block c is rescaled and stored) instead of ld32 -> wait -> compute -> store per block;
 // OPT bit 1: the gate pre-pass keeps its gk rows in registers between the column-sum pass and the rescale pass
 //            (8 fewer 16-byte shared loads per thread and item).
 // OPT bit 2 (PRE): the operands arrive PRE-GATED -- tm.q / tm.k map q~ = scale q e^G and k~ = k e^-G (written by
@@ -123,16 +122,28 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     //            the key dim: decay is [B,H,NT,V].  This is the form the backward needs (contraction over V, state S^T).
     // OPT bit 4 (OUT32): o is written as fp32 (the backward's dq~ / dk~ partial sums feed a cumsum).
     constexpr bool ROW = (OPT & 8) != 0, OUT32 = (OPT & 16) != 0;
-    // OPT bit 5 (STATE2, with PRE): the idle pre-pass warps 0-3 take the upper half of the state columns in the state pass
-    //            (a warp may touch TMEM lanes 32*(warp%4)..+31 only, so warps 0-3 mirror warps 12-15 lane for lane).
+    // OPT bit 5 (STATE2, with PRE): the idle pre-pass warps 0-3 and 4-7 join warps 12-15 in the state pass (a warp may touch
+    //            TMEM lanes 32*(warp%4)..+31 only, so they mirror warps 12-15 lane for lane).  The state is handled in
+    //            32-column blocks, block b by group b % NG, each block with its own mbarrier so that the q~ S MMA of the
+    //            next item starts on block 0 while the later blocks are still being rescaled.
     constexpr bool STATE2 = (OPT & 32) != 0;
-    static_assert(!STATE2 || PRE, "the second state-pass warpgroup are the pre-pass warps");
+    static_assert(!STATE2 || PRE, "the extra state-pass warpgroups are the pre-pass warps");
+    constexpr int NB = K / 32;
+    constexpr int NG = STATE2 ? (NB >= 3 ? 3 : NB) : 1;
     static_assert(!ROW || PRE, "row decay needs pre-gated operands");
     using cfg = Cfg<K>;
+    // With pre-gated operands the gk side tiles (2 * G_BYTES = QK_BYTES) are unused: they hold EITHER a second v stage (default)
+    // OR a third q~/k~ stage (QK3).  Measured at the bench shape: 2+2 stages 3182 cycles per item, 3+1 stages 3381 (the
+    // loader is one thread: with one v stage it sits in the V_EMPTY wait and cannot run ahead on q~/k~ anyway).
+    constexpr bool QK3 = false;
+    constexpr int NS = (PRE && QK3) ? 3 : 2;
+    constexpr bool V2 = PRE && !QK3;
+    static_assert(2 * cfg::G_BYTES == cfg::QK_BYTES, "third stage lives in the gk tiles");
+    constexpr uint32_t V_STAGE1 = V2 ? cfg::OFF_G : cfg::OFF_V;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cfg::OFF_BAR);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + cfg::OFF_BAR + 24 * 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + cfg::OFF_BAR + 32 * 8);
     float *dvec = reinterpret_cast<float *>(smem + cfg::OFF_DVEC);
     float *part = reinterpret_cast<float *>(smem + cfg::OFF_PART);
 
@@ -147,14 +158,16 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
         mbar_init(&bars[B_QK_FULL0], NPREP); mbar_init(&bars[B_QK_FULL1], NPREP);
-        mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1);
+        mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1); mbar_init(&bars[B_QK_EMPTY2], 1);
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
         mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
-        mbar_init(&bars[B_ST_FULL], 1); mbar_init(&bars[B_SA_FULL], STATE2 ? 256 : 128);
-        mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1);
+        mbar_init(&bars[B_ST_FULL], 1);
+        for (int b = 0; b < NB; ++b) mbar_init(&bars[B_SA_BLK0 + b], 128);
+        mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1); mbar_init(&bars[B_RAW_FULL2], 1);
         mbar_init(&bars[B_G_EMPTY0], NPREP); mbar_init(&bars[B_G_EMPTY1], NPREP);
-        mbar_init(&bars[B_V_FULL], 1); mbar_init(&bars[B_V_EMPTY], 1);
+        mbar_init(&bars[B_V_FULL0], 1); mbar_init(&bars[B_V_EMPTY0], 1);
+        mbar_init(&bars[B_V_FULL1], 1); mbar_init(&bars[B_V_EMPTY1], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -163,8 +176,14 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const bool st2 = STATE2 && warp < 4;
-    if (warp < 8 && !st2) {
+    auto qk_stage_off = [](int st) -> uint32_t { return st < 2 ? cfg::OFF_QK + st * cfg::QK_BYTES : cfg::OFF_G; };
+    // chunk-decay ring: NS + 1 slots (the loader runs NS items ahead of the state pass); the 4th lives in the unused `part`
+    auto dvec_slot = [&](int n) -> float * { const int sl = n % (NS + 1); return sl < 3 ? dvec + sl * K : part; };
+    int sg = -1;                                   // state-pass group of this warp
+    if (warp >= 12 && warp < 16) sg = 0;
+    else if (NG > 1 && warp < 4) sg = 1;
+    else if (NG > 2 && warp >= 4 && warp < 8) sg = 2;
+    if (warp < 8 && sg < 0) {
       if (!PRE) {
         // ====================== warps 0-7: gate pre-pass, in place on the landed q / k rows ======================
         const int p = tid;                         // 0..255
@@ -210,7 +229,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             named_sync(1, NPREP);                  // `part` may be rewritten by the next item from here on
             if (rg == NRG - 1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dvec[(n % 3) * K + c * 8 + j] = __expf(G[j] + csum[j]);
+                for (int j = 0; j < 8; ++j) dvec_slot(n)[c * 8 + j] = __expf(G[j] + csum[j]);
             }
             // from here on G is kept in log2 units so every exponential is a single ex2
 #pragma unroll
@@ -251,15 +270,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.v);
             if (!PRE) tma_prefetch_desc(&tm.g);
             for (int n = 0; n < n_items; ++n) {
-                const int s = n & 1, t0 = n * C;
-                const uint32_t qk_tile = smem_u32(smem + cfg::OFF_QK + s * cfg::QK_BYTES);
+                const int s = n % NS, u = n / NS, t0 = n * C;
+                const uint32_t qk_tile = smem_u32(smem + qk_stage_off(s));
                 const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
-                wait_bar(&bars[B_QK_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
-                if (!PRE) wait_bar(&bars[B_G_EMPTY0 + s], ((n >> 1) & 1) ^ 1);
+                wait_bar(&bars[B_QK_EMPTY0 + s], (u & 1) ^ 1);
+                if (!PRE) wait_bar(&bars[B_G_EMPTY0 + s], (u & 1) ^ 1);
                 TRACE(1, n, 0);
                 mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + (ROW ? 0u : K * 4u)) : cfg::RAW_TX);
                 if (PRE && !ROW)   // dvec ring slot n % 3 <- decay[b, h, n, :]  (safe: the loader runs at most 2 items ahead)
-                    tma_load_1d(smem_u32(dvec + (n % 3) * K), decay + ((size_t)bh * n_items + n) * K, K * 4u,
+                    tma_load_1d(smem_u32(dvec_slot(n)), decay + ((size_t)bh * n_items + n) * K, K * 4u,
                                 &bars[B_RAW_FULL0 + s]);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
@@ -268,11 +287,12 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                 }
                 TRACE(1, n, 1);
-                wait_bar(&bars[B_V_EMPTY], (n & 1) ^ 1);
-                mbar_expect_tx(&bars[B_V_FULL], VT_BYTES);
-                const uint32_t v_tile = smem_u32(smem + cfg::OFF_V);
-                tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL]);
-                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL]);
+                const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;         // v stage and its use count
+                wait_bar(&bars[B_V_EMPTY0 + sv], (uv & 1) ^ 1);
+                mbar_expect_tx(&bars[B_V_FULL0 + sv], VT_BYTES);
+                const uint32_t v_tile = smem_u32(smem + (sv ? V_STAGE1 : cfg::OFF_V));
+                tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL0 + sv]);
+                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL0 + sv]);
                 TRACE(1, n, 2);
             }
         }
@@ -290,15 +310,21 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             // instruction cost ~10 dependent uniform-datapath ops per MMA, and the single issuing thread is the kernel's
             // critical resource (40 MMAs per 64-token item).
             const uint32_t qk0 = smem_u32(smem + cfg::OFF_QK);
-            const uint64_t d_q[2] = {smem_desc_sw128(qk0, 0, 1024), smem_desc_sw128(qk0 + cfg::QK_BYTES, 0, 1024)};
-            const uint64_t d_k[2] = {smem_desc_sw128(qk0 + 8192, 0, 1024), smem_desc_sw128(qk0 + cfg::QK_BYTES + 8192, 0, 1024)};
-            const uint64_t d_k3[2] = {smem_desc_sw128(qk0 + 8192, cfg::QK_BLK, 1024),
-                                      smem_desc_sw128(qk0 + cfg::QK_BYTES + 8192, cfg::QK_BLK, 1024)};
-            const uint64_t d_v = smem_desc_sw128(v_tile, 8192, 1024), d_p = smem_desc_sw128(p_tile, 0, 1024);
+            const uint32_t qk1 = qk0 + cfg::QK_BYTES, qk2 = smem_u32(smem + cfg::OFF_G);
+            const uint64_t d_q0 = smem_desc_sw128(qk0, 0, 1024), d_q1 = smem_desc_sw128(qk1, 0, 1024), d_q2 = smem_desc_sw128(qk2, 0, 1024);
+            const uint64_t d_k0 = smem_desc_sw128(qk0 + 8192, 0, 1024), d_k1 = smem_desc_sw128(qk1 + 8192, 0, 1024),
+                           d_k2 = smem_desc_sw128(qk2 + 8192, 0, 1024);
+            const uint64_t d_k30 = smem_desc_sw128(qk0 + 8192, cfg::QK_BLK, 1024), d_k31 = smem_desc_sw128(qk1 + 8192, cfg::QK_BLK, 1024),
+                           d_k32 = smem_desc_sw128(qk2 + 8192, cfg::QK_BLK, 1024);
+            const uint64_t d_v0 = smem_desc_sw128(v_tile, 8192, 1024), d_v1 = smem_desc_sw128(smem_u32(smem + V_STAGE1), 8192, 1024);
+            const uint64_t d_p = smem_desc_sw128(p_tile, 0, 1024);
             for (int n = 0; n < n_items; ++n) {
-                const int s = n & 1;
-                const uint64_t dq = d_q[s], dk = d_k[s], dk3 = d_k3[s];
-                wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);
+                const int s = n % NS, u = n / NS;
+                const uint64_t dq = s == 0 ? d_q0 : (s == 1 ? d_q1 : d_q2), dk = s == 0 ? d_k0 : (s == 1 ? d_k1 : d_k2);
+                const uint64_t dk3 = s == 0 ? d_k30 : (s == 1 ? d_k31 : d_k32);
+                const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;
+                const uint64_t d_v = sv ? d_v1 : d_v0;
+                wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], u & 1);
                 wait_bar(&bars[B_P_TEMPTY], (n & 1) ^ 1);
                 tc_fence_after();
                 TRACE(2, n, 0);
@@ -309,18 +335,21 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     mma_ss(tmem + COL_P, dq + off, dk + off, id_p, ks > 0);
                 }
                 mma_commit(&bars[B_P_FULL]);
-                wait_bar(&bars[B_SA_FULL], n & 1);
                 wait_bar(&bars[B_O_EMPTY], (n & 1) ^ 1);
-                tc_fence_after();
-                TRACE(2, n, 1);
-                // (1) OT = SA q~^T   (A from TMEM)
+                // (1) OT = SA q~^T   (A from TMEM), two k-steps per 32-column block of the state as the blocks become ready
 #pragma unroll
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
-                    mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, dq + off, id_p, ks > 0);
+                for (int cb = 0; cb < NB; ++cb) {
+                    wait_bar(&bars[B_SA_BLK0 + cb], n & 1);
+                    tc_fence_after();
+                    if (cb == 0) TRACE(2, n, 1);
+#pragma unroll
+                    for (int ks = 2 * cb; ks < 2 * cb + 2; ++ks) {
+                        const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
+                        mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, dq + off, id_p, ks > 0);
+                    }
                 }
                 wait_bar(&bars[B_PS_FULL], n & 1);
-                wait_bar(&bars[B_V_FULL], n & 1);
+                wait_bar(&bars[B_V_FULL0 + sv], uv & 1);
                 tc_fence_after();
                 TRACE(2, n, 2);
                 // (2) OT += v^T P^T
@@ -335,7 +364,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     mma_ss(tmem + COL_ST, d_v + (uint64_t)(ks * 128), dk3 + (uint64_t)(ks * 128), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
                 mma_commit(&bars[B_QK_EMPTY0 + s]);
-                mma_commit(&bars[B_V_EMPTY]);
+                mma_commit(&bars[B_V_EMPTY0 + sv]);
                 TRACE(2, n, 3);
             }
         }
@@ -409,15 +438,14 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             }
             if (r == 0) TRACE(4, n, 1);
         }
-    } else if ((warp >= 12 && warp < 16) || st2) {
-        // ====================== warps 12-15 (+ 0-3 with STATE2): state pass ======================
-        const int qd = st2 ? warp : warp - 12, r = qd * 32 + lane;
-        const int cb_lo = st2 ? K / 64 : 0, cb_hi = (STATE2 && !st2) ? K / 64 : K / 32;   // 32-column blocks of this group
+    } else if (sg >= 0) {
+        // ====================== state pass: warps 12-15 (+ 0-3, 4-7 with STATE2), 32-column block b by group b % NG ======================
+        const int qd = warp & 3, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         const size_t sbase = (size_t)bh * K * V + v0 + r;          // + kappa * V
         // initial state -> ST (fp32) and SA (bf16)
 #pragma unroll 1
-        for (int cb = cb_lo; cb < cb_hi; ++cb) {
+        for (int cb = sg; cb < NB; cb += NG) {
             uint32_t f[32], pk[16];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -431,53 +459,19 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars[B_SA_FULL]);
+        for (int cb = sg; cb < NB; cb += NG) mbar_arrive(&bars[B_SA_BLK0 + cb]);
         for (int n = 0; n < n_items; ++n) {
-            const int s = n & 1;
-            wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], (n >> 1) & 1);   // dvec of this item is published with it
+            const int s = n % NS, u = n / NS;
+            wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], u & 1);   // dvec of this item is published with it
             wait_bar(&bars[B_ST_FULL], n & 1);
             tc_fence_after();
-            if (r == 0 && !st2) TRACE(5, n, 0);
-            const float *dv = dvec + (n % 3) * K;
+            if (r == 0 && sg == 0) TRACE(5, n, 0);
+            const float *dv = dvec_slot(n);
             const bool last = n == n_items - 1;
             float rd = 1.f;
             if (ROW) rd = decay[((size_t)bh * n_items + n) * V + v0 + r];
-            if (OPT & 1) {
-                // 16-column blocks, double-buffered: ld(c+1) is issued before block c is processed
-                auto process = [&](uint32_t (&f)[16], int c) {
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 d4 = *reinterpret_cast<const float4 *>(dv + c * 16 + j);
-                        f[j + 0] = __float_as_uint(__uint_as_float(f[j + 0]) * d4.x);
-                        f[j + 1] = __float_as_uint(__uint_as_float(f[j + 1]) * d4.y);
-                        f[j + 2] = __float_as_uint(__uint_as_float(f[j + 2]) * d4.z);
-                        f[j + 3] = __float_as_uint(__uint_as_float(f[j + 3]) * d4.w);
-                    }
-                    if (!last) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
-                        tmem_st16(tmem + lane_addr + COL_ST + c * 16, f);
-                        tmem_st8(tmem + lane_addr + COL_SA + c * 8, pk);
-                    } else if (ht != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) ht[sbase + (size_t)(c * 16 + j) * V] = __uint_as_float(f[j]);
-                    }
-                };
-                uint32_t fa[16], fb[16];
-                tmem_ld16(tmem + lane_addr + COL_ST, fa);
 #pragma unroll 1
-                for (int c = 0; c < K / 16; c += 2) {
-                    tmem_ld_wait();
-                    tmem_ld16(tmem + lane_addr + COL_ST + (c + 1) * 16, fb);
-                    process(fa, c);
-                    tmem_ld_wait();
-                    if (c + 2 < K / 16) tmem_ld16(tmem + lane_addr + COL_ST + (c + 2) * 16, fa);
-                    process(fb, c + 1);
-                }
-            } else {
-#pragma unroll 1
-            for (int cb = cb_lo; cb < cb_hi; ++cb) {
+            for (int cb = sg; cb < NB; cb += NG) {
                 uint32_t f[32], pk[16];
                 tmem_ld32(tmem + lane_addr + COL_ST + cb * 32, f);
                 tmem_ld_wait();
@@ -494,16 +488,15 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(f[2 * j]), __uint_as_float(f[2 * j + 1]));
                     tmem_st32(tmem + lane_addr + COL_ST + cb * 32, f);
                     tmem_st16(tmem + lane_addr + COL_SA + cb * 16, pk);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars[B_SA_BLK0 + cb]);        // this block of SA / ST is final for the next item
                 } else if (ht != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) ht[sbase + (size_t)(cb * 32 + j) * V] = __uint_as_float(f[j]);
                 }
             }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[B_SA_FULL]);
-            if (r == 0 && !st2) TRACE(5, n, 1);
+            if (r == 0 && sg == 0) TRACE(5, n, 1);
         }
     }
     tc_fence_before();
@@ -652,9 +645,9 @@ extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const
     cudaStream_t st = (cudaStream_t)stream;
     bthd = bthd ? 1 : 0;
     if (row_decay) {
-        if (K == 64) return launch<64, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
-        if (K == 128) return launch<128, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
-        return launch<256, 28>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+        if (K == 64) return launch<64, 60>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+        if (K == 128) return launch<128, 60>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
+        return launch<256, 60>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
     }
     if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
     if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
