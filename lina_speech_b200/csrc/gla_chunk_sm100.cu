@@ -128,14 +128,21 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     //            next item starts on block 0 while the later blocks are still being rescaled.
     constexpr bool STATE2 = (OPT & 32) != 0;
     static_assert(!STATE2 || PRE, "the extra state-pass warpgroups are the pre-pass warps");
+    // OPT bit 6 (CL, with PRE): the V/128 CTAs of one (batch, head) form a thread-block CLUSTER and share the q~ / k~ loads:
+    //            each CTA fetches 1/csize of the 64x64 boxes of a stage and TMA multicasts them into every CTA's operand
+    //            tiles (L2 -> SM traffic of the kernel 2.4 GB -> 0.9 GB at the bench shape; it was the binding resource once
+    //            MMA issue was fixed).  A stage is reloaded only when ALL CTAs have released it (multicast tcgen05.commit).
+    constexpr bool CL = (OPT & 64) != 0;
+    static_assert(!CL || PRE, "cluster multicast is implemented for pre-gated operands");
     constexpr int NB = K / 32;
     constexpr int NG = STATE2 ? (NB >= 3 ? 3 : NB) : 1;
     static_assert(!ROW || PRE, "row decay needs pre-gated operands");
     using cfg = Cfg<K>;
     // With pre-gated operands the gk side tiles (2 * G_BYTES = QK_BYTES) are unused: they hold EITHER a second v stage (default)
-    // OR a third q~/k~ stage (QK3).  Measured at the bench shape: 2+2 stages 3182 cycles per item, 3+1 stages 3381 (the
-    // loader is one thread: with one v stage it sits in the V_EMPTY wait and cannot run ahead on q~/k~ anyway).
-    constexpr bool QK3 = false;
+    // OR a third q~/k~ stage (QK3, OPT bit 7).  Measured at the bench shape in one process: 2+2 stages 0.264 ms, 3+1 stages
+    // 0.295 ms, 2+2 with cluster multicast 0.276 ms -- after the issue-loop fix the kernel is bound by the tensor pipe fed
+    // from shared memory (~2780 of ~3200 cycles per item: SS MMAs run at ~75 B/clk of operand reads), not by loads.
+    constexpr bool QK3 = (OPT & 128) != 0;        // OPT bit 7
     constexpr int NS = (PRE && QK3) ? 3 : 2;
     constexpr bool V2 = PRE && !QK3;
     static_assert(2 * cfg::G_BYTES == cfg::QK_BYTES, "third stage lives in the gk tiles");
@@ -149,6 +156,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.y, v0 = blockIdx.x * BV;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
     const int n_items = (T + C - 1) / C;
     const int bb = bh / H, hh = bh - bb * H;
     // o is [B,H,T,V] (bthd == 0) or [B,T,H,V] (bthd == 1)
@@ -158,7 +167,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
         mbar_init(&bars[B_QK_FULL0], NPREP); mbar_init(&bars[B_QK_FULL1], NPREP);
-        mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1); mbar_init(&bars[B_QK_EMPTY2], 1);
+        mbar_init(&bars[B_QK_EMPTY0], csize); mbar_init(&bars[B_QK_EMPTY1], csize); mbar_init(&bars[B_QK_EMPTY2], csize);
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
         mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
@@ -173,6 +182,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();          // every CTA's mbarriers are initialised before any peer multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -269,31 +279,63 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm.q); tma_prefetch_desc(&tm.k); tma_prefetch_desc(&tm.v);
             if (!PRE) tma_prefetch_desc(&tm.g);
-            for (int n = 0; n < n_items; ++n) {
-                const int s = n % NS, u = n / NS, t0 = n * C;
-                const uint32_t qk_tile = smem_u32(smem + qk_stage_off(s));
-                const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
-                wait_bar(&bars[B_QK_EMPTY0 + s], (u & 1) ^ 1);
-                if (!PRE) wait_bar(&bars[B_G_EMPTY0 + s], (u & 1) ^ 1);
-                TRACE(1, n, 0);
-                mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + (ROW ? 0u : K * 4u)) : cfg::RAW_TX);
-                if (PRE && !ROW)   // dvec ring slot n % 3 <- decay[b, h, n, :]  (safe: the loader runs at most 2 items ahead)
-                    tma_load_1d(smem_u32(dvec_slot(n)), decay + ((size_t)bh * n_items + n) * K, K * 4u,
-                                &bars[B_RAW_FULL0 + s]);
+            // Two independent streams (q~/k~[/gk] stages and v tiles) served by ONE thread: it polls both EMPTY barriers
+            // instead of blocking on one, so a full v ring never stops the operand ring from running ahead (and vice versa).
+            int nq = 0, nv = 0;
+            long long t_idle = clock64();
+            while (nq < n_items || nv < n_items) {
+                bool progressed = false;
+                if (nq < n_items) {
+                    const int n = nq, s = n % NS, u = n / NS, t0 = n * C;
+                    if (mbar_try_wait(&bars[B_QK_EMPTY0 + s], (u & 1) ^ 1) &&
+                        (PRE || mbar_try_wait(&bars[B_G_EMPTY0 + s], (u & 1) ^ 1))) {
+                        const uint32_t qk_tile = smem_u32(smem + qk_stage_off(s));
+                        const uint32_t g_tile = smem_u32(smem + cfg::OFF_G + s * cfg::G_BYTES);
+                        TRACE(1, n, 0);
+                        mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + (ROW ? 0u : K * 4u)) : cfg::RAW_TX);
+                        if (PRE && !ROW)   // chunk-decay ring slot <- decay[b, h, n, :]
+                            tma_load_1d(smem_u32(dvec_slot(n)), decay + ((size_t)bh * n_items + n) * K, K * 4u,
+                                        &bars[B_RAW_FULL0 + s]);
+                        if (CL) {
+                            // box i of the stage (q~ boxes then k~ boxes) is fetched by CTA i % csize and multicast to the cluster
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    if (!PRE) tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
-                    tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
-                    tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                            for (int i = 0; i < 2 * KB; ++i) {
+                                if ((uint32_t)i % csize != crank) continue;
+                                const int kb = i < KB ? i : i - KB;
+                                tma_load_4d_mc(qk_tile + kb * cfg::QK_BLK + (i < KB ? 0 : 8192), i < KB ? &tm.q : &tm.k, kb * 64, t0,
+                                               hh, bb, &bars[B_RAW_FULL0 + s], cmask);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kb = 0; kb < KB; ++kb) {
+                                if (!PRE) tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                                tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                                tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                            }
+                        }
+                        TRACE(1, n, 1);
+                        ++nq;
+                        progressed = true;
+                    }
                 }
-                TRACE(1, n, 1);
-                const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;         // v stage and its use count
-                wait_bar(&bars[B_V_EMPTY0 + sv], (uv & 1) ^ 1);
-                mbar_expect_tx(&bars[B_V_FULL0 + sv], VT_BYTES);
-                const uint32_t v_tile = smem_u32(smem + (sv ? V_STAGE1 : cfg::OFF_V));
-                tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL0 + sv]);
-                tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL0 + sv]);
-                TRACE(1, n, 2);
+                if (nv < n_items) {
+                    const int n = nv, t0 = n * C;
+                    const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;         // v stage and its use count
+                    if (mbar_try_wait(&bars[B_V_EMPTY0 + sv], (uv & 1) ^ 1)) {
+                        mbar_expect_tx(&bars[B_V_FULL0 + sv], VT_BYTES);
+                        const uint32_t v_tile = smem_u32(smem + (sv ? V_STAGE1 : cfg::OFF_V));
+                        tma_load_4d(v_tile, &tm.v, v0, t0, hh, bb, &bars[B_V_FULL0 + sv]);
+                        tma_load_4d(v_tile + 8192, &tm.v, v0 + 64, t0, hh, bb, &bars[B_V_FULL0 + sv]);
+                        TRACE(1, n, 2);
+                        ++nv;
+                        progressed = true;
+                    }
+                }
+                if (progressed) t_idle = clock64();
+                else if (clock64() - t_idle > 4000000000LL) {
+                    printf("gla_chunk_sm100: loader timeout (block %d,%d nq %d nv %d)\n", blockIdx.x, blockIdx.y, nq, nv);
+                    __trap();
+                }
             }
         }
         __syncwarp();
@@ -363,7 +405,8 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 for (int ks = 0; ks < C / 16; ++ks)
                     mma_ss(tmem + COL_ST, d_v + (uint64_t)(ks * 128), dk3 + (uint64_t)(ks * 128), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
-                mma_commit(&bars[B_QK_EMPTY0 + s]);
+                if (CL) mma_commit_mc(&bars[B_QK_EMPTY0 + s], cmask);
+                else mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY0 + sv]);
                 TRACE(2, n, 3);
             }
@@ -501,6 +544,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();          // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -548,6 +592,18 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
         }
     }
     dim3 grid(V / BV, B * H);
+    if ((OPT & 64) != 0) {               // the V/128 CTAs of a (batch, head) are one cluster
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = V / BV; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        bf16 *op = (bf16 *)o;
+        LINA_CUDA_OK(cudaLaunchKernelEx(&lc, gla_chunk_fwd_sm100_kernel<K, OPT>, tm, h0, h0_dtype, op, ht, T, V, H, bthd, scale,
+                                        trace, decay));
+        return LINA_OK;
+    }
     gla_chunk_fwd_sm100_kernel<K, OPT><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
                                                                         trace, decay);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
@@ -615,7 +671,18 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
                  "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
     LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_lina_variant[4] == 0) {            // two warpgroups share the state pass (variant 4 = 1: one warpgroup)
+    const int nvs = V / BV;
+    if (g_lina_variant[4] == 0 && g_lina_variant[7] == 1 && (nvs == 2 || nvs == 4 || nvs == 8)) {   // A/B: + cluster multicast
+        if (K == 64) return launch<64, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        if (K == 128) return launch<128, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        return launch<256, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    }
+    if (g_lina_variant[4] == 0 && g_lina_variant[6] == 1) {   // A/B: three q~/k~ stages + one v stage (default: two + two)
+        if (K == 64) return launch<64, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        if (K == 128) return launch<128, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+        return launch<256, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    }
+    if (g_lina_variant[4] == 0) {            // three warpgroups share the state pass (variant 4 = 1: one warpgroup)
         if (K == 64) return launch<64, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
         if (K == 128) return launch<128, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
         return launch<256, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);

@@ -201,6 +201,26 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// ---- thread-block clusters: rank / size, cluster-wide barrier, multicast TMA and multicast tcgen05.commit ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the tile lands at the SAME shared-memory offset of every CTA in `mask`, and complete_tx is signalled on the mbarrier at
+// the same offset of each of them
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst_smem, const void *tmap, int c0, int c1, int c2, int c3, uint64_t *bar,
+                                               uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                 "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+// one arrive on the mbarrier at this offset in every CTA of `mask` when the previously issued MMAs of this thread complete
+__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -201,6 +201,13 @@ def gla_pre():
 report("gla_chunk_fwd_pregated_bthd (tcgen05)", timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
 res["gla_chunk_fwd_pregated_bthd (tcgen05)"]["finite"] = bool(torch.isfinite(o_b.float()).all())
 o_one = o_b.clone()
+for key, name in ((6, "3+1 stages instead of 2+2"), (7, "cluster multicast (2+2 stages)")):
+    lib.lina_debug_set_variant(key, 1)
+    nm = "gla_chunk_fwd_pregated_bthd " + name
+    report(nm, timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
+    res[nm]["max_diff_vs_default"] = (o_b.float() - o_one.float()).abs().max().item()
+    print("   max diff", res[nm]["max_diff_vs_default"])
+    lib.lina_debug_set_variant(key, 0)
 lib.lina_debug_set_variant(4, 1)
 report("gla_chunk_fwd_pregated_bthd one state warpgroup", timeit(gla_pre), B * H * T * (2 * K + 2 * V) * 2 + decay.numel() * 4)
 res["gla_chunk_fwd_pregated_bthd one state warpgroup"]["max_diff_vs_default"] = (o_b.float() - o_one.float()).abs().max().item()
