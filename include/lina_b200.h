@@ -222,6 +222,14 @@ int lina_add_layernorm(const void *a, const void *x, const void *gamma, const vo
 int lina_cross_entropy_rows(const void *logits, long long ld, const int64_t *target, const uint8_t *row_mask,
                             float *loss, float *valid, int M, int Vn, long long ignore_index, int dtype, void *stream);
 
+/* Fused top-k sampling of the decode loop (model/tools.py:38-44 `topk_sampling`, called per quantizer at
+ * model/modeling_lina.py:159-165): kth = k-th largest UNSCALED logit of the row, keep x/temp >= kth (the reference's quirk),
+ * softmax over the kept entries, id = inverse-CDF sample with the caller's uniform[b] in [0,1).  logits [B, ld] (`dtype`,
+ * first Vn columns), out [B] int64.  k = 1 returns the arg-max.  torch.multinomial's bit pattern is not reproduced (same
+ * distribution). */
+int lina_topk_sample(const void *logits, long long ld, int B, int Vn, int k, float temp, const float *uniform,
+                     int64_t *out, int dtype, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * WavTokenizer decode tail (fp32).  The dense convolutions / linears of the backbone stay library
  * GEMMs on the host side; these are the HBM-bound stages between them.

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "lina_swiglu_act": (_i, [_p, _p, _i, _i, _i, _p]),
     "lina_add_layernorm": (_i, [_p] * 6 + [_i, _i, _f, _i, _p]),
     "lina_cross_entropy_rows": (_i, [_p, C.c_longlong, _p, _p, _p, _p, _i, _i, C.c_longlong, _i, _p]),
+    "lina_topk_sample": (_i, [_p, C.c_longlong, _i, _i, _i, _f, _p, _p, _i, _p]),
     "lina_codec_codes_to_features": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_codec_groupnorm_swish": (_i, [_p] * 5 + [_i] * 4 + [_f, _i, _p]),
     "lina_codec_dwconv_adaln": (_i, [_p] * 6 + [_i] * 3 + [_f, _p]),

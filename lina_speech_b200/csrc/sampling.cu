@@ -1,0 +1,140 @@
+// Fused top-k sampling of the decode loop (model/tools.py:38-44 topk_sampling + model/modeling_lina.py:159-165):
+//   kth = k-th largest logit of the row (UNSCALED, the reference's quirk) ; keep x/temp >= kth ; p = softmax(kept) ;
+//   id  = inverse-CDF sample of p with the caller's uniform u in [0,1)
+// One CTA per row: the row is staged in shared memory as fp32, the k-th value found by a 4-pass 8-bit radix select on the
+// order-preserving integer image of the floats, the softmax sum by a block reduction, the sample by a block scan over
+// per-thread segment sums.  Replaces ~15 torch launches per step (topk = sort, div, compare, masked_fill, softmax,
+// multinomial ...: ~130 us at bs128) with one.  torch.multinomial's own algorithm cannot be matched bit for bit; the
+// distribution is the same, and k = 1 (greedy) returns the arg-max exactly (exact ties are split by u, like multinomial).
+#include "common.cuh"
+
+namespace {
+
+constexpr int ST = 256;                 // threads per row
+constexpr int MAXV = 8192;              // row length staged in shared memory
+
+__device__ __forceinline__ uint32_t f2ord(float f) {      // monotone float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ST)
+topk_sample_kernel(const T *__restrict__ logits, long long ld, int Vn, int k, float inv_temp, const float *__restrict__ uni,
+                   long long *__restrict__ out) {
+    __shared__ float row[MAXV];
+    __shared__ unsigned int hist[256];
+    __shared__ float red[ST / 32];
+    __shared__ float seg[ST];
+    __shared__ uint32_t sel_prefix;
+    __shared__ int sel_k;
+    __shared__ float bcast[2];
+    __shared__ int winner;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T *r = logits + (size_t)blockIdx.x * ld;
+    for (int i = tid; i < Vn; i += ST) row[i] = to_f(r[i]);
+    if (tid == 0) { sel_prefix = 0u; sel_k = k; }
+    __syncthreads();
+    // ---- k-th largest by radix select, most significant byte first ----
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = sel_prefix;
+        const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < Vn; i += ST) {
+            const uint32_t o = f2ord(row[i]);
+            if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {                  // walk the 256 bins from the top: the bin holding the sel_k-th largest candidate
+            int need = sel_k, b = 255;
+            for (; b > 0; --b) {
+                const int c = (int)hist[b];
+                if (c >= need) break;
+                need -= c;
+            }
+            sel_k = need;
+            sel_prefix = prefix | ((uint32_t)b << shift);
+        }
+        __syncthreads();
+    }
+    const float kth = ord2f(sel_prefix);
+    // ---- softmax over the kept entries (x * inv_temp >= kth) ----
+    float mx = -INFINITY;
+    for (int i = tid; i < Vn; i += ST) mx = fmaxf(mx, row[i] * inv_temp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0];
+        for (int w = 1; w < ST / 32; ++w) m = fmaxf(m, red[w]);
+        bcast[0] = m;
+    }
+    __syncthreads();
+    mx = bcast[0];                       // max of the scaled row
+    // temp != 1 can push every scaled logit below the unscaled k-th value (the reference then feeds NaNs to
+    // torch.multinomial, which raises); keep at least the maximum
+    const float thr = fminf(kth, mx);
+    __syncthreads();
+    // thread t owns the contiguous segment [t*per, (t+1)*per): weights written back into `row`
+    const int per = (Vn + ST - 1) / ST;
+    const int lo = tid * per, hi = min(Vn, lo + per);
+    float ssum = 0.f;
+    for (int i = lo; i < hi; ++i) {
+        const float x = row[i] * inv_temp;
+        const float w = (x >= thr) ? __expf(x - mx) : 0.f;
+        row[i] = w;
+        ssum += w;
+    }
+    seg[tid] = ssum;
+    __syncthreads();
+    if (tid == 0) {                      // serial scan of the 256 segment sums (tiny): the segment holding u * total
+        float tot = 0.f;
+        for (int t = 0; t < ST; ++t) tot += seg[t];
+        const float target = uni[blockIdx.x] * tot;
+        float acc = 0.f, ex = 0.f;
+        int wseg = -1;
+        for (int t = 0; t < ST; ++t) {
+            if (seg[t] <= 0.f) continue;
+            wseg = t;                    // the last non-empty segment catches target == total (rounding)
+            ex = acc;
+            if (acc + seg[t] > target) break;
+            acc += seg[t];
+        }
+        winner = wseg;
+        bcast[0] = target;
+        bcast[1] = ex;
+    }
+    __syncthreads();
+    if (tid == winner) {
+        const float target = bcast[0];
+        float acc = bcast[1];
+        int pick = -1;
+        for (int i = lo; i < hi; ++i) {
+            const float w = row[i];
+            if (w > 0.f) { pick = i; if (acc + w > target) break; acc += w; }
+        }
+        out[blockIdx.x] = (long long)pick;
+    }
+}
+
+}  // namespace
+
+extern "C" int lina_topk_sample(const void *logits, long long ld, int B, int Vn, int k, float temp, const float *uniform,
+                                int64_t *out, int dtype, void *stream) {
+    LINA_REQUIRE(logits && uniform && out && B > 0 && Vn > 0 && ld >= Vn && temp > 0.f, LINA_ERR_BAD_ARG,
+                 "topk_sample: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(dtype), LINA_ERR_BAD_ARG, "topk_sample: unknown dtype");
+    LINA_REQUIRE(Vn <= MAXV, LINA_ERR_UNSUPPORTED, "topk_sample: vocabulary %d > %d", Vn, MAXV);
+    LINA_REQUIRE(k >= 1 && k <= Vn, LINA_ERR_BAD_ARG, "topk_sample: k=%d outside [1, %d]", k, Vn);
+    LINA_DISPATCH_DTYPE(dtype, topk_sample_kernel<T_><<<B, ST, 0, (cudaStream_t)stream>>>(
+                                   (const T_ *)logits, ld, Vn, k, 1.f / temp, uniform, (long long *)out));
+    LINA_LAUNCH_OK("topk_sample_kernel");
+    return LINA_OK;
+}

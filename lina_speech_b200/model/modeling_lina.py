@@ -13,6 +13,7 @@ on top of the B200 GLA backbone.  Additions (all opt-in, defaults reproduce the 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -24,6 +25,9 @@ from .contracts import AttentiveRNN
 from .embeddings import MultiEmbedding
 from ..parallel import gather_tokens
 from .tools import topk_sampling, undelay_rvq
+
+
+FUSED_SAMPLING = os.environ.get("LINA_FUSED_SAMPLING", "1") != "0"
 
 
 def exists(x):
@@ -133,6 +137,22 @@ class LinaModel(nn.Module):
     def _sample(self, logits, k, first_greedy_quant, temp):
         """logits [b,1,q,l] -> ids [q,b,1] (modeling_lina.py:156-165; NB quantizers with index
         < first_greedy_quant are the *sampled* ones, the rest greedy -- the name is inverted upstream)."""
+        if FUSED_SAMPLING and logits.is_cuda and not torch.is_grad_enabled() and logits.stride(-1) == 1 \
+                and logits.dtype in (torch.float32, torch.bfloat16, torch.float16) and logits.shape[-1] <= 8192:
+            # one launch per quantizer (lina_topk_sample) instead of topk (a sort) + div + compare + masked_fill + softmax +
+            # multinomial; same distribution, greedy ids identical
+            from .. import _lib as L
+            b, _, q, l = logits.shape
+            out = torch.empty(q, b, 1, dtype=torch.long, device=logits.device)
+            u = torch.rand(q, b, device=logits.device, dtype=torch.float32)
+            for i in range(q):
+                row = logits[:, 0, i]
+                ki, ti = (k, temp) if i < first_greedy_quant else (1, 1.0)
+                rc = L.lib().lina_topk_sample(L.ptr(row), row.stride(0), b, l, min(int(ki), l), float(ti), L.ptr(u[i]),
+                                              L.ptr(out[i]), L.dt(row), L.stream(row))
+                L.count_launches(1)
+                L.check(rc, "lina_topk_sample")
+            return out
         lg = rearrange(logits, "b 1 q l -> q b l").float()
         out = [topk_sampling(qq, k=k, temp=temp) if i < first_greedy_quant else topk_sampling(qq, k=1)
                for i, qq in enumerate(lg)]

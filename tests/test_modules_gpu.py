@@ -368,3 +368,54 @@ def test_short_conv_bf16_backward_packed_kernel(B, Ln, D, silu):
     (y.float() * dy.to(DEV).float()).sum().backward()
     _close(xg.grad, xr.grad, 2e-2, 1e-2, what="conv dx (bf16)")
     _close(conv.weight.grad[:, 0], wr.grad, 5e-2, 2e-2, what="conv dw (bf16)")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Vn,ld", [(128, 4099, 4104), (7, 67, 72), (3, 300, 300)])
+def test_fused_topk_sampling(dtype, B, Vn, ld):
+    """lina_topk_sample: k = 1 is the arg-max; k = 100 equals the inverse-CDF sample of the reference's masked softmax
+    (model/tools.py:38-44, incl. the unscaled-threshold quirk) for the same uniform numbers."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(B + Vn)
+    buf = (torch.randn(B, ld) * 3).to(dtype)
+    x = buf[:, :Vn].float()
+    bd = buf.to(DEV)
+    u = torch.rand(B)
+    ud = u.to(DEV)
+    out = torch.empty(B, dtype=torch.long, device=DEV)
+    lib = L.lib()
+    L.check(lib.lina_topk_sample(L.ptr(bd), ld, B, Vn, 1, 1.0, L.ptr(ud), L.ptr(out), L.dt(bd), L.stream(bd)), "topk k=1")
+    ref1 = x.argmax(-1)
+    assert torch.equal(x.gather(1, out.cpu()[:, None]), x.gather(1, ref1[:, None])), "k=1 must pick a maximum"
+    for k, temp in ((min(100, Vn), 1.0), (min(20, Vn), 0.7)):
+        L.check(lib.lina_topk_sample(L.ptr(bd), ld, B, Vn, k, temp, L.ptr(ud), L.ptr(out), L.dt(bd), L.stream(bd)), "topk")
+        got = out.cpu()
+        kth = torch.topk(x, k, dim=-1).values[:, -1:]
+        xs = x / temp
+        keep = xs >= torch.minimum(kth, xs.max(-1, keepdim=True).values)
+        w = torch.where(keep, (xs - xs.max(-1, keepdim=True).values).exp(), torch.zeros_like(xs)).double()
+        cdf = w.cumsum(-1)
+        target = u.double()[:, None] * cdf[:, -1:]
+        ref = (cdf > target).float().argmax(-1)
+        assert keep.gather(1, got[:, None]).all(), "sample outside the kept set"
+        agree = (got == ref).float().mean().item()
+        assert agree >= 0.97, f"k={k}: only {agree:.3f} of the rows match the inverse-CDF reference"
+        # the disagreeing rows sit on a CDF boundary: their cumulative probability is within fp32 rounding of the target
+        bad = (got != ref).nonzero().flatten()
+        for i in bad.tolist():
+            lo, hi = sorted((int(got[i]), int(ref[i])))
+            gap = (cdf[i, hi] - cdf[i, lo]).item() / cdf[i, -1].item()
+            near = abs(cdf[i, lo].item() - target[i].item()) / cdf[i, -1].item()
+            assert near < 1e-4 or gap < 1e-4, f"row {i}: picks {int(got[i])} vs {int(ref[i])} are not a rounding tie"
+
+
+def test_generate_batch_with_fused_sampling_runs_and_stays_in_vocabulary(golden_model):
+    import lina_speech_b200.model as m
+    g = golden_model
+    rnn = m.AttentiveGLA(64, 2, 2, blind=True, use_short_conv=True, pos_type="convolutional")
+    lm = m.LinaModel(rnn, 64, 1, 64, 3, 3, 32, txt_encoder=m.TextEncoder(64, 2, n_layers=1, dropout=0.0, rotary=False))
+    lm.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("w.")})
+    lm = lm.to(DEV).eval()
+    qs, atts, stop_tokens, cuts = lm.generate_batch(g["xt"].to(DEV), batch_size=4, prompt=g["prompt"].to(DEV), max_seqlen=16,
+                                                    k=10, force_max_seqlen=True, cuda_graph=True)
+    assert qs.shape == (1, 4, 16) and int(qs.min()) >= 0 and int(qs.max()) < 64 + 3
