@@ -116,6 +116,14 @@ int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void 
                      int B, int H, int K, int V, int W, int dtype, int state_dtype,
                      float scale, float gate_normalizer, float eps, int ldx, int ldg, void *stream);
 
+/* Same, with the gate logits computed inside from the rank-R factors of gk_proj (model/gla.py:96-97): lo [B,R] (row stride
+ * ld_lo), w2 [H*K,R], b2 [H*K] or NULL -- one GEMM launch less per layer per token. */
+int lina_gla_step_lr(const void *xq, const void *xk, const void *xv, const void *lo, int ld_lo, const void *w2,
+                     const void *b2, int R, const void *g, const void *wq, const void *wk, const void *wv,
+                     void *cq, void *ck, void *cv, void *S, const void *norm_w, void *out, void *ws,
+                     int B, int H, int K, int V, int W, int dtype, int state_dtype,
+                     float scale, float gate_normalizer, float eps, int ldx, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Post-projection pass of a whole-sequence GLA mixer call in ONE launch (inference prefill):
  *   q, k, v = SiLU(ShortConvolution(x_q | x_k | x_v))   (FLA/fla/modules/convolution.py:141-178, model/gla.py:161-163)

@@ -21,7 +21,9 @@ __global__ void gla_step_prep_kernel(const T *__restrict__ xq, const T *__restri
                                      const T *__restrict__ wk, const T *__restrict__ wv, CT *__restrict__ cq,
                                      CT *__restrict__ ck, CT *__restrict__ cv, float *__restrict__ qf,
                                      float *__restrict__ kf, float *__restrict__ ef, float *__restrict__ vf,
-                                     int B, int HK, int HV, int W, float scale, float inv_norm, int ld_qk, int ld_v, int ldg) {
+                                     int B, int HK, int HV, int W, float scale, float inv_norm, int ld_qk, int ld_v, int ldg,
+                                     const T *__restrict__ lo, int ld_lo, const T *__restrict__ w2,
+                                     const T *__restrict__ b2, int R) {
     const int per_b = 3 * HK + HV;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * per_b) return;
@@ -29,7 +31,16 @@ __global__ void gla_step_prep_kernel(const T *__restrict__ xq, const T *__restri
     int c = (int)(i - (long long)b * per_b);
     if (c >= 2 * HK + HV) {                         // gate channel
         c -= 2 * HK + HV;
-        const float x = to_f(gk_raw[(size_t)b * ldg + c]);
+        float x;
+        if (lo != nullptr) {
+            // gate logits from the rank-R factorisation in place: x = b2[c] + sum_r lo[b, r] * w2[c, r]  (gk_proj[1] of
+            // model/gla.py:96-97), rounded to the activation dtype like the GEMM it replaces
+            float acc = b2 != nullptr ? to_f(b2[c]) : 0.f;
+            for (int r = 0; r < R; ++r) acc = fmaf(to_f(lo[(size_t)b * ld_lo + r]), to_f(w2[(size_t)c * R + r]), acc);
+            x = to_f(from_f<T>(acc));
+        } else {
+            x = to_f(gk_raw[(size_t)b * ldg + c]);
+        }
         ef[(size_t)b * HK + c] = expf(logsigmoidf_(x) * inv_norm);
         return;
     }
@@ -190,7 +201,8 @@ template <typename T, typename CT>
 int launch_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g, const void *wq,
                 const void *wk, const void *wv, void *cq, void *ck, void *cv, void *S, const void *norm_w,
                 void *out, float *ws, int B, int H, int K, int V, int W, float scale, float gate_normalizer,
-                float eps, int ld_qk, int ld_v, int ldg, cudaStream_t st) {
+                float eps, int ld_qk, int ld_v, int ldg, cudaStream_t st, const void *lo = nullptr, int ld_lo = 0,
+                const void *w2 = nullptr, const void *b2 = nullptr, int R = 0) {
     const int HK = H * K, HV = H * V;
     float *qf = ws, *kf = qf + (size_t)B * HK, *ef = kf + (size_t)B * HK, *vf = ef + (size_t)B * HK,
           *of = vf + (size_t)B * HV;
@@ -198,7 +210,7 @@ int launch_step(const void *xq, const void *xk, const void *xv, const void *gk_r
     gla_step_prep_kernel<T, CT><<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(
         (const T *)xq, (const T *)xk, (const T *)xv, (const T *)gk_raw, (const T *)wq, (const T *)wk,
         (const T *)wv, (CT *)cq, (CT *)ck, (CT *)cv, qf, kf, ef, vf, B, HK, HV, W, scale, 1.f / gate_normalizer,
-        ld_qk, ld_v, ldg);
+        ld_qk, ld_v, ldg, (const T *)lo, ld_lo, (const T *)w2, (const T *)b2, R);
     LINA_LAUNCH_OK("gla_step_prep_kernel");
     constexpr int VEC = sizeof(CT) == 4 ? 4 : 8;
     dim3 grid((V + 32 * VEC - 1) / (32 * VEC), B * H);
@@ -220,13 +232,15 @@ extern "C" size_t lina_gla_step_workspace_bytes(int B, int H, int K, int V) {
 
 // ldx: common row stride (elements) of xq, xk, xv, g when they are column slices of ONE projection buffer
 // (0 = each tensor dense); ldg: row stride of gk_raw (0 = dense).
-extern "C" int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
-                                const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
-                                void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
-                                int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
-                                int ldx, int ldg, void *stream) {
+static int gla_step_impl(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                         const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                         void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
+                         int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
+                         int ldx, int ldg, void *stream, const void *lo, int ld_lo, const void *w2, const void *b2, int R) {
     LINA_REQUIRE(B > 0 && H > 0 && K > 0 && V > 0, LINA_ERR_BAD_ARG, "gla_step: non-positive size");
-    LINA_REQUIRE(xq && xk && xv && gk_raw && g && S && out && ws, LINA_ERR_BAD_ARG, "gla_step: null pointer");
+    LINA_REQUIRE(xq && xk && xv && (gk_raw || lo) && g && S && out && ws, LINA_ERR_BAD_ARG, "gla_step: null pointer");
+    LINA_REQUIRE(lo == nullptr || (w2 != nullptr && R >= 1 && R <= 256 && ld_lo >= R), LINA_ERR_BAD_ARG,
+                 "gla_step: low-rank gate needs w2 and 1 <= R <= 256");
     const bool conv = wq != nullptr;
     LINA_REQUIRE(!conv || (wk && wv && cq && ck && cv && W >= 1 && W <= 16), LINA_ERR_BAD_ARG,
                  "gla_step: short conv needs all three taps/states and 1 <= W <= 16");
@@ -243,7 +257,8 @@ extern "C" int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, 
     const int ld_qk = ldx ? ldx : H * K, ld_v = ldx ? ldx : H * V, lg = ldg ? ldg : H * K;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO_(T, CT) return launch_step<T, CT>(xq, xk, xv, gk_raw, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, \
-                                             (float *)ws, B, H, K, V, W, scale, gate_normalizer, eps, ld_qk, ld_v, lg, st)
+                                             (float *)ws, B, H, K, V, W, scale, gate_normalizer, eps, ld_qk, ld_v, lg, st, \
+                                             lo, ld_lo, w2, b2, R)
     if (dtype == LINA_F32 && state_dtype == LINA_F32) GO_(float, float);
     if (dtype == LINA_BF16 && state_dtype == LINA_BF16) GO_(bf16, bf16);
     if (dtype == LINA_BF16 && state_dtype == LINA_F32) GO_(bf16, float);
@@ -251,6 +266,27 @@ extern "C" int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, 
 #undef GO_
     lina_set_error("gla_step: dtype %d / state dtype %d combination not implemented", dtype, state_dtype);
     return LINA_ERR_UNSUPPORTED;
+}
+
+extern "C" int lina_gla_step_ld(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,
+                                const void *wq, const void *wk, const void *wv, void *cq, void *ck, void *cv,
+                                void *S, const void *norm_w, void *out, void *ws, int B, int H, int K, int V, int W,
+                                int dtype, int state_dtype, float scale, float gate_normalizer, float eps,
+                                int ldx, int ldg, void *stream) {
+    return gla_step_impl(xq, xk, xv, gk_raw, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, ws, B, H, K, V, W, dtype, state_dtype,
+                         scale, gate_normalizer, eps, ldx, ldg, stream, nullptr, 0, nullptr, nullptr, 0);
+}
+
+// Same with the gate logits computed in the kernel from the rank-R factors: lo [B, R] (row stride ld_lo; e.g. the last
+// columns of the [q;k;v;g;gk0] projection), w2 [H*K, R], b2 [H*K] or NULL -- saves the gk_proj[1] GEMM launch per layer
+// per token.
+extern "C" int lina_gla_step_lr(const void *xq, const void *xk, const void *xv, const void *lo, int ld_lo, const void *w2,
+                                const void *b2, int R, const void *g, const void *wq, const void *wk, const void *wv,
+                                void *cq, void *ck, void *cv, void *S, const void *norm_w, void *out, void *ws, int B,
+                                int H, int K, int V, int W, int dtype, int state_dtype, float scale,
+                                float gate_normalizer, float eps, int ldx, void *stream) {
+    return gla_step_impl(xq, xk, xv, nullptr, g, wq, wk, wv, cq, ck, cv, S, norm_w, out, ws, B, H, K, V, W, dtype, state_dtype,
+                         scale, gate_normalizer, eps, ldx, 0, stream, lo, ld_lo, w2, b2, R);
 }
 
 extern "C" int lina_gla_step(const void *xq, const void *xk, const void *xv, const void *gk_raw, const void *g,

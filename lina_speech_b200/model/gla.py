@@ -111,7 +111,6 @@ class GatedLinearAttention(nn.Module):
         H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
         proj = F.linear(x.view(B, -1), self._cat_weight())
         xq, xk, xv, g, lo = torch.split(proj, [kd, kd, vd, vd, proj.shape[1] - 2 * kd - 2 * vd], dim=1)
-        gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
         ldx = proj.shape[1]                            # the four slices are read in place with this row stride
         if self.use_short_conv:
             cq, ck, cv, S = state
@@ -130,13 +129,16 @@ class GatedLinearAttention(nn.Module):
         ws = torch.empty(int(lib.lina_gla_step_workspace_bytes(B, H, K, V)), dtype=torch.uint8, device=x.device)
         nw = self.g_norm_swish_gate.weight
         nw = nw.to(x.dtype) if nw is not None else None
-        rc = lib.lina_gla_step_ld(L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(gk_raw), L.ptr(g), L.ptr(wq), L.ptr(wk),
-                                  L.ptr(wv), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.ptr(S), L.ptr(nw), L.ptr(out),
+        w2, b2 = self.gk_proj[1].weight, self.gk_proj[1].bias           # rank-R gate factors, applied inside the step kernel
+        w2c = w2.to(x.dtype).contiguous()
+        b2c = b2.to(x.dtype).contiguous() if b2 is not None else None
+        rc = lib.lina_gla_step_lr(L.ptr(xq), L.ptr(xk), L.ptr(xv), L.ptr(lo), ldx, L.ptr(w2c),
+                                  L.ptr(b2c), w2.shape[1], L.ptr(g), L.ptr(wq),
+                                  L.ptr(wk), L.ptr(wv), L.ptr(cq), L.ptr(ck), L.ptr(cv), L.ptr(S), L.ptr(nw), L.ptr(out),
                                   L.ptr(ws), B, H, K, V, W, L.dt(x), L.dt(S), float(K) ** -0.5,
-                                  float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), ldx,
-                                  gk_raw.stride(0), L.stream(x))
+                                  float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), ldx, L.stream(x))
         L.count_launches(3)
-        L.check(rc, "lina_gla_step")
+        L.check(rc, "lina_gla_step_lr")
         return self.o_proj(out).view(B, 1, -1)
 
     # -- whole-sequence inference fast path ----------------------------------------------------------
