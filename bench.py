@@ -297,9 +297,11 @@ def main_ours(args):
     ops.PROFILE = []
     l0 = _lib.launches()
     def mid_sample():
+        # one cheap NVML query from the launching thread (the GPU is busy with the queued step); the throttle reasons are
+        # read by the background thread only -- a slow NVML call here would drain the launch queue inside the timed region
         if sampler.nv is not None:
             try:
-                sampler._sample()
+                sampler.samples.append(sampler.nv.nvmlDeviceGetClockInfo(sampler.h, sampler.nv.NVML_CLOCK_SM))
             except Exception:       # noqa: BLE001
                 pass
 
