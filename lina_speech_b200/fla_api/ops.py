@@ -86,6 +86,16 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool, bthd: bool = F
 
 
 TC_BWD = os.environ.get("LINA_TC_BWD", "1") != "0"
+CONCURRENT_BWD = os.environ.get("LINA_CONCURRENT_BWD", "1") != "0"
+_SIDE = {}
+
+
+def _side_streams(dev, n):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def _tc_bwd_eligible(q, v) -> bool:
@@ -164,28 +174,40 @@ def _bwd_tc(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
     L.count_launches(2)
     dht32 = dht.float().contiguous() if dht is not None else None
 
-    # dv (+ dh0): reversed time, key-dim decay
-    dv_r = alloc(Tp, V, bf)
-    dh0 = torch.empty(B, H, K, V, dtype=f32, device=dev) if want_dh0 else None
-    _run_pregated(kh_r, qh_r, do_r, Dr, dht32, dv_r, dh0, False, bthd)
-    dv = dv_r.flip(tdim).narrow(tdim, 0, T)
-
+    # The five runs are independent and each fills only part of the machine at training batch sizes (dq / dk pieces: 2 x B*H
+    # CTAs), so they are issued on side streams and joined before the post pass.  Everything they touch was allocated on the
+    # calling stream before the fork and is released after the join, so no allocator cross-stream bookkeeping is needed.
     ns = (V + 255) // 256
     Vp = V // ns
-    dq_parts, dk_parts, ST = [], [], []
+    main = torch.cuda.current_stream(dev)
+    sides = _side_streams(dev, 2 * ns) if CONCURRENT_BWD else []
+    dv_r = alloc(Tp, V, bf)
+    dh0 = torch.empty(B, H, K, V, dtype=f32, device=dev) if want_dh0 else None
+    dq_parts = [alloc(T, K, f32) for _ in range(ns)]
+    dk_parts = [alloc(Tp, K, f32) for _ in range(ns)]
+    hts = [torch.empty(B, H, Vp, K, dtype=f32, device=dev) if dht is not None else None for _ in range(ns)]
+    h0s = [h0[..., j * Vp:(j + 1) * Vp].float().transpose(-1, -2).contiguous() if h0 is not None else None for j in range(ns)]
+    dhts = [dht32[..., j * Vp:(j + 1) * Vp].transpose(-1, -2).contiguous() if dht32 is not None else None for j in range(ns)]
+    fork = main.record_event()
+
+    def on(i):
+        if not sides:
+            return torch.cuda.stream(main)
+        sides[i].wait_event(fork)
+        return torch.cuda.stream(sides[i])
+
+    # dv (+ dh0): reversed time, key-dim decay -- on the calling stream
+    _run_pregated(kh_r, qh_r, do_r, Dr, dht32, dv_r, dh0, False, bthd)
     for j in range(ns):
         sl = slice(j * Vp, (j + 1) * Vp)
-        h0_j = h0[..., sl].float().transpose(-1, -2).contiguous() if h0 is not None else None
-        o = alloc(T, K, f32)
-        ht = torch.empty(B, H, Vp, K, dtype=f32, device=dev) if dht is not None else None
-        _run_pregated(do[..., sl], v[..., sl], kt, D, h0_j, o, ht, True, bthd)            # dq~ piece (forward time, row decay)
-        dq_parts.append(o)
-        if ht is not None:
-            ST.append(ht.transpose(-1, -2))
-        dht_j = dht32[..., sl].transpose(-1, -2).contiguous() if dht32 is not None else None
-        o2 = alloc(Tp, K, f32)
-        _run_pregated(v_r[..., sl], do_r[..., sl], qh_r, Dr, dht_j, o2, None, True, bthd)  # dk^ piece (reversed time)
-        dk_parts.append(o2)
+        with on(2 * j):       # dq~ piece (forward time, row decay)
+            _run_pregated(do[..., sl], v[..., sl], kt, D, h0s[j], dq_parts[j], hts[j], True, bthd)
+        with on(2 * j + 1):   # dk^ piece (reversed time)
+            _run_pregated(v_r[..., sl], do_r[..., sl], qh_r, Dr, dhts[j], dk_parts[j], None, True, bthd)
+    for sd in sides:
+        main.wait_event(sd.record_event())
+    dv = dv_r.flip(tdim).narrow(tdim, 0, T)
+    ST = [ht.transpose(-1, -2) for ht in hts if ht is not None]
     while len(dq_parts) > 2:                       # V > 512: fold the extra pieces (the post kernel sums two)
         dq_parts[0].add_(dq_parts.pop())
         dk_parts[0].add_(dk_parts.pop())
