@@ -633,12 +633,9 @@ static int chunk_fwd_tc(const void *q, const void *k, const void *v, const void 
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
     if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-    switch (g_lina_variant[2] & 3) {       // A/B of the kernel options at the flagship head size
-        case 1: return launch<256, 1>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-        case 2: return launch<256, 2>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-        case 3: return launch<256, 3>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-        default: return launch<256, 0>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-    }
+    if (g_lina_variant[2] & 2)             // A/B: the gate pre-pass keeps its gk rows in registers (neutral, not default)
+        return launch<256, 2>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
+    return launch<256, 0>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
 }
 
 extern "C" int lina_gla_chunk_fwd(const void *q, const void *k, const void *v, const void *gk, const void *h0,

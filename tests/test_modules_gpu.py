@@ -290,18 +290,20 @@ def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
     torch.cuda.synchronize()
     _close(o.transpose(1, 2), ro, 3e-2 * ro.abs().max().item(), 0.0, what="o (pregated tcgen05)")
     _close(ht, rht, 3e-2 * rht.abs().max().item(), 0.0, what="final state")
-    # the variant whose state pass is shared by two warpgroups computes the same bits
-    o2, ht2 = torch.empty_like(o), torch.empty_like(ht)
-    lib.lina_debug_set_variant(4, 1)
-    try:
-        rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(h0d),
-                                                  L.dt(h0d) if h0d is not None else 0, L.ptr(o2), L.ptr(ht2), B, H, T, K, V,
-                                                  L.stream(pd))
-        L.check(rc, "lina_gla_chunk_fwd_pregated_bthd (STATE2)")
-        torch.cuda.synchronize()
-    finally:
-        lib.lina_debug_set_variant(4, 0)
-    assert torch.equal(o2, o) and torch.equal(ht2, ht), "STATE2 variant differs"
+    # the kernel's build variants compute the same bits: one state warpgroup (key 4), three operand stages + one v stage
+    # (key 6), cluster-multicast operand loads across the V-slice CTAs (key 7; a cluster only when V / 128 is 2, 4 or 8)
+    for key in (4, 6, 7):
+        o2, ht2 = torch.empty_like(o), torch.empty_like(ht)
+        lib.lina_debug_set_variant(key, 1)
+        try:
+            rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(h0d),
+                                                      L.dt(h0d) if h0d is not None else 0, L.ptr(o2), L.ptr(ht2), B, H, T, K, V,
+                                                      L.stream(pd))
+            L.check(rc, f"lina_gla_chunk_fwd_pregated_bthd (variant {key})")
+            torch.cuda.synchronize()
+        finally:
+            lib.lina_debug_set_variant(key, 0)
+        assert torch.equal(o2, o) and torch.equal(ht2, ht), f"variant {key} differs"
 
 
 def test_bf16_layer_prefill_pregated_matches_op_by_op_and_oracle():
