@@ -222,6 +222,13 @@ int lina_swiglu_act(const void *h, void *out, int M, int Hp, int dtype, void *st
 int lina_add_layernorm(const void *a, const void *x, const void *gamma, const void *beta, void *sum_out,
                        void *ln_out, int M, int N, float eps, int dtype, void *stream);
 
+/* nn.LayerNorm for the bf16-autocast TRAINING path (MixingBlock norm1 / norm2, model/base_blocks.py:65-68): fp32 residual
+ * stream in, `out_dtype` output (what every consuming autocast Linear would cast it to anyway), mean / rstd [M] saved.
+ * Backward: dx fp32, dgamma / dbeta fp32 accumulators that the caller zeroes.  N % 4 == 0, N <= 1024. */
+int lina_layernorm_f32in_fwd(const float *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                             int M, int N, float eps, int out_dtype, void *stream);
+int lina_layernorm_f32in_bwd(const float *x, const float *gamma, const float *mean, const float *rstd, const void *dy,
+                             float *dx, float *dgamma, float *dbeta, int M, int N, int dy_dtype, void *stream);
 /* Row-wise cross entropy of LinaModel.forward (model/modeling_lina.py:104-106: F.cross_entropy(logits.float(),
  * target, ignore_index=1)) straight from the `dtype` logits, fp32 math: loss[m] = logsumexp(logits[m,:Vn]) -
  * logits[m,target[m]], valid[m] = 1; rows with target == ignore_index or row_mask[m] == 0 give loss = valid = 0.

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "lina_gate_logsigmoid": (_i, [_p, _p, C.c_longlong, _f, _f, _i, _i, _p]),
     "lina_swiglu_act": (_i, [_p, _p, _i, _i, _i, _p]),
     "lina_add_layernorm": (_i, [_p] * 6 + [_i, _i, _f, _i, _p]),
+    "lina_layernorm_f32in_fwd": (_i, [_p] * 6 + [_i, _i, _f, _i, _p]),
+    "lina_layernorm_f32in_bwd": (_i, [_p] * 8 + [_i, _i, _i, _p]),
     "lina_cross_entropy_rows": (_i, [_p, C.c_longlong, _p, _p, _p, _p, _i, _i, C.c_longlong, _i, _p]),
     "lina_topk_sample": (_i, [_p, C.c_longlong, _i, _i, _i, _f, _p, _p, _i, _p]),
     "lina_codec_codes_to_features": (_i, [_p] * 3 + [_i] * 5 + [_p]),

@@ -251,3 +251,169 @@ extern "C" int lina_cross_entropy_rows(const void *logits, long long ld, const i
     LINA_LAUNCH_OK("cross_entropy_rows_kernel");
     return LINA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm for the autocast TRAINING path: fp32 residual stream in, activation-dtype (bf16) output, statistics saved.
+// Under torch autocast nn.LayerNorm returns fp32 and every consuming Linear (five in the GLA mixer) casts it to bf16 again:
+// 34 bytes per element of traffic for norm1 instead of the 6 of this kernel; values reaching the GEMMs are identical.
+namespace {
+
+template <typename TO, int CH>
+__global__ void __launch_bounds__(256)
+layernorm_f32in_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                           TO *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out, int M, int N,
+                           float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nch = N / 4;                         // float4 chunks; host guarantees N % 4 == 0, nch <= 32 * CH
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * N);
+    float4 v[CH];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = lane + c * 32;
+        v[c] = ch < nch ? xr[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    }
+    const float mean = warp_sum(s) / (float)N;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        if (lane + c * 32 < nch) {
+            const float a = v[c].x - mean, b = v[c].y - mean, d = v[c].z - mean, e = v[c].w - mean;
+            ss += (a * a + b * b) + (d * d + e * e);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)N + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    TO *yr = y + (size_t)row * N;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            const float4 g = reinterpret_cast<const float4 *>(gamma)[ch], b = reinterpret_cast<const float4 *>(beta)[ch];
+            const float o0 = (v[c].x - mean) * rstd * g.x + b.x, o1 = (v[c].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[c].z - mean) * rstd * g.z + b.z, o3 = (v[c].w - mean) * rstd * g.w + b.w;
+            yr[ch * 4 + 0] = from_f<TO>(o0); yr[ch * 4 + 1] = from_f<TO>(o1);
+            yr[ch * 4 + 2] = from_f<TO>(o2); yr[ch * 4 + 3] = from_f<TO>(o3);
+        }
+    }
+}
+
+// dx = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)), dxh = dy * gamma, xh = (x - mean) * rstd ; dgamma += dy * xh ; dbeta += dy
+// Persistent grid (2 blocks per SM), rows strided over the warps; dgamma / dbeta reduced in registers, then per block in
+// shared memory, then one atomic per column per block.
+template <typename TO, int CH>
+__global__ void __launch_bounds__(256)
+layernorm_f32in_bwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean_in,
+                           const float *__restrict__ rstd_in, const TO *__restrict__ dy, float *__restrict__ dx,
+                           float *__restrict__ dgamma, float *__restrict__ dbeta, int M, int N) {
+    __shared__ float red[8][32 * CH * 4 + 1];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nch = N / 4;
+    float dg[CH][4], db[CH][4];
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dg[c][i] = 0.f; db[c][i] = 0.f; }
+    for (int row = blockIdx.x * 8 + wl; row < M; row += gridDim.x * 8) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * N);
+        const TO *dyr = dy + (size_t)row * N;
+        float4 xv[CH];
+        float dyv[CH][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+                xv[c] = xr[ch];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dyv[c][i] = to_f(dyr[ch * 4 + i]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+                const float4 g = reinterpret_cast<const float4 *>(gamma)[ch];
+                const float xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (xs[i] - mean) * rstd, dxh = dyv[c][i] * gs[i];
+                    s1 += dxh;
+                    s2 = fmaf(dxh, xh, s2);
+                    dg[c][i] = fmaf(dyv[c][i], xh, dg[c][i]);
+                    db[c][i] += dyv[c][i];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)N;
+        s2 = warp_sum(s2) / (float)N;
+        float4 *dxr = reinterpret_cast<float4 *>(dx + (size_t)row * N);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nch) {
+                const float4 g = reinterpret_cast<const float4 *>(gamma)[ch];
+                const float xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, gs[4] = {g.x, g.y, g.z, g.w};
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (xs[i] - mean) * rstd;
+                    o[i] = rstd * (dyv[c][i] * gs[i] - s1 - xh * s2);
+                }
+                dxr[ch] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    // block reduction of dgamma, then of dbeta, through one shared buffer; one atomic per column per block
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[wl][(lane + c * 32) * 4 + i] = which == 0 ? dg[c][i] : db[c][i];
+        __syncthreads();
+        float *dst = which == 0 ? dgamma : dbeta;
+        for (int col = threadIdx.x; col < N; col += 256) {
+            float a = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) a += red[w8][col];
+            atomicAdd(&dst[col], a);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int lina_layernorm_f32in_fwd(const float *x, const float *gamma, const float *beta, void *y, float *mean,
+                                        float *rstd, int M, int N, float eps, int out_dtype, void *stream) {
+    LINA_REQUIRE(x && gamma && beta && y && mean && rstd && M > 0 && N > 0, LINA_ERR_BAD_ARG, "layernorm_f32in_fwd: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(out_dtype), LINA_ERR_BAD_ARG, "layernorm_f32in_fwd: unknown dtype");
+    LINA_REQUIRE(N % 4 == 0 && N / 4 <= 32 * 8 && (uintptr_t)x % 16 == 0 && (uintptr_t)gamma % 16 == 0 &&
+                     (uintptr_t)beta % 16 == 0, LINA_ERR_UNSUPPORTED,
+                 "layernorm_f32in_fwd: N=%d must be a multiple of 4, <= 1024, tensors 16-byte aligned", N);
+    LINA_DISPATCH_DTYPE(out_dtype, layernorm_f32in_fwd_kernel<T_, 8><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+                                       x, gamma, beta, (T_ *)y, mean, rstd, M, N, eps));
+    LINA_LAUNCH_OK("layernorm_f32in_fwd_kernel");
+    return LINA_OK;
+}
+
+extern "C" int lina_layernorm_f32in_bwd(const float *x, const float *gamma, const float *mean, const float *rstd,
+                                        const void *dy, float *dx, float *dgamma, float *dbeta, int M, int N, int dy_dtype,
+                                        void *stream) {
+    LINA_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta && M > 0 && N > 0, LINA_ERR_BAD_ARG,
+                 "layernorm_f32in_bwd: bad argument");
+    LINA_REQUIRE(lina_dtype_ok(dy_dtype), LINA_ERR_BAD_ARG, "layernorm_f32in_bwd: unknown dtype");
+    LINA_REQUIRE(N % 4 == 0 && N / 4 <= 32 * 8 && (uintptr_t)x % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
+                     (uintptr_t)gamma % 16 == 0, LINA_ERR_UNSUPPORTED,
+                 "layernorm_f32in_bwd: N=%d must be a multiple of 4, <= 1024, tensors 16-byte aligned", N);
+    int nblk = (M + 7) / 8;
+    if (nblk > 148) nblk = 148;                 // persistent: one 8-warp block per SM (156 registers), rows strided
+    LINA_DISPATCH_DTYPE(dy_dtype, layernorm_f32in_bwd_kernel<T_, 8><<<nblk, 256, 0, (cudaStream_t)stream>>>(
+                                      x, gamma, mean, rstd, (const T_ *)dy, dx, dgamma, dbeta, M, N));
+    LINA_LAUNCH_OK("layernorm_f32in_bwd_kernel");
+    return LINA_OK;
+}

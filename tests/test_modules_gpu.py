@@ -421,3 +421,32 @@ def test_generate_batch_with_fused_sampling_runs_and_stays_in_vocabulary(golden_
     qs, atts, stop_tokens, cuts = lm.generate_batch(g["xt"].to(DEV), batch_size=4, prompt=g["prompt"].to(DEV), max_seqlen=16,
                                                     k=10, force_max_seqlen=True, cuda_graph=True)
     assert qs.shape == (1, 4, 16) and int(qs.min()) >= 0 and int(qs.max()) < 64 + 3
+
+
+@pytest.mark.parametrize("N", [64, 1024])
+def test_autocast_layernorm_matches_torch(N):
+    """fp32-in / bf16-out LayerNorm of the autocast training path: forward equals torch's fp32 LayerNorm rounded to bf16,
+    gradients (dx, dgamma, dbeta) equal autograd through torch's LayerNorm on the same upstream gradient."""
+    from lina_speech_b200.model.base_blocks import autocast_layernorm
+    torch.manual_seed(N)
+    norm = torch.nn.LayerNorm(N).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5); norm.bias.normal_()
+    x = (torch.randn(5, 37, N, device=DEV) * 2 + 0.3).requires_grad_(True)
+    dy = torch.randn(5, 37, N, device=DEV).to(torch.bfloat16)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = autocast_layernorm(x, norm)
+    assert y.dtype == torch.bfloat16
+    ref = norm(x.detach().clone().requires_grad_(True))
+    xr = x.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (N,), norm.weight, norm.bias, norm.eps)
+    _close(y, ref, 1e-2, 8e-3, what="ln y")                      # bf16 rounding of the output
+    y.backward(dy)
+    gw, gb = norm.weight.grad.clone(), norm.bias.grad.clone()
+    norm.weight.grad = None; norm.bias.grad = None
+    ref.backward(dy.float())
+    _close(x.grad, xr.grad, 1e-4, 1e-4, what="ln dx")
+    _close(gw, norm.weight.grad, 1e-3, 1e-4, what="ln dgamma")
+    _close(gb, norm.bias.grad, 1e-3, 1e-4, what="ln dbeta")
+    # outside autocast nothing changes
+    assert autocast_layernorm(x.detach(), norm).dtype == torch.float32
