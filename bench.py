@@ -234,6 +234,22 @@ def main_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout must carry exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints
+    # its version banner there at communicator creation, whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the
+    # whole run and restored only to emit the line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        import ctypes
+        sys.stdout.flush()
+        try:
+            ctypes.CDLL(None).fflush(None)          # C stdio buffers of native libraries, while fd 1 is still stderr
+        except Exception:       # noqa: BLE001
+            pass
+        os.write(real_stdout, (line + "\n").encode())
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
@@ -400,7 +416,7 @@ def main_ours(args):
             out["train_step"] = train
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
