@@ -70,3 +70,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
+
+
+def test_new_entry_points_validate_arguments_without_a_device():
+    """the entries added for the pre-gated path, the tensor-core backward glue, the sampler and the autocast LayerNorm
+    reject bad arguments before touching CUDA (error code + message through the C ABI)."""
+    from lina_speech_b200 import _lib
+    lib = _lib.lib()
+    err = lambda: lib.lina_last_error_string().decode()
+    assert lib.lina_gla_prefill_prep_gated(None, 0, None, 0, None, 0, None, None, None, None, 0, None, None, None, None, None,
+                                           None, None, 0, 1, 8, 4, 256, 512, 4, 16.0, 0.0625, None) == -1
+    assert "null pointer" in err()
+    assert lib.lina_gla_chunk_fwd_pregated_bthd(None, None, None, None, None, 0, None, None, 1, 4, 128, 256, 512, None) == -1
+    assert lib.lina_gla_chunk_fwd_pregated(None, None, None, None, None, 0, None, None, 1, 4, 128, 256, 512, 0, 0, 0, 0, 0, 0,
+                                           None) == -1
+    assert lib.lina_gla_bwd_prep(None, None, None, None, None, None, None, None, 1, 4, 128, 256, 0, 0.0625, None) == -1
+    assert lib.lina_gla_bwd_post(None, None, None, None, None, None, None, None, None, None, None, 1, 4, 128, 256, 0, 0.0625,
+                                 None) == -1
+    assert lib.lina_topk_sample(None, 0, 1, 10, 1, 1.0, None, None, _lib.F32, None) == -1
+    assert lib.lina_layernorm_f32in_fwd(None, None, None, None, None, None, 4, 8, 1e-5, _lib.BF16, None) == -1
+    assert lib.lina_cross_entropy_rows(None, 0, None, None, None, None, 4, 8, 1, _lib.BF16, None) == -1
+    assert lib.lina_debug_set_variant(99, 1) == -1 and lib.lina_debug_set_variant(0, 0) == 0
