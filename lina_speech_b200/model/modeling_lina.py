@@ -162,11 +162,18 @@ class LinaModel(nn.Module):
     def generate_batch(self, x: Tensor, batch_size: int = 3, prompt: Optional[Tensor] = None, device: str = "cpu",
                        max_seqlen: int = 1000, k: int = 100, first_greedy_quant: int = 1, temp: float = 1.0,
                        init_state=None, force_max_seqlen: bool = False, stop_check_interval: int = 1,
-                       cuda_graph: bool = False, dist_group=None, _timing: Optional[dict] = None):
+                       cuda_graph: bool = False, dist_group=None, prefill_prompt: bool = False,
+                       _timing: Optional[dict] = None):
         """modeling_lina.py:112-192.  Returns (qs [q,b,steps], atts [b,2,steps,n], stop_tokens, cuts).
 
         With ``dist_group`` every rank passes its LOCAL ``batch_size``; qs / stop_tokens / cuts come back
-        for the GLOBAL batch (rank-major), atts stay local."""
+        for the GLOBAL batch (rank-major), atts stay local.
+
+        ``prefill_prompt`` (new, opt-in; the reference teacher-forces the prompt one token per step): the start
+        token and the prompt go through ONE multi-token pass of every block with the cache -- the chunkwise GLA kernels,
+        conv tails and the cross attention's pos_net state end where the token-by-token loop would leave them -- and the
+        loop starts at the first free position.  Outputs keep their shape (the positions inside the prompt are sampled
+        from the same logits as in the loop)."""
         if device == "cpu":
             device = next(self.parameters()).device            # no CPU path: follow the weights
         x = repeat(x, "n -> b n", b=batch_size).to(device)
@@ -223,7 +230,23 @@ class LinaModel(nn.Module):
             _timing["start"].record()
         qs, atts, stop_tokens = [], [], []
         all_stop = torch.zeros(batch_size * world, 1, device=device, dtype=torch.bool)
-        for t in range(max_seqlen):
+        t_start = 0
+        if prefill_prompt and exists(prompt) and p_len > 0:
+            n_pre = min(p_len + 1, max_seqlen)                      # inputs of steps 0 .. p_len: start token, then the prompt
+            y_seq = torch.cat([y_embd, prompt[:, :n_pre - 1]], dim=1)
+            y_out, att_pre, _ = self.attentive_rnn.step(y_seq, x_enc, 0, state)
+            logits_pre = self.logits_head(y_out)
+            for t in range(n_pre):
+                q_sampled = self._sample(logits_pre[:, t:t + 1], k, first_greedy_quant, temp)
+                atts.append(att_pre[:, :, t:t + 1] if att_pre is not None else None)
+                q_all = gather_tokens(q_sampled, dist_group) if dist_group is not None else q_sampled
+                qs.append(q_all)
+                is_stop = (q_all == stop_token).prod(dim=0)
+                stop_tokens.append(is_stop)
+                all_stop.logical_or_(is_stop.bool())
+            y_embd = self.rvq_embed(q_sampled).sum(0)               # first free position: fed with the last sampled token
+            t_start = n_pre
+        for t in range(t_start, max_seqlen):
             if graph is not None:
                 y_buf.copy_(y_embd)
                 graph.replay()

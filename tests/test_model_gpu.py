@@ -115,3 +115,17 @@ def test_initial_state_tuning_loop_reduces_the_loss(golden_model):
     assert all(torch.equal(w0[k], v) for k, v in lm.state_dict().items())                # weights untouched
     sd = speaker_state_dict(params)
     assert set(sd) == {f"layer{i}_{s}" for i in range(4) for s in "kv"} and not lm.training
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_prompt_prefill_equals_token_by_token_teacher_forcing(golden_model, graph):
+    """generate_batch(prefill_prompt=True): start token + prompt in ONE multi-token pass with the cache (chunkwise GLA, conv
+    tails, pos_net state) must continue exactly like the reference's token-by-token teacher forcing (model/modeling_lina.py:
+    152-179): same greedy ids (also the golden ones), same attention maps, same stop flags."""
+    g, lm = golden_model, _tiny(golden_model)
+    kw = dict(batch_size=3, prompt=g["prompt"].to(DEV), max_seqlen=24, k=1, force_max_seqlen=True, cuda_graph=graph)
+    qs0, atts0, st0, _ = lm.generate_batch(g["xt"].to(DEV), **kw)
+    qs1, atts1, st1, cuts1 = lm.generate_batch(g["xt"].to(DEV), prefill_prompt=True, **kw)
+    assert torch.equal(qs1, qs0) and torch.equal(qs1.cpu(), g["qs"]), "prefilled prompt changes the greedy continuation"
+    _close(atts1, atts0, 1e-4, what="atts (prefill vs steps)")
+    assert torch.equal(st1, st0) and len(cuts1) == 3
