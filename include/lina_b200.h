@@ -298,6 +298,9 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
 int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);
+/* Round-2 bring-up (not yet run on hardware): M x N x 16 MMAs with M in {64,128}, no-swizzle K-major operands; D receives the
+ * RAW accumulator tile [128 TMEM lanes][N] (cells the MMA did not write hold -12345) so the M = 64 lane mapping can be read. */
+int lina_debug_umma_probe_m(const float *A, const float *B, float *D, int M, int N, int KD, void *stream);
 /* Same with 128-byte-swizzled operands (a_mode / b_mode: 0 K-major, 1 MN-major); use_tma != 0 loads A from
  * A_bf16 [128,KD] through a 2-D tensor map with CU_TENSOR_MAP_SWIZZLE_128B instead of writing it by hand. */
 int lina_debug_umma_probe_sw128(const float *A, const float *B, float *D, const void *A_bf16, int N, int KD,

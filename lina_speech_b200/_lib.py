@@ -68,6 +68,7 @@ PROTOTYPES = {
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
     "lina_debug_set_variant": (_i, [_i, _i]),
     "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
+    "lina_debug_umma_probe_m": (_i, [_p] * 3 + [_i] * 3 + [_p]),
     "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
     "lina_debug_umma_timing": (_i, [_p] + [_i] * 6 + [_p]),
     "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),

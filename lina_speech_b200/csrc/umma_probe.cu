@@ -102,6 +102,80 @@ extern "C" int lina_debug_umma_probe(const float *A, const float *B, float *D, i
     return LINA_OK;
 }
 
+// ---- M = 64 layout probe (round-2 bring-up, NOT yet run on hardware): same no-swizzle K-major operands, instruction shape
+// M x N x 16 with M in {64, 128}; dumps the RAW accumulator tile -- all 128 TMEM lanes x N columns -- so that the lane mapping
+// of an M = 64 accumulator can be read off (profiles/probe_m64.py).  Motivation: the score MMA of the GLA kernel needs only
+// its 64 q~ rows; at M = 128 half of its shared-memory A reads (the kernel's binding resource) are a by-product.
+namespace {
+
+__global__ void __launch_bounds__(128)
+umma_probe_m_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ D, int M, int N, int KD) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t gA_k = (M + 1) * 16, gB_k = (N + 1) * 16;
+    uint8_t *a_tile = smem, *b_tile = smem + 40 * 1024;
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = tid; i < M * KD; i += 128) {
+        const int m = i / KD, k = i % KD;
+        *reinterpret_cast<bf16 *>(a_tile + (k / 8) * gA_k + m * 16 + (k % 8) * 2) = __float2bfloat16_rn(A[i]);
+    }
+    for (int i = tid; i < N * KD; i += 128) {
+        const int n = i / KD, k = i % KD;
+        *reinterpret_cast<bf16 *>(b_tile + (k / 8) * gB_k + n * 16 + (k % 8) * 2) = __float2bfloat16_rn(Bm[i]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    {   // poison the tile so untouched cells are recognisable
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(-12345.f);
+        for (int c0 = 0; c0 < N; c0 += 32) tmem_st32(tbase + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_st_wait();
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0 && elect_one_sync()) {
+        const uint32_t idesc = idesc_bf16(M, N, 0, 0);
+        for (int ks = 0; ks < KD / 16; ++ks)
+            mma_ss(tbase, smem_desc(smem_u32(a_tile) + ks * 2 * gA_k, gA_k, 128), smem_desc(smem_u32(b_tile) + ks * 2 * gB_k, gB_k, 128),
+                   idesc, ks > 0);
+        mma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+}  // namespace
+
+extern "C" int lina_debug_umma_probe_m(const float *A, const float *B, float *D, int M, int N, int KD, void *stream) {
+    LINA_REQUIRE(A && B && D, LINA_ERR_BAD_ARG, "umma_probe_m: null pointer");
+    LINA_REQUIRE((M == 64 || M == 128) && N % 32 == 0 && N >= 32 && N <= 256 && KD % 16 == 0 && KD >= 16 && KD <= 128,
+                 LINA_ERR_BAD_ARG, "umma_probe_m: need M in {64,128}, N in [32,256] %% 32, KD in [16,128] %% 16");
+    const int smem = 120 * 1024;
+    LINA_CUDA_OK(cudaFuncSetAttribute(umma_probe_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_probe_m_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, M, N, KD);
+    LINA_LAUNCH_OK("umma_probe_m_kernel");
+    return LINA_OK;
+}
+
 // ---- second probe: 128-byte-swizzled operands (K-major / MN-major) and a TMA-loaded A ----------------------
 #include "tma.cuh"
 
