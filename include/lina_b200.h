@@ -294,7 +294,8 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16,
  * key 4 = 1 runs the pre-gated GLA kernel's state pass on one warpgroup, key 5 = 1 selects the round-1 short-conv backward,
  * key 6 = 1 gives the pre-gated GLA kernel three operand stages + one v stage (default 2 + 2), key 7 = 1 turns on its
- * cluster-multicast operand loads. */
+ * cluster-multicast operand loads, key 8 = 1 routes lina_codec_istft_head (n_fft = 1280) to the warp-per-frame fixed-radix
+ * FFT kernel (csrc/fft640.cuh; index arithmetic checked on the host, kernel not yet run on hardware). */
 int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);

@@ -8,6 +8,9 @@
 //   dwconv_adaln fuses the depthwise conv, the transpose and the (Ada)LayerNorm in one pass over x;
 //   scale_residual_t fuses gamma*h, the transpose back and the residual add.
 #include "common.cuh"
+#include "fft640.cuh"
+
+extern int g_lina_variant[16];
 
 namespace {
 
@@ -497,6 +500,34 @@ istft_frames_kernel(const float *__restrict__ h, const float *__restrict__ windo
     }
 }
 
+// n_fft = 1280: one warp per frame, fixed radices 10 * 4 * 4 * 4 (csrc/fft640.cuh holds the phases and their rationale).
+// 8 warps per CTA, 97 KB of shared memory (15 KB of tables + 10 KB per warp), 2 CTAs per SM.
+constexpr int F640_WARPS = 8;
+constexpr size_t F640_SMEM = (size_t)(fft640::TABLE_FLOATS + F640_WARPS * fft640::WARP_FLOATS) * sizeof(float);
+
+__global__ void __launch_bounds__(F640_WARPS * 32)
+istft_frames_1280_kernel(const float *__restrict__ h, const float *__restrict__ window, float *__restrict__ frames, int nframes) {
+    using namespace fft640;
+    extern __shared__ float smem[];
+    float *tab = smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < TABLE_FLOATS; i += F640_WARPS * 32) tab[i] = table_entry(i, window);
+    __syncthreads();
+    float *re0 = smem + TABLE_FLOATS + warp * WARP_FLOATS, *im0 = re0 + NBINS, *re1 = im0 + NBINS, *im1 = re1 + M;
+    for (int f = blockIdx.x * F640_WARPS + warp; f < nframes; f += gridDim.x * F640_WARPS) {
+        phase_polar(lane, h + (size_t)f * (N + 2), re0, im0);
+        __syncwarp();
+        phase_r10(lane, re0, im0, tab, re1, im1);
+        __syncwarp();
+        phase_r4<10>(lane, re1, im1, tab, T_ST2, re0, im0);
+        __syncwarp();
+        phase_r4<40>(lane, re0, im0, tab, T_ST3, re1, im1);
+        __syncwarp();
+        phase_r4_out(lane, re1, im1, tab, frames + (size_t)f * N);
+        __syncwarp();                                   // the next frame's polar phase overwrites re0 / im0
+    }
+}
+
 // overlap-add + trim + envelope normalisation (spectral_ops.py:60-73)
 __global__ void __launch_bounds__(256)
 istft_ola_kernel(const float *__restrict__ frames, const float *__restrict__ window, float *__restrict__ wav,
@@ -675,6 +706,20 @@ extern "C" int lina_codec_istft_head(const float *h, const float *window, float 
     LINA_REQUIRE(B <= 65535, LINA_ERR_UNSUPPORTED, "istft_head: B > 65535");
     cudaStream_t st = (cudaStream_t)stream;
     const int nframes = B * L;
+    if (g_lina_variant[8] == 1 && n_fft == fft640::N && (uintptr_t)ws % 8 == 0) {
+        static thread_local bool configured = false;
+        if (!configured) {
+            LINA_CUDA_OK(cudaFuncSetAttribute(istft_frames_1280_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F640_SMEM));
+            configured = true;
+        }
+        const int want = (nframes + F640_WARPS - 1) / F640_WARPS;
+        istft_frames_1280_kernel<<<want < 148 * 2 ? want : 148 * 2, F640_WARPS * 32, F640_SMEM, st>>>(h, window, (float *)ws, nframes);
+        LINA_LAUNCH_OK("istft_frames_1280_kernel");
+        dim3 g2((L * hop + 255) / 256, B);
+        istft_ola_kernel<<<g2, 256, 0, st>>>((const float *)ws, window, wav, L, n_fft, hop);
+        LINA_LAUNCH_OK("istft_ola_kernel");
+        return LINA_OK;
+    }
     const int grid = nframes < 148 * 16 ? nframes : 148 * 16;
     istft_frames_kernel<<<grid, 128, smem, st>>>(h, window, (float *)ws, nframes, plan);
     LINA_LAUNCH_OK("istft_frames_kernel");

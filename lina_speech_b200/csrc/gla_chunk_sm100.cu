@@ -39,7 +39,7 @@
 
 using namespace sm100;
 
-extern int g_lina_variant[8];
+extern int g_lina_variant[16];
 
 int lina_gla_recurrent_fwd_impl(const void *q, const void *k, const void *v, const void *gk, const void *h0,
                                 int h0_dtype, void *o, float *ht, int B, int H, int T, int K, int V, int dtype,

@@ -12,10 +12,10 @@
 #include "sm100.cuh"
 #include "packed.cuh"
 
-int g_lina_variant[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_lina_variant[16] = {0};
 
 extern "C" int lina_debug_set_variant(int key, int value) {
-    if (key < 0 || key >= 8) return LINA_ERR_BAD_ARG;
+    if (key < 0 || key >= 16) return LINA_ERR_BAD_ARG;
     g_lina_variant[key] = value;
     return LINA_OK;
 }

@@ -10,7 +10,7 @@
 #include "sm100.cuh"
 #include "packed.cuh"
 
-extern int g_lina_variant[8];
+extern int g_lina_variant[16];
 // gla_prep.cu: TL-row tiles, all loads of a thread issued up front (the production W == 4 path)
 int lina_short_conv4_tiles(const void *x, long long ldx, const void *w, void *y, void *cache, int cache_dtype, int B,
                            int L, int D, int silu, int dtype, void *stream);

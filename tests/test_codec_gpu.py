@@ -1,4 +1,5 @@
 """GPU parity of the WavTokenizer decode path against the reference's golden waveforms and the oracle."""
+import os
 import pytest
 import torch
 
@@ -67,6 +68,27 @@ def test_istft_head_alone_against_torch_irfft():
     ref = CO.istft_head(sd, x.cpu(), 320)
     err = (wav.cpu() - ref).abs().max().item()
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), f"istft max err {err:.3e} (ref absmax {ref.abs().max():.2f})"
+
+
+@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="kernel variants compiled but not yet run on hardware")
+def test_istft_warp_per_frame_kernel_matches_the_generic_one():
+    """variant key 8: the fixed-radix warp-per-frame FFT (csrc/fft640.cuh; host-checked in tests/test_host.py)."""
+    from lina_speech_b200.codec import ISTFTHead
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(1)
+    head = ISTFTHead(32, 1280, 320).to(DEV)
+    with torch.no_grad():
+        head.out.weight.mul_(30.0)
+        head.out.bias.normal_()
+    x = torch.randn(5, 77, 32, device=DEV)
+    base = head(x)
+    L.lib().lina_debug_set_variant(8, 1)
+    try:
+        wav = head(x)
+    finally:
+        L.lib().lina_debug_set_variant(8, 0)
+    err = (wav - base).abs().max().item()
+    assert err <= 2e-5 * max(1.0, base.abs().max().item()), f"max diff {err:.3e}"
 
 
 def test_tf32_gemm_mode_stays_close(golden_codec):

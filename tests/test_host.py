@@ -98,3 +98,28 @@ def test_backward_through_the_forward_kernel_host_logic(B, H, T, K, V, with_stat
     for name, a, b in zip(("dq", "dk", "dv", "dgk", "dh0"), got, ref):
         err = (a.double() - b).abs().max().item() / b.abs().max().item()
         assert err < 5e-6, f"{name}: relative error {err:.2e}"       # fp32 intermediates inside _bwd_tc
+
+
+def test_istft_fft640_device_phases_on_the_host(tmp_path):
+    """csrc/fft640.cuh (the warp-per-frame ISTFT kernel's phases) compiled for the host and run lane by lane:
+    polar -> 640-point complex FFT (10*4*4*4) -> windowed frame, against numpy's irfft (DEC/spectral_ops.py:57-58)."""
+    import ctypes, os, shutil, subprocess
+    import numpy as np
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "libfft640.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "host_fft640.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    rng = np.random.default_rng(1)
+    F = 9
+    h = np.concatenate([rng.standard_normal((F, 641)) * 1.5, rng.uniform(-6, 6, (F, 641))], 1).astype(np.float32)
+    h[0, :641] = 8.0                                    # exercises the clip at 100
+    win = torch.hann_window(1280).numpy().astype(np.float32)
+    out = np.zeros((F, 1280), np.float32)
+    P = ctypes.POINTER(ctypes.c_float)
+    assert lib.fft640_frames(h.ctypes.data_as(P), win.ctypes.data_as(P), out.ctypes.data_as(P), F) == 0
+    mag = np.minimum(np.exp(h[:, :641].astype(np.float64)), 100.0)
+    X = mag * np.exp(1j * h[:, 641:].astype(np.float64))
+    ref = np.fft.irfft(X, n=1280, axis=1) * win
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max() + 2e-6
