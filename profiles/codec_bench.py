@@ -70,6 +70,16 @@ wav = torch.empty(B, Ln * HOP, device=dev)
 ws = torch.empty(int(lib.lina_codec_istft_workspace_bytes(B, Ln, NFFT)), dtype=torch.uint8, device=dev)
 report("istft_head (polar + irfft1280 + window + OLA)", timeit(lambda: check(lib.lina_codec_istft_head(L.ptr(hh), L.ptr(win), L.ptr(wav), L.ptr(ws), B, Ln, NFFT, HOP, st()))),
        hh.numel() * 4 + wav.numel() * 4)
+if os.environ.get("LINA_BRINGUP"):                      # variant key 8: warp-per-frame fixed-radix FFT (not yet run on hardware)
+    wav0 = wav.clone()
+    lib.lina_debug_set_variant(8, 1)
+    try:
+        report("istft_head, warp-per-frame FFT (variant 8)", timeit(lambda: check(lib.lina_codec_istft_head(L.ptr(hh), L.ptr(win), L.ptr(wav), L.ptr(ws), B, Ln, NFFT, HOP, st()))),
+               hh.numel() * 4 + wav.numel() * 4)
+        res["istft variant 8 max diff"] = float((wav - wav0).abs().max())
+        print("istft variant 8 max diff vs default:", res["istft variant 8 max diff"], flush=True)
+    finally:
+        lib.lina_debug_set_variant(8, 0)
 codes = torch.randint(0, 4096, (1, B, Ln), device=dev)
 books = torch.randn(4096, 512, device=dev)
 feat = torch.empty(B, 512, Ln, device=dev)
