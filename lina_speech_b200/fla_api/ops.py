@@ -366,12 +366,20 @@ def fused_recurrent_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, gk: t
                         gv: torch.Tensor = None, scale: Optional[float] = None,
                         initial_state: torch.Tensor = None, output_final_state: bool = False,
                         reverse: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """FLA/fla/ops/gla/recurrent_fuse.py:13-27.  ``gv`` / ``reverse`` / ``gk=None`` are generic
-    fla options Lina never uses (model/gla.py:187-203); they raise instead of silently differing."""
-    if gv is not None or reverse or gk is None:
-        raise NotImplementedError("lina_speech_b200.fused_recurrent_gla: only the (q,k,v,gk) causal form used by "
-                                  "model/gla.py is implemented (no gv, no reverse, gk required)")
-    return _GLAFunction.apply(q, k, v, gk, _scale(scale, q.shape[-1]), initial_state, output_final_state, "recurrent")
+    """FLA/fla/ops/gla/recurrent_fuse.py:13-27.  ``gk=None`` is the ungated recurrence (zero log-gates);
+    ``reverse=True`` runs the recurrence from t = T-1 down to 0 (common/fused_recurrent.py:44-51: pointers start at the
+    last step and walk backwards) -- served by the same kernels on time-flipped operands, the flips being ordinary
+    differentiable torch ops.  ``gv`` (value-side gates) is a generic fla option Lina never uses (model/gla.py:187-203);
+    it raises instead of silently differing."""
+    if gv is not None:
+        raise NotImplementedError("lina_speech_b200.fused_recurrent_gla: value-side gates (gv) are not implemented; "
+                                  "model/gla.py only uses the (q, k, v, gk) form")
+    if gk is None:
+        gk = torch.zeros_like(q)
+    if reverse:
+        q, k, v, gk = (x.flip(2) for x in (q, k, v, gk))
+    o, ht = _GLAFunction.apply(q, k, v, gk, _scale(scale, q.shape[-1]), initial_state, output_final_state, "recurrent")
+    return (o.flip(2) if reverse else o), ht
 
 
 def fused_chunk_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, scale: float = -1,

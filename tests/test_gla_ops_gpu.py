@@ -295,3 +295,30 @@ def test_tensor_core_backward(K, V, T, with_state, layout):
         _assert_close(leaf.grad, r, 0.0, 3e-2, what=f"{name} K={K} T={T}")
     if with_state:
         _assert_close(h0d.grad, ref[4], 0.0, 2e-2, what="dh0")
+
+
+def test_fused_recurrent_reverse_and_ungated_forms():
+    """recurrent_fuse.py:13-27 options outside Lina's use: ``reverse=True`` (time runs T-1 -> 0) and ``gk=None`` (no decay),
+    forward + gradients against the oracle on explicitly flipped / zero-gated inputs."""
+    from lina_speech_b200.fla_api import fused_recurrent_gla
+    torch.manual_seed(42)
+    B, H, T, K, V = 2, 2, 37, 32, 64
+    q, k, gk = torch.randn(B, H, T, K), torch.randn(B, H, T, K), F.logsigmoid(torch.randn(B, H, T, K)) / 4
+    v, h0, do = torch.randn(B, H, T, V), torch.randn(B, H, K, V), torch.randn(B, H, T, V)
+    # reverse
+    ro, rht = GO.recurrent_gla(q.flip(2), k.flip(2), v.flip(2), gk.flip(2), initial_state=h0, acc_dtype=torch.float64)
+    leaves = [x.to(DEV).requires_grad_(True) for x in (q, k, v, gk)]
+    o, ht = fused_recurrent_gla(*leaves, initial_state=h0.to(DEV), output_final_state=True, reverse=True)
+    _assert_close(o, ro.flip(2), 1e-4, what="reverse o")
+    _assert_close(ht, rht, 1e-4, what="reverse ht")
+    (o * do.to(DEV)).sum().backward()
+    dq, dk, dv, dgk, _ = GO.recurrent_gla_bwd(q.flip(2), k.flip(2), v.flip(2), gk.flip(2), h0, do.flip(2))
+    for got, ref, name in zip(leaves, (dq, dk, dv, dgk), "q k v gk".split()):
+        _assert_close(got.grad, ref.flip(2), 1e-3, 1e-3, what=f"reverse d{name}")
+    # no gates
+    ro, rht = GO.recurrent_gla(q, k, v, torch.zeros_like(q), initial_state=None, acc_dtype=torch.float64)
+    o, ht = fused_recurrent_gla(q.to(DEV), k.to(DEV), v.to(DEV), output_final_state=True)
+    _assert_close(o, ro, 2e-4, what="ungated o")
+    _assert_close(ht, rht, 2e-4, what="ungated ht")
+    with pytest.raises(NotImplementedError):
+        fused_recurrent_gla(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), gv=torch.zeros_like(v).to(DEV))
