@@ -401,13 +401,31 @@ def chunk_gla(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor
     return _GLAFunction.apply(q, k, v, g, _scale(scale, q.shape[-1]), initial_state, output_final_state, "chunk")
 
 
+def _rwkv6_through_gla(r, k, v, w, u, scale: float, initial_state, output_final_state: bool, kind: str):
+    """RWKV6 with gradients, as the GLA operator on shifted queries plus the bonus term:
+      o_t = scale r_t S_{t-1} + scale (r_t . u . k_t) v_t,   S_t = e^{w_t} S_{t-1} + k_t^T v_t
+    and GLA with q'_s = r_{s+1} returns scale r_{s+1} S_s at step s, i.e. o's state part shifted by one step; step 0 reads
+    the initial state.  Everything around the op is differentiable torch, so dr, dk, dv, dw, du and dh0 come from the GLA
+    backward (tensor cores for bf16 at Lina's head sizes).  FLA/fla/ops/rwkv6/recurrent_naive.py:8-42 is the spec."""
+    B, H, T, K = r.shape
+    q_shift = torch.cat([r[:, :, 1:], r.new_zeros(B, H, 1, K)], dim=2)
+    o_g, ht = _GLAFunction.apply(q_shift, k, v, w, scale, initial_state, output_final_state, kind)
+    if initial_state is not None:
+        first = scale * torch.einsum("bhk,bhkv->bhv", r[:, :, 0].float(), initial_state.float()).unsqueeze(2)
+    else:
+        first = torch.zeros(B, H, 1, v.shape[-1], dtype=torch.float32, device=v.device)
+    bonus = scale * (r.float() * u.float()[None, :, None, :] * k.float()).sum(-1, keepdim=True) * v.float()
+    o = torch.cat([first, o_g[:, :, :-1].float()], dim=2) + bonus
+    return o.to(v.dtype), ht
+
+
 def fused_recurrent_rwkv6(r: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w: torch.Tensor, u: torch.Tensor,
                           scale: float = -1, initial_state: torch.Tensor = None, output_final_state: bool = False
                           ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """FLA/fla/ops/rwkv6/recurrent_fuse.py:335-368, forward only (inference): ``w`` are log-space decays, ``u`` [H,K]
-    the bonus.  Gradients are not implemented (the only caller, model/rwkv6.py, is stale upstream -- SURVEY D6)."""
-    if any(t.requires_grad for t in (r, k, v, w, u)) and torch.is_grad_enabled():
-        raise NotImplementedError("lina_speech_b200.fused_recurrent_rwkv6 is forward-only")
+    """FLA/fla/ops/rwkv6/recurrent_fuse.py:335-368: ``w`` are log-space decays, ``u`` [H,K] the bonus.  Without autograd one
+    dedicated kernel; when a gradient is required the op runs as GLA on shifted queries (:func:`_rwkv6_through_gla`)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (r, k, v, w, u, initial_state)):
+        return _rwkv6_through_gla(r, k, v, w, u, _scale(scale, r.shape[-1]), initial_state, output_final_state, "recurrent")
     L.require_cuda(r, k, v, w, u, initial_state)
     odt = v.dtype
     if not (r.dtype == k.dtype == v.dtype == w.dtype == u.dtype):
@@ -428,5 +446,8 @@ def fused_recurrent_rwkv6(r: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w: 
 
 def chunk_rwkv6(r, k, v, g, u, scale: float = -1, initial_state=None, output_final_state: bool = False,
                 checkpoint_level: Optional[int] = 0):
-    """FLA/fla/ops/rwkv6/chunk.py:803- : same function as the recurrent form; served by the same kernel."""
+    """FLA/fla/ops/rwkv6/chunk.py:803- : same function as the recurrent form.  Inference: the same dedicated kernel; with
+    autograd: the chunkwise GLA operator on shifted queries."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (r, k, v, g, u, initial_state)):
+        return _rwkv6_through_gla(r, k, v, g, u, _scale(scale, r.shape[-1]), initial_state, output_final_state, "chunk")
     return fused_recurrent_rwkv6(r, k, v, g, u, scale, initial_state, output_final_state)

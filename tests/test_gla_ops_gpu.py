@@ -322,3 +322,26 @@ def test_fused_recurrent_reverse_and_ungated_forms():
     _assert_close(ht, rht, 2e-4, what="ungated ht")
     with pytest.raises(NotImplementedError):
         fused_recurrent_gla(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), gv=torch.zeros_like(v).to(DEV))
+
+
+@pytest.mark.parametrize("op", ["fused_recurrent_rwkv6", "chunk_rwkv6"])
+def test_rwkv6_gradients(op):
+    """a13 with autograd: RWKV6 as the GLA operator on shifted queries + bonus; every gradient (r, k, v, w, u, h0) against
+    torch autograd through the oracle's restatement of recurrent_naive.py:8-42 in fp64."""
+    import lina_speech_b200.fla_api as A
+    fn = getattr(A, op)
+    torch.manual_seed(42)
+    B, H, T, K, V = 2, 2, 70, 32, 64
+    r, k, v = torch.randn(B, H, T, K), torch.randn(B, H, T, K), torch.randn(B, H, T, V)
+    w, u, h0 = -torch.exp(torch.randn(B, H, T, K) - 1.5), torch.randn(H, K), torch.randn(B, H, K, V)
+    do, dht = torch.randn(B, H, T, V), torch.randn(B, H, K, V)
+    ref_leaves = [x.double().requires_grad_(True) for x in (r, k, v, w, u, h0)]
+    ro, rht = GO.recurrent_rwkv6(*ref_leaves[:5], initial_state=ref_leaves[5], acc_dtype=torch.float64)
+    ((ro * do).sum() + (rht.double() * dht).sum()).backward()
+    leaves = [x.to(DEV).requires_grad_(True) for x in (r, k, v, w, u, h0)]
+    o, ht = fn(*leaves[:5], initial_state=leaves[5], output_final_state=True)
+    _assert_close(o, ro, 2e-4, what=f"{op} o")
+    _assert_close(ht, rht, 2e-4, what=f"{op} ht")
+    ((o * do.to(DEV)).sum() + (ht * dht.to(DEV)).sum()).backward()
+    for got, ref, name in zip(leaves, ref_leaves, "r k v w u h0".split()):
+        _assert_close(got.grad, ref.grad, 1e-3, 1e-3, what=f"{op} d{name}")
