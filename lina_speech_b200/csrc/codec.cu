@@ -615,11 +615,10 @@ static int launch_dwconv_adaln(const float *x, const float *dw_w, const float *d
     const int TL = conv ? 26 : 32;
     const size_t smem = ((size_t)TL * (C + 1) + (conv ? (size_t)C * 41 : 0)) * sizeof(float);
     LINA_REQUIRE(smem <= 227 * 1024, LINA_ERR_UNSUPPORTED, "dwconv_adaln: C=%d too large for shared memory", C);
-    static thread_local size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[conv]) {
-        if (conv) LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[conv] = smem;
+    static thread_local uint64_t configured[2] = {0, 0};
+    if (lina_first_use_on_device(&configured[conv])) {            // once per device: allow the whole 227 KB
+        if (conv) LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else LINA_CUDA_OK(cudaFuncSetAttribute(dwconv_adaln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     dim3 grid((L + TL - 1) / TL, B);
     if (conv) dwconv_adaln_kernel<true><<<grid, DW_THREADS, smem, st>>>(x, dw_w, dw_b, scale, shift, y, C, L, eps);
@@ -707,11 +706,9 @@ extern "C" int lina_codec_istft_head(const float *h, const float *window, float 
     cudaStream_t st = (cudaStream_t)stream;
     const int nframes = B * L;
     if (g_lina_variant[8] == 1 && n_fft == fft640::N && (uintptr_t)ws % 8 == 0) {
-        static thread_local bool configured = false;
-        if (!configured) {
+        static thread_local uint64_t configured = 0;
+        if (lina_first_use_on_device(&configured))
             LINA_CUDA_OK(cudaFuncSetAttribute(istft_frames_1280_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F640_SMEM));
-            configured = true;
-        }
         const int want = (nframes + F640_WARPS - 1) / F640_WARPS;
         istft_frames_1280_kernel<<<want < 148 * 2 ? want : 148 * 2, F640_WARPS * 32, F640_SMEM, st>>>(h, window, (float *)ws, nframes);
         LINA_LAUNCH_OK("istft_frames_1280_kernel");

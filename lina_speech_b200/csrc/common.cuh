@@ -38,6 +38,17 @@ void lina_set_error(const char *fmt, ...);
         }                                                                                    \
     } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device only: a call site remembers per device (bit = ordinal mod 64) whether
+// it has configured its kernel.  Usage: static thread_local uint64_t done = 0; if (lina_first_use_on_device(&done)) {...}
+static inline bool lina_first_use_on_device(uint64_t *done_mask) {
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (*done_mask & bit) return false;
+    *done_mask |= bit;
+    return true;
+}
+
 // ---- dtype conversion -------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T x);
 template <> __device__ __forceinline__ float to_f<float>(float x) { return x; }

@@ -553,12 +553,10 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
            float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr,
            const float *decay = nullptr, int ldq = 0, int ldk = 0, int ldv = 0) {
     using cfg = Cfg<K>;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local uint64_t configured = 0;
+    if (lina_first_use_on_device(&configured))
         LINA_CUDA_OK(cudaFuncSetAttribute(gla_chunk_fwd_sm100_kernel<K, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)cfg::SMEM));
-        configured = true;
-    }
     // 4-D views (innermost first) (D, T, H, B) of [B,H,T,D] (bthd == 0) or [B,T,H,D] (bthd == 1) tensors;
     // 64 x 64 boxes over (D, T); rows past T read as zero.
     TMaps tm;
