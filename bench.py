@@ -125,18 +125,11 @@ def _cpu_reference_setup():
     if _CPU_REF:
         return _CPU_REF
     from oracle import lina_oracle as LO
-    import lina_speech_b200.model as m
-    torch.manual_seed(0)
     c = CFG
-    rnn = m.AttentiveGLA(c["d_model"], c["n_layer"], c["heads"], blind=True, use_short_conv=True,
-                         pos_type="convolutional")
-    lm = m.LinaModel(rnn, c["d_model"], 1, c["n_codebook"], 3, 3, c["n_txt_vocab"],
-                     txt_encoder=m.TextEncoder(c["d_model"], c["txt_heads"], n_layers=c["txt_layers"], dropout=0.0,
-                                               rotary=False))
-    sd = {k: v.detach().float() for k, v in lm.state_dict().items()}
-    del lm, rnn
     cfg = {"d_model": c["d_model"], "n_layer": c["n_layer"], "heads": c["heads"], "txt_heads": c["txt_heads"],
-           "pos_type": "convolutional"}
+           "txt_layers": c["txt_layers"], "pos_type": "convolutional"}
+    # same architecture, default-initialiser scales, built by the oracle itself: nothing of the product package on this path
+    sd = LO.random_state_dict(cfg, c["n_codebook"], 3, c["n_txt_vocab"], seed=0)
     B = 2
 
     def run(T):

@@ -224,3 +224,62 @@ def lina_generate_greedy(sd: SD, cfg, x, batch_size: int, prompt=None, max_seqle
         atts.append(att)
         y_embd = prompt[:, [t]] if (prompt is not None and t < p_len) else rvq_embed(sd, tok)
     return torch.stack(qs, dim=2).squeeze(-1), torch.cat(atts, dim=2), torch.stack(all_logits)
+
+
+def random_state_dict(cfg, n_codebook: int = 4096, n_special: int = 3, n_txt_vocab: int = 256, n_quant: int = 1,
+                      seed: int = 0) -> SD:
+    """A reference-keyed fp32 state dict with the shapes of ``LinaModel(AttentiveGLA(d, n_layer, heads, blind=True,
+    use_short_conv=True, pos_type='convolutional'), ..., txt_encoder=TextEncoder(d, txt_heads, n_layers=txt_layers))``
+    (model/modeling_lina.py:24-58, model/gla.py:35-129,252-285, model/crossatt.py:61-103, model/base_blocks.py:42-62) and
+    torch's default initialisers' scales (uniform(+-1/sqrt(fan_in)) matrices, unit norms, N(0,1) embeddings).  Lets the CPU
+    baseline build its model without touching the product package; tests check keys and shapes against the host classes."""
+    g = torch.Generator().manual_seed(seed)
+    d, H = cfg["d_model"], cfg["heads"]
+    kd, vd = int(d * cfg.get("expand_k", 1.0)), int(d * cfg.get("expand_v", 2.0))
+    hid = 4 * d // 3
+    sd: SD = {}
+
+    def mat(name, out_f, in_f, bias=False):
+        sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) / math.sqrt(in_f)
+        if bias:
+            sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) / math.sqrt(in_f)
+
+    def norm(name, n):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(n), torch.zeros(n)
+
+    def cmix(p):
+        mat(p + "cmix.p_in", 2 * hid, d, True)
+        mat(p + "cmix.p_out", d, hid, True)
+
+    def block(p):
+        mat(p + "tmix.q_proj", kd, d); mat(p + "tmix.k_proj", kd, d); mat(p + "tmix.v_proj", vd, d); mat(p + "tmix.g_proj", vd, d)
+        mat(p + "tmix.gk_proj.0", 16, d); mat(p + "tmix.gk_proj.1", kd, 16, True)
+        mat(p + "tmix.o_proj", d, vd)
+        for n_, w in (("q", kd), ("k", kd), ("v", vd)):
+            sd[p + f"tmix.{n_}_conv1d.weight"] = (torch.rand(w, 1, 4, generator=g) * 2 - 1) / 2.0
+        sd[p + "tmix.g_norm_swish_gate.weight"] = torch.ones(vd // H)
+        cmix(p)
+        norm(p + "norm1", d); norm(p + "norm2", d)
+
+    for i in range(cfg.get("txt_layers", 0)):
+        p = f"txt_encoder.sa.{i}."
+        mat(p + "tmix.qkv", 3 * d, d, True)
+        cmix(p)
+        norm(p + "norm1", d); norm(p + "norm2", d)
+    for i in range(cfg["n_layer"]):
+        block(f"attentive_rnn.encoder.{i}.")
+    for i in range(cfg["n_layer"]):
+        block(f"attentive_rnn.decoder.{i}.")
+    ca = "attentive_rnn.cross_att."
+    for n_ in "qkv":
+        mat(ca + n_, d, d, True)
+    block(ca + "pos_net.")
+    sd[ca + "pos_embed.embed.weight"] = torch.randn(2000, d, generator=g)
+    sd[ca + "pos_embed.dw_conv.weight"] = (torch.rand(d, 1, 31, generator=g) * 2 - 1) / math.sqrt(31)
+    sd[ca + "pos_embed.dw_conv.bias"] = (torch.rand(d, generator=g) * 2 - 1) / math.sqrt(31)
+    for n_ in "qkv":
+        norm(ca + "ln_" + n_, d)
+    sd["txt_embed.weight"] = torch.randn(n_txt_vocab, d, generator=g)
+    sd["rvq_embed.weight"] = torch.randn(n_quant, n_codebook + n_special, d, generator=g)
+    sd["logits_head.weight"] = torch.randn(n_quant, n_codebook + n_special, d, generator=g) / math.sqrt(d)
+    return sd

@@ -119,3 +119,23 @@ def test_rwkv6_recurrence_matches_reference(request):
         c = _case(g, ci)
         o, ht = GO.recurrent_rwkv6(c["r"], c["k"], c["v"], c["w"], c["u"], initial_state=c.get("h0"))
         assert torch.allclose(o, c["o"], atol=1e-5, rtol=1e-5) and torch.allclose(ht, c["ht"], atol=1e-4, rtol=1e-5)
+
+
+def test_random_state_dict_has_the_host_classes_keys_and_shapes():
+    """bench.py's CPU arm builds its model from oracle.lina_oracle.random_state_dict alone; it must describe the same
+    architecture as the host mirror of LinaModel (model/modeling_lina.py:24-58) and run through lina_forward."""
+    import torch
+    from oracle import lina_oracle as LO
+    import lina_speech_b200.model as m
+    d, nl, h = 64, 2, 2
+    rnn = m.AttentiveGLA(d, nl, h, blind=True, use_short_conv=True, pos_type="convolutional")
+    lm = m.LinaModel(rnn, d, 1, 4096, 3, 3, 256, txt_encoder=m.TextEncoder(d, 2, n_layers=1, dropout=0.0, rotary=False))
+    cfg = {"d_model": d, "n_layer": nl, "heads": h, "txt_heads": 2, "txt_layers": 1, "pos_type": "convolutional"}
+    sd = LO.random_state_dict(cfg, 4096, 3, 256)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in lm.state_dict().items()}
+    x = torch.randint(3, 256, (2, 9))
+    y = torch.randint(3, 4099, (2, 12, 1))
+    em = torch.ones(2, 9, 9, dtype=torch.bool)
+    cm = torch.ones(2, 12, 9, dtype=torch.bool)
+    logits, loss = LO.lina_forward(sd, cfg, x, y, em, cm)[:2]
+    assert torch.isfinite(logits).all() and torch.isfinite(loss)
