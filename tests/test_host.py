@@ -123,3 +123,26 @@ def test_istft_fft640_device_phases_on_the_host(tmp_path):
     X = mag * np.exp(1j * h[:, 641:].astype(np.float64))
     ref = np.fft.irfft(X, n=1280, axis=1) * win
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max() + 2e-6
+
+
+def test_reverse_and_rwkv6_host_logic_with_the_kernel_stubbed_by_the_oracle(monkeypatch):
+    """fused_recurrent_gla(reverse=True / gk=None) and the RWKV6-through-GLA composition are pure host logic around the GLA
+    operator: run the GPU tests' own bodies on the CPU with _GLAFunction replaced by the oracle recurrence (autograd through
+    torch), so flips, the one-step query shift, the bonus term and every gradient path are checked without a device."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import gla_oracle as GO
+    import lina_speech_b200.fla_api.ops as O
+    import test_gla_ops_gpu as T
+
+    class OracleGLA:
+        @staticmethod
+        def apply(q, k, v, gk, scale, h0, want_ht, kind):
+            o, ht = GO.recurrent_gla(q, k, v, gk, scale=scale, initial_state=h0)
+            return o, (ht if want_ht else None)
+
+    monkeypatch.setattr(O, "_GLAFunction", OracleGLA)
+    monkeypatch.setattr(T, "DEV", "cpu")
+    T.test_fused_recurrent_reverse_and_ungated_forms()
+    for op in ("fused_recurrent_rwkv6", "chunk_rwkv6"):
+        T.test_rwkv6_gradients(op)
