@@ -55,14 +55,13 @@ class _ShortConvFn(torch.autograd.Function):
 
 class ShortConvolution(nn.Conv1d):
     """Depthwise causal conv (+SiLU) over ``[B, L, D]``; weight ``[D, 1, W]`` (state-dict key
-    ``...conv1d.weight``), no bias by default -- FLA/fla/modules/convolution.py:84-139."""
+    ``...conv1d.weight``), no bias by default -- FLA/fla/modules/convolution.py:84-139.  Lina never sets ``bias=True``
+    (model/gla.py:106-108); that form runs the kernels without activation and adds bias + SiLU with torch ops."""
 
     def __init__(self, hidden_size: int, kernel_size: int, bias: bool = False,
                  activation: Optional[str] = "silu", use_fast_conv1d: Optional[bool] = True):
         super().__init__(in_channels=hidden_size, out_channels=hidden_size, kernel_size=kernel_size,
                          groups=hidden_size, bias=bias, padding=kernel_size - 1)
-        if bias:
-            raise NotImplementedError("ShortConvolution(bias=True) is not used by Lina (model/gla.py:106-108)")
         self.hidden_size = hidden_size
         self.activation = None
         if activation is not None:
@@ -77,7 +76,13 @@ class ShortConvolution(nn.Conv1d):
             x = x.mul_(mask.unsqueeze(-1))
         if cache is not None and x.shape[1] == 1:
             return self.step(x, cache)
+        if self.bias is not None:
+            return self._bias_act(_ShortConvFn.apply(x, self.weight, cache, False))
         return _ShortConvFn.apply(x, self.weight, cache, self.activation is not None)
+
+    def _bias_act(self, y: torch.Tensor) -> torch.Tensor:
+        y = y + self.bias.to(y.dtype)
+        return torch.nn.functional.silu(y) if self.activation is not None else y
 
     def step(self, x: torch.Tensor, cache: torch.Tensor):
         """convolution.py:180-205 (one token, rolls ``cache``)."""
@@ -90,10 +95,13 @@ class ShortConvolution(nn.Conv1d):
         y = torch.empty_like(xs)
         if not cache.is_contiguous():
             raise ValueError("conv cache must be contiguous [B, D, W]")
+        fused_act = self.activation is not None and self.bias is None
         rc = L.lib().lina_short_conv_update(L.ptr(xs), L.ptr(cache), L.dt(cache), L.ptr(w), L.ptr(y), B, D, W,
-                                            int(self.activation is not None), L.dt(xs), L.stream(xs))
+                                            int(fused_act), L.dt(xs), L.stream(xs))
         L.count_launches(1)
         L.check(rc, "lina_short_conv_update")
+        if self.bias is not None:
+            y = self._bias_act(y)
         return y.unsqueeze(1)
 
     @property

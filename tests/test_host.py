@@ -146,3 +146,26 @@ def test_reverse_and_rwkv6_host_logic_with_the_kernel_stubbed_by_the_oracle(monk
     T.test_fused_recurrent_reverse_and_ungated_forms()
     for op in ("fused_recurrent_rwkv6", "chunk_rwkv6"):
         T.test_rwkv6_gradients(op)
+
+
+def test_short_convolution_with_bias_host_composition(monkeypatch):
+    """ShortConvolution(bias=True) (convolution.py:84-139; unused by Lina) = kernel without activation + bias + SiLU in torch:
+    checked against F.conv1d with the kernel call replaced by the oracle's conv."""
+    import torch.nn.functional as F
+    from oracle import gla_oracle as GO
+    import lina_speech_b200.fla_api.modules as M
+
+    class OracleConv:
+        @staticmethod
+        def apply(x, weight, cache, silu):
+            return GO.short_conv_prefill(x, weight.squeeze(1), cache, "silu" if silu else None)
+
+    monkeypatch.setattr(M, "_ShortConvFn", OracleConv)
+    torch.manual_seed(0)
+    conv = M.ShortConvolution(24, 4, bias=True, activation="silu")
+    x = torch.randn(2, 11, 24)
+    cache = torch.zeros(2, 24, 4)
+    y = conv(x, cache=cache)
+    ref = F.silu(F.conv1d(F.pad(x.transpose(1, 2), (3, 0)), conv.weight, conv.bias, groups=24)).transpose(1, 2)
+    assert torch.allclose(y, ref, atol=1e-6)
+    assert torch.equal(cache, x.transpose(1, 2)[..., -4:])
