@@ -170,9 +170,21 @@ class FusedRMSNormSwishGate(nn.Module):
         return s + f", eps={self.eps})"
 
     def forward(self, x, o, residual=None, prenorm=False, residual_in_fp32=False):
-        if residual is not None or prenorm:
-            raise NotImplementedError("residual / prenorm are never used by Lina (model/gla.py:218)")
-        return _NormGateFn.apply(x, o, self.weight, self.eps)
+        """Lina calls ``forward(x, o)`` only (model/gla.py:218).  The residual / prenorm options follow
+        fused_norm_gate.py:100-111,460-480: the sum ``x + residual`` is formed in fp32 and normalised as such, stored as
+        ``residual_out`` in the residual's dtype (fp32 with ``residual_in_fp32`` and no residual), ``y`` keeps x's dtype;
+        they are torch ops around the same kernel."""
+        if residual is None and not prenorm:
+            return _NormGateFn.apply(x, o, self.weight, self.eps)
+        if residual is not None:
+            assert residual.shape == x.shape
+            xs = x.float() + residual.float()
+            residual_out = xs.to(residual.dtype)
+        else:
+            xs = x.float() if residual_in_fp32 else x
+            residual_out = xs
+        y = _NormGateFn.apply(xs, o, self.weight, self.eps).to(x.dtype)
+        return (y, residual_out) if prenorm else y
 
 
 # ------------------------------------------------------------------------------------------------

@@ -169,3 +169,31 @@ def test_short_convolution_with_bias_host_composition(monkeypatch):
     ref = F.silu(F.conv1d(F.pad(x.transpose(1, 2), (3, 0)), conv.weight, conv.bias, groups=24)).transpose(1, 2)
     assert torch.allclose(y, ref, atol=1e-6)
     assert torch.equal(cache, x.transpose(1, 2)[..., -4:])
+
+
+def test_norm_gate_residual_and_prenorm_host_composition(monkeypatch):
+    """FusedRMSNormSwishGate(x, o, residual, prenorm, residual_in_fp32) (fused_norm_gate.py:100-111,460-480; unused by Lina):
+    fp32 sum, normalised un-rounded, residual_out in the residual's dtype -- with the kernel replaced by the oracle."""
+    from oracle import gla_oracle as GO
+    import lina_speech_b200.fla_api.modules as M
+
+    class OracleNormGate:
+        @staticmethod
+        def apply(x, g, weight, eps):
+            return GO.rmsnorm_swish_gate(x, g.to(x.dtype), weight, eps)
+
+    monkeypatch.setattr(M, "_NormGateFn", OracleNormGate)
+    torch.manual_seed(0)
+    m = M.FusedRMSNormSwishGate(32)
+    with torch.no_grad():
+        m.weight.uniform_(0.5, 1.5)
+    x, o, r = torch.randn(3, 5, 32).bfloat16(), torch.randn(3, 5, 32).bfloat16(), torch.randn(3, 5, 32)
+    y, res = m(x, o, residual=r, prenorm=True)
+    xs = x.float() + r
+    ref = xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + 1e-5) * m.weight * o.float() * torch.sigmoid(o.float())
+    assert y.dtype == torch.bfloat16 and res.dtype == torch.float32 and torch.equal(res, xs)
+    assert torch.allclose(y.float(), ref, atol=2e-2, rtol=2e-2)
+    y2, res2 = m(x, o, prenorm=True, residual_in_fp32=True)
+    assert res2.dtype == torch.float32 and torch.equal(res2, x.float()) and y2.dtype == torch.bfloat16
+    y3, res3 = m(x, o, prenorm=True)
+    assert res3 is x
