@@ -231,6 +231,12 @@ class Cache:
     def get_max_length(self) -> Optional[int]:
         return None
 
+    def reorder_cache(self, beam_idx: torch.LongTensor):
+        """models/utils.py:86-90 (beam search): batch rows re-selected; works on the per-layer tuples Lina stores (the
+        reference's version assumes one tensor per layer)."""
+        for layer_idx, st in enumerate(self.states):
+            self.states[layer_idx] = tuple(t.index_select(0, beam_idx.to(t.device)) for t in st)
+
     def to_legacy_cache(self):
         return tuple(self.states)
 

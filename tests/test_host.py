@@ -197,3 +197,12 @@ def test_norm_gate_residual_and_prenorm_host_composition(monkeypatch):
     assert res2.dtype == torch.float32 and torch.equal(res2, x.float()) and y2.dtype == torch.bfloat16
     y3, res3 = m(x, o, prenorm=True)
     assert res3 is x
+
+
+def test_cache_reorder_selects_batch_rows_of_every_state_tensor():
+    c = Cache()
+    c.update((torch.arange(6.).view(3, 2), torch.arange(12.).view(3, 4)), 0)
+    c.update((torch.arange(3.).view(3, 1),), 1)
+    c.reorder_cache(torch.tensor([2, 0, 0]))
+    assert torch.equal(c[0][0], torch.tensor([[4., 5.], [0., 1.], [0., 1.]]))
+    assert torch.equal(c[0][1][:, 0], torch.tensor([8., 0., 0.])) and torch.equal(c[1][0].flatten(), torch.tensor([2., 0., 0.]))
