@@ -157,6 +157,11 @@ def autocast_layernorm(x, norm: nn.LayerNorm):
     return norm(x)
 
 
+def unpack_ignore(x):
+    """model/base_blocks.py:53-54: token mixers may return (output, extras); keep the output."""
+    return x[0] if type(x) is tuple else x
+
+
 class MixingBlock(nn.Module):
     """Pre-LN residual wrapper (model/base_blocks.py:56-69): tmix then cmix."""
 

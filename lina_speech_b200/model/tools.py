@@ -4,6 +4,13 @@ from itertools import accumulate
 import torch
 
 
+def pad_2d_sequence(seq, padding_value=0):
+    """model/tools.py:8-15: right/bottom-pad 2-D tensors to the largest height and width and stack them."""
+    rows, cols = max(t.shape[0] for t in seq), max(t.shape[1] for t in seq)
+    return torch.stack([torch.nn.functional.pad(t, (0, cols - t.shape[1], 0, rows - t.shape[0]), value=padding_value)
+                        for t in seq])
+
+
 def topk_sampling(seq, k=1, temp=1.0):
     """model/tools.py:38-44, including its quirk: the k-th largest *unscaled* logit is the
     threshold applied to the temperature-scaled logits."""

@@ -19,6 +19,22 @@ from torch.nn.utils.rnn import pad_sequence
 from .model.tools import delay_rvq, sequence_mask
 
 
+def filter_unk(x, tokenizer) -> bool:
+    """initial_state.py:13-18 (the notebook's dataset filter, InferenceLina.ipynb cell "expresso_ds.filter"): True when the
+    tokenizer can encode the transcript."""
+    try:
+        tokenizer.encode(x)
+        return True
+    except Exception:
+        return False
+
+
+def filter_except(x, tokenizer=None) -> bool:
+    """initial_state.py:32-37 reads a module-level ``tokenizer`` that the reference never defines, so it always answers
+    False there; here the tokenizer can be passed, and without one the answer is the reference's."""
+    return False if tokenizer is None else filter_unk(x, tokenizer)
+
+
 def speaker_state_dict(params) -> Dict[str, torch.Tensor]:
     """initial_state.py:20-30 -- flat dict ready for safetensors.save_file."""
     out = {}

@@ -206,3 +206,20 @@ def test_cache_reorder_selects_batch_rows_of_every_state_tensor():
     c.reorder_cache(torch.tensor([2, 0, 0]))
     assert torch.equal(c[0][0], torch.tensor([[4., 5.], [0., 1.], [0., 1.]]))
     assert torch.equal(c[0][1][:, 0], torch.tensor([8., 0., 0.])) and torch.equal(c[1][0].flatten(), torch.tensor([2., 0., 0.]))
+
+
+def test_small_reference_helpers():
+    """model/tools.py:8-15 pad_2d_sequence, initial_state.py:13-18 filter_unk (imported by the notebook), base_blocks.unpack_ignore."""
+    from lina_speech_b200.initial_state import filter_unk, filter_except
+    from lina_speech_b200.model.base_blocks import unpack_ignore
+    p = tools.pad_2d_sequence([torch.ones(2, 3), torch.ones(4, 1)], padding_value=7)
+    assert p.shape == (2, 4, 3) and p[0, 2:].eq(7).all() and p[1, :, 1:].eq(7).all() and p[1, :, 0].eq(1).all()
+
+    class Tok:
+        def encode(self, x):
+            if "?" in x:
+                raise KeyError(x)
+            return [1]
+
+    assert filter_unk("abc", Tok()) and not filter_unk("a?c", Tok()) and not filter_except("abc")
+    assert unpack_ignore((1, 2)) == 1 and unpack_ignore(3) == 3
