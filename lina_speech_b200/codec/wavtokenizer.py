@@ -277,6 +277,30 @@ class WavTokenizer(nn.Module):
                                  adanorm_num_embeddings=adanorm_num_embeddings),
                    ISTFTHead(dim, n_fft, hop_length, padding))
 
+    @classmethod
+    def from_hparams0802(cls, config_path: str) -> "WavTokenizer":
+        """pretrained.py:81-92: build from the training yaml (``model.init_args.{feature_extractor,backbone,head}.init_args``).
+        Only the decode side is instantiated; encoder-only keys of the feature extractor are ignored."""
+        import yaml
+        with open(config_path, "r") as f:
+            init = yaml.safe_load(f)["model"]["init_args"]
+        fe = init["feature_extractor"].get("init_args", {})
+        bb = init["backbone"].get("init_args", {})
+        hd = init["head"].get("init_args", {})
+        backbone = VocosBackbone(bb["input_channels"], bb["dim"], bb["intermediate_dim"], bb["num_layers"],
+                                 bb.get("layer_scale_init_value"), bb.get("adanorm_num_embeddings"))
+        head = ISTFTHead(hd["dim"], hd["n_fft"], hd["hop_length"], hd.get("padding", "same"))
+        return cls(CodebookFeatures(fe.get("num_quantizers", 1), fe.get("vq_bins", 16384), bb["input_channels"]), backbone, head)
+
+    @classmethod
+    def from_pretrained0802(cls, config_path: str, model_path: str) -> "WavTokenizer":
+        """pretrained.py:95-115 (what InferenceLina.ipynb calls): yaml + Lightning checkpoint; the decode-side tensors of
+        ``state_dict`` (backbone.*, head.*, the quantizer codebooks) are loaded strictly, the model is returned in eval mode."""
+        model = cls.from_hparams0802(config_path)
+        raw = torch.load(model_path, map_location="cpu", weights_only=False)["state_dict"]
+        model.load_reference_state_dict(raw)
+        return model.eval()
+
     def load_reference_state_dict(self, state_dict):
         keep = {k: v for k, v in state_dict.items()
                 if k.startswith(("backbone.", "head.")) or (k.startswith("feature_extractor.") and k.endswith("_codebook.embed"))}

@@ -223,3 +223,31 @@ def test_small_reference_helpers():
 
     assert filter_unk("abc", Tok()) and not filter_unk("a?c", Tok()) and not filter_except("abc")
     assert unpack_ignore((1, 2)) == 1 and unpack_ignore(3) == 3
+
+
+def test_wavtokenizer_from_pretrained0802_reads_yaml_and_checkpoint(tmp_path):
+    """DEC/pretrained.py:81-115: the notebook's constructor.  A yaml with the shipped structure + a checkpoint holding a
+    reference-keyed state dict (with encoder-side keys that must be ignored) round-trips into the decode-side module."""
+    import yaml
+    cfg = {"model": {"init_args": {
+        "feature_extractor": {"class_path": "decoder.feature_extractors.EncodecFeatures",
+                              "init_args": {"encodec_model": "encodec_24khz", "bandwidths": [6.6], "train_codebooks": True,
+                                            "num_quantizers": 1, "dowmsamples": [8, 5, 4, 2], "vq_bins": 64, "vq_kmeans": 200}},
+        "backbone": {"class_path": "decoder.models.VocosBackbone",
+                     "init_args": {"input_channels": 32, "dim": 64, "intermediate_dim": 96, "num_layers": 2,
+                                   "adanorm_num_embeddings": 4}},
+        "head": {"class_path": "decoder.heads.ISTFTHead", "init_args": {"dim": 64, "n_fft": 64, "hop_length": 16, "padding": "same"}}}}}
+    (tmp_path / "c.yaml").write_text(yaml.safe_dump(cfg))
+    src = WavTokenizer.from_hparams0802(str(tmp_path / "c.yaml"))
+    with torch.no_grad():
+        for p in src.parameters():
+            p.normal_()
+        src.feature_extractor.encodec.quantizer.vq.layers[0]._codebook.embed.normal_()
+    sd = dict(src.state_dict())
+    sd["feature_extractor.encodec.encoder.model.0.conv.conv.weight"] = torch.zeros(3)      # encoder side: ignored
+    sd["discriminator.x"] = torch.zeros(1)
+    torch.save({"state_dict": sd}, tmp_path / "m.ckpt")
+    wt = WavTokenizer.from_pretrained0802(str(tmp_path / "c.yaml"), str(tmp_path / "m.ckpt"))
+    assert not wt.training
+    for k, v in src.state_dict().items():
+        assert torch.equal(wt.state_dict()[k], v), k
