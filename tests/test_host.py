@@ -251,3 +251,27 @@ def test_wavtokenizer_from_pretrained0802_reads_yaml_and_checkpoint(tmp_path):
     assert not wt.training
     for k, v in src.state_dict().items():
         assert torch.equal(wt.state_dict()[k], v), k
+
+
+def test_train_lina_mirror_checkpoint_round_trip_and_optimizer(tmp_path):
+    """train_lina.py:12-120 without Lightning: constructor, a Lightning-style checkpoint (hyper_parameters + state_dict with
+    ``model.*`` keys) loads back bit-exactly, configure_optimizers gives AdamW + the cosine warm-up schedule."""
+    from lina_speech_b200.train_lina import TrainLina
+
+    def parts():
+        return dict(attentive_rnn=m.AttentiveGLA(32, 1, 2, blind=True, use_short_conv=True, pos_type="convolutional"),
+                    txt_encoder=m.TextEncoder(32, 2, n_layers=1, dropout=0.0, rotary=False))
+
+    hp = dict(d_model=32, quant_layer=[0], n_codebook=64, n_special_token_in=3, n_special_token_out=3, n_txt_vocab=40,
+              learning_rate=2e-4, betas=(0.9, 0.95), n_warmup_steps=5, n_training_steps=50)
+    torch.manual_seed(0)
+    a = TrainLina(**parts(), **hp)
+    assert all(k.startswith("model.") for k in a.state_dict())
+    torch.save({"state_dict": a.state_dict(), "hyper_parameters": dict(hp, **parts())}, tmp_path / "last.ckpt")
+    torch.manual_seed(1)
+    b = TrainLina.load_from_checkpoint(str(tmp_path / "last.ckpt"))
+    for k, v in a.state_dict().items():
+        assert torch.equal(b.state_dict()[k], v), k
+    (opt,), (sch,) = b.configure_optimizers()
+    assert isinstance(opt, torch.optim.AdamW) and opt.defaults["betas"] == (0.9, 0.95) and sch["interval"] == "step"
+    assert opt.param_groups[0]["weight_decay"] == 0.1 and abs(opt.param_groups[0]["lr"]) < 1e-12      # warm-up starts at 0

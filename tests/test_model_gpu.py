@@ -1,4 +1,6 @@
 """GPU parity at layer and model level against the reference's golden fixtures (tests/golden)."""
+import os
+
 import pytest
 import torch
 
@@ -129,3 +131,33 @@ def test_prompt_prefill_equals_token_by_token_teacher_forcing(golden_model, grap
     assert torch.equal(qs1, qs0) and torch.equal(qs1.cpu(), g["qs"]), "prefilled prompt changes the greedy continuation"
     _close(atts1, atts0, 1e-4, what="atts (prefill vs steps)")
     assert torch.equal(st1, st0) and len(cuts1) == 3
+
+
+@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1; first run: profiles/gpu_call_r02_bringup.sh")
+def test_train_lina_mirror_steps_reduce_the_loss():
+    """train_lina.py:72-120 through the Lightning-free mirror: collate -> step -> backward -> AdamW + cosine warm-up."""
+    import lina_speech_b200.model as m
+    from lina_speech_b200.train_lina import TrainLina
+    from lina_speech_b200.tuning import simple_collate
+
+    class Tok:
+        def encode(self, s):
+            return [1] + [3 + (ord(c) % 29) for c in s[5:-5]] + [2]
+
+    torch.manual_seed(0)
+    tl = TrainLina(m.AttentiveGLA(64, 1, 2, blind=True, use_short_conv=True, pos_type="convolutional"), 64, [0], 64, 3, 3, 40,
+                   txt_encoder=m.TextEncoder(64, 2, n_layers=1, dropout=0.0, rotary=False), learning_rate=3e-3,
+                   n_warmup_steps=2, n_training_steps=40).to(DEV).train()
+    data = [{"audio_token": torch.randint(0, 64, (1, 40)), "text": t} for t in ("hello world", "good morning")]
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in simple_collate(data, Tok()).items()}
+    batch["crossatt_pos"] = None
+    (opt,), (sch,) = tl.configure_optimizers()
+    losses = []
+    for i in range(20):
+        opt.zero_grad(set_to_none=True)
+        loss = tl.training_step(batch, i)
+        loss.backward()
+        opt.step()
+        sch["scheduler"].step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses) and losses[-1] < 0.7 * losses[0], losses
