@@ -275,3 +275,37 @@ def test_train_lina_mirror_checkpoint_round_trip_and_optimizer(tmp_path):
     (opt,), (sch,) = b.configure_optimizers()
     assert isinstance(opt, torch.optim.AdamW) and opt.defaults["betas"] == (0.9, 0.95) and sch["interval"] == "step"
     assert opt.param_groups[0]["weight_decay"] == 0.1 and abs(opt.param_groups[0]["lr"]) < 1e-12      # warm-up starts at 0
+
+
+def test_reference_import_names_resolve_after_install_aliases(tmp_path):
+    """InferenceLina.ipynb cell 1 imports + un-pickling of reference-named classes, in a subprocess (sys.modules is global)."""
+    import subprocess, sys, os, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys, pickle
+        sys.path.insert(0, {root!r})
+        from lina_speech_b200.compat import install_reference_aliases
+        done = install_reference_aliases()
+        from train_lina import TrainLina
+        from decoder.pretrained import WavTokenizer
+        from initial_state import train_initial_state, filter_unk
+        from model.gla import AttentiveGLA
+        from model.encoder import TextEncoder
+        from model.multiembed import MultiEmbedding
+        from model.attentive_rnn import AttentiveRNN
+        from model.accuracy import MulticlassAccuracy
+        import torch
+        # a pickle that names the reference's module path un-pickles into the mirror class
+        real = TextEncoder.__module__
+        TextEncoder.__module__ = "model.encoder"
+        blob = pickle.dumps(TextEncoder(32, 2, n_layers=1, dropout=0.0, rotary=False))
+        TextEncoder.__module__ = real
+        assert b"model.encoder" in blob and type(pickle.loads(blob)) is TextEncoder
+        acc = MulticlassAccuracy(5, top_k=2, ignore_index=[0])
+        p = torch.tensor([[0.1, 0.9, 0.5, 0., 0.], [0.9, 0.1, 0., 0., 0.], [0., 0., 0., 1., 0.5]])
+        assert float(acc(p, torch.tensor([2, 0, 1]))) == 0.5
+        assert issubclass(AttentiveGLA, AttentiveRNN) and hasattr(WavTokenizer, "from_pretrained0802") and len(done) >= 12
+        print("ok")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
