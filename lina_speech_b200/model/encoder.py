@@ -18,3 +18,6 @@ class TextEncoder(torch.nn.Module):
         for block in self.sa:
             x = block(x, mask=mask, pos=pos)
         return x
+
+
+from .speaker import SimpleSpeakerEncoder  # noqa: E402,F401  (model/encoder.py:45-84 lives in speaker.py here)
