@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of round 2: (1) the regular GPU suite, (2) the items that were compiled at the end of round 1 without a
-# device (LINA_BRINGUP gates them): ISTFT warp-per-frame FFT (variant key 8), M = 64 accumulator layout probe.
+# First GPU call of round 2: (1) the regular GPU suite, (2) the items written at the end of round 1 (parity green in the last
+# 14 s call, never timed): ISTFT warp-per-frame FFT (variant key 8; LINA_BRINGUP adds the multi-pass size), M = 64 layout probe.
 # Each step under its own timeout so that a hang costs minutes, not the call.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out

@@ -299,7 +299,6 @@ def test_tensor_core_backward(K, V, T, with_state, layout):
         _assert_close(h0d.grad, ref[4], 0.0, 2e-2, what="dh0")
 
 
-@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1 (host logic checked on CPU with a stubbed kernel); first run: profiles/gpu_call_r02_bringup.sh")
 def test_fused_recurrent_reverse_and_ungated_forms():
     """recurrent_fuse.py:13-27 options outside Lina's use: ``reverse=True`` (time runs T-1 -> 0) and ``gk=None`` (no decay),
     forward + gradients against the oracle on explicitly flipped / zero-gated inputs."""
@@ -327,7 +326,6 @@ def test_fused_recurrent_reverse_and_ungated_forms():
         fused_recurrent_gla(q.to(DEV), k.to(DEV), v.to(DEV), gk.to(DEV), gv=torch.zeros_like(v).to(DEV))
 
 
-@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1 (host logic checked on CPU with a stubbed kernel); first run: profiles/gpu_call_r02_bringup.sh")
 @pytest.mark.parametrize("op", ["fused_recurrent_rwkv6", "chunk_rwkv6"])
 def test_rwkv6_gradients(op):
     """a13 with autograd: RWKV6 as the GLA operator on shifted queries + bonus; every gradient (r, k, v, w, u, h0) against

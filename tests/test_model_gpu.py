@@ -133,7 +133,6 @@ def test_prompt_prefill_equals_token_by_token_teacher_forcing(golden_model, grap
     assert torch.equal(st1, st0) and len(cuts1) == 3
 
 
-@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1; first run: profiles/gpu_call_r02_bringup.sh")
 def test_train_lina_mirror_steps_reduce_the_loss():
     """train_lina.py:72-120 through the Lightning-free mirror: collate -> step -> backward -> AdamW + cosine warm-up."""
     import lina_speech_b200.model as m
