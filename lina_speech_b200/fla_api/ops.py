@@ -85,6 +85,45 @@ def _fwd(kind: str, q, k, v, gk, h0, scale: float, want_ht: bool, bthd: bool = F
     return o, ht
 
 
+# The tensor-core chunk kernels use one pivot per 64-token chunk: k e^{-G} leaves the fp32 / bf16 exponent range when the
+# summed log-gate of a channel inside one chunk goes below about -85 (DESIGN.md 4.1 "Numerics").  The reference is exact for any
+# gate (chunk_fuse.py:196-238 computes the intra-chunk term pairwise in fp32), so the operator API checks the gates first and
+# serves such inputs with the exact recurrence kernels instead.  One small reduction + one host read per call;
+# LINA_GATE_CHECK=0 removes it (then the caller guarantees the envelope).
+GATE_CHECK = os.environ.get("LINA_GATE_CHECK", "1") != "0"
+GATE_SUM_LIMIT = -80.0
+_CHUNK = 64
+
+
+def _min_chunk_gate_sum(gk: torch.Tensor) -> torch.Tensor:
+    """min over (b, h, chunk, channel) of the summed log-gates of one 64-token chunk; gk [B,H,T,K], any strides."""
+    T = gk.shape[2]
+    full = T // _CHUNK
+    parts = []
+    if full:
+        parts.append(gk.narrow(2, 0, full * _CHUNK).unflatten(2, (full, _CHUNK)).sum(3, dtype=torch.float32).amin())
+    if T % _CHUNK:
+        parts.append(gk.narrow(2, full * _CHUNK, T % _CHUNK).sum(2, dtype=torch.float32).amin())
+    return parts[0] if len(parts) == 1 else torch.minimum(parts[0], parts[1])
+
+
+def _gates_in_envelope(gk: torch.Tensor) -> bool:
+    return bool(_min_chunk_gate_sum(gk).item() >= GATE_SUM_LIMIT)        # NaN gates compare False -> exact path
+
+
+def _route(kind: str, q, v, gk, uses_tc):
+    """'recurrent' | 'chunk' | 'fused_chunk' -> (kernel family that serves the forward, gates_ok): the chunk forms fall back
+    to the exact recurrence when they would run on the tensor-core kernel with gates outside its numeric envelope.
+    gates_ok is None when the gates were not looked at (the backward looks then, if it wants the tensor-core path)."""
+    if kind == "recurrent" or not GATE_CHECK:
+        return kind, (None if GATE_CHECK else True)
+    B, H, T, K = q.shape
+    if not uses_tc(B, H, T, K, v.shape[-1], L._DT.get(q.dtype, -1)):
+        return kind, None
+    ok = _gates_in_envelope(gk)
+    return (kind if ok else "recurrent"), ok
+
+
 TC_BWD = os.environ.get("LINA_TC_BWD", "1") != "0"
 CONCURRENT_BWD = os.environ.get("LINA_CONCURRENT_BWD", "1") != "0"
 _SIDE = {}
@@ -302,9 +341,9 @@ def _bwd_tc_reference(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, ru
     return dq.to(lo), dk.to(lo), dv, dgk.to(lo), dh0
 
 
-def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool):
+def _bwd(q, k, v, gk, h0, do, dht, scale: float, want_dh0: bool, allow_tc: bool = True):
     lib = L.lib()
-    if _tc_bwd_eligible(q, v):
+    if allow_tc and _tc_bwd_eligible(q, v):
         if do.dtype != q.dtype:
             do = do.to(q.dtype)
         return _bwd_tc(q, k, v, gk, h0, do, dht, scale, want_dh0)
@@ -336,8 +375,11 @@ class _GLAFunction(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, q, k, v, gk, scale, initial_state, output_final_state, kind):
         in_dtypes = (q.dtype, k.dtype, v.dtype, gk.dtype)
-        q, k, v, gk, h0, bthd = _prep(q, k, v, gk, initial_state, kind)
-        o, ht = _fwd("recurrent" if kind == "recurrent" else "chunk", q, k, v, gk, h0, scale, output_final_state, bthd)
+        L.require_cuda(q, k, v, gk, initial_state)
+        served, ctx.gates_ok = (_route(kind, q, v, gk, L.lib().lina_gla_chunk_fwd_uses_tensor_cores)
+                                if q.dtype == gk.dtype else (kind, None))
+        q, k, v, gk, h0, bthd = _prep(q, k, v, gk, initial_state, served)
+        o, ht = _fwd("recurrent" if served == "recurrent" else "chunk", q, k, v, gk, h0, scale, output_final_state, bthd)
         ctx.save_for_backward(q, k, v, gk, h0)
         ctx.scale, ctx.kind, ctx.in_dtypes = scale, kind, in_dtypes
         ctx.h0_dtype = initial_state.dtype if initial_state is not None else None
@@ -351,7 +393,10 @@ class _GLAFunction(torch.autograd.Function):
         if do is None:
             do = torch.zeros_like(v)
         want_dh0 = h0 is not None and ctx.needs_input_grad[5] and ctx.kind != "fused_chunk"
-        dq, dk, dv, dgk, dh0 = _bwd(q, k, v, gk, h0, do, dht, ctx.scale, want_dh0)
+        allow_tc = ctx.gates_ok
+        if allow_tc is None:                                     # forward did not look at the gates (recurrent kind, ...)
+            allow_tc = _gates_in_envelope(gk) if _tc_bwd_eligible(q, v) else False
+        dq, dk, dv, dgk, dh0 = _bwd(q, k, v, gk, h0, do, dht, ctx.scale, want_dh0, allow_tc)
         dts = ctx.in_dtypes
         if dh0 is not None and ctx.h0_dtype is not None:
             dh0 = dh0.to(ctx.h0_dtype)

@@ -347,3 +347,29 @@ def test_rwkv6_gradients(op):
     ((o * do.to(DEV)).sum() + (ht * dht.to(DEV)).sum()).backward()
     for got, ref, name in zip(leaves, ref_leaves, "r k v w u h0".split()):
         _assert_close(got.grad, ref.grad, 1e-3, 1e-3, what=f"{op} d{name}")
+
+
+@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1 (routing logic checked on CPU in tests/test_host.py)")
+@pytest.mark.parametrize("op", ["chunk", "fused_chunk"])
+def test_gates_outside_the_tensor_core_envelope_are_served_exactly(op):
+    """-2 per step on a few channels = -128 per 64-token chunk: beyond the single-pivot range of the tcgen05 kernel; the
+    operator must notice and answer with the exact recurrence, forward and backward (the reference is exact for any gate)."""
+    fn = _ops()[op]
+    torch.manual_seed(5)
+    B, H, T, K, V = 1, 2, 192, 128, 128
+    bf = torch.bfloat16
+    q, k, v, do = (torch.randn(B, H, T, d).to(bf) for d in (K, K, V, V))
+    gk = F.logsigmoid(torch.randn(B, H, T, K)) / 16
+    gk[:, :, :, ::17] = -2.0
+    gk = gk.to(bf)
+    ro, rh = GO.recurrent_gla(q.float(), k.float(), v.float(), gk.float())
+    ref = GO.recurrent_gla_bwd(q.float(), k.float(), v.float(), gk.float(), None, do.float(), None)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (q, k, v, gk)]
+    o, ht = fn(*leaves, output_final_state=True)
+    assert torch.isfinite(o).all() and torch.isfinite(ht).all()
+    _assert_close(o, ro, 0.0, 2.0 ** -7, what="o")
+    _assert_close(ht, rh, 1e-4, 1e-3, what="ht")
+    (o.float() * do.to(DEV).float()).sum().backward()
+    for name, leaf, r in zip(("dq", "dk", "dv", "dgk"), leaves, ref[:4]):
+        assert torch.isfinite(leaf.grad).all()
+        _assert_close(leaf.grad, r, 0.0, 2e-2, what=name)

@@ -309,3 +309,31 @@ def test_reference_import_names_resolve_after_install_aliases(tmp_path):
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_gate_envelope_routing_of_the_chunk_operators():
+    """fla_api/ops.py:_route -- the tensor-core chunk kernels hold one pivot per 64-token chunk, so inputs whose summed
+    log-gate inside a chunk passes -80 on any channel are served by the exact recurrence (the reference is exact for any
+    gate, chunk_fuse.py:196-238).  Pure host logic: checked here on CPU tensors, both memory layouts, ragged T."""
+    import torch.nn.functional as F
+    import lina_speech_b200.fla_api.ops as O
+    torch.manual_seed(0)
+    B, H, T, K = 2, 3, 150, 16
+    mild = (F.logsigmoid(torch.randn(B, H, T, K)) / 16).bfloat16()                  # model/gla.py:174-181
+    fla = F.logsigmoid(torch.randn(B, H, T, K)).clamp_min(-3)                       # FLA/tests/ops/test_gla.py:27 (sum ~ -60)
+    ref = torch.stack([c.float().sum(2) for c in mild.split(64, dim=2)], 2).amin()
+    assert torch.allclose(O._min_chunk_gate_sum(mild), ref)
+    bthd = mild.transpose(1, 2).contiguous().transpose(1, 2)                         # [B,H,T,K] view of [B,T,H,K] memory
+    assert not bthd.is_contiguous() and torch.allclose(O._min_chunk_gate_sum(bthd), ref)
+    assert O._gates_in_envelope(mild) and O._gates_in_envelope(fla)
+    strong = mild.clone()
+    strong[1, 2, 128:150, 5] = -4.0                                                  # 22 steps of -4 in the ragged tail chunk
+    assert not O._gates_in_envelope(strong)
+    nan = mild.clone(); nan[0, 0, 3, 0] = float("nan")
+    assert not O._gates_in_envelope(nan)
+    q, v = torch.empty(B, H, T, K, dtype=torch.bfloat16), torch.empty(B, H, T, 32, dtype=torch.bfloat16)
+    yes, no = (lambda *a: 1), (lambda *a: 0)
+    assert O._route("chunk", q, v, mild, yes) == ("chunk", True)
+    assert O._route("fused_chunk", q, v, strong, yes) == ("recurrent", False)
+    assert O._route("chunk", q, v, strong, no) == ("chunk", None)                    # CUDA-core chunk path: exact already
+    assert O._route("recurrent", q, v, strong, yes) == ("recurrent", None)           # the backward looks at the gates
