@@ -218,6 +218,130 @@ def train_step_metrics(dev, B=8, T=4096, Tx=256, steps=3):
     return out
 
 
+def codec_metrics(dev, B=32, Ln=750, steps=5):
+    """SURVEY 8d cfg 5's tail: WavTokenizer ``codes_to_features`` + ``decode`` of [1, B, 750] codes -> [B, 240000] fp32
+    waveform (10 s of 24 kHz audio per sequence) at the reference's fp32 precision, shipped widths, random weights."""
+    from lina_speech_b200.codec import WavTokenizer
+    from lina_speech_b200.codec import wavtokenizer as WT
+    torch.manual_seed(0)
+    wt = WavTokenizer.from_hparams().eval()
+    with torch.no_grad():
+        wt.feature_extractor.encodec.quantizer.vq.layers[0]._codebook.embed.normal_()
+    wt = wt.to(dev)
+    g = torch.Generator().manual_seed(2)
+    codes_h = torch.randint(0, 4096, (1, B, Ln), generator=g).pin_memory()
+    codes = codes_h.to(dev)
+    bw = torch.tensor([0], device=dev)
+
+    def run(c):
+        return wt.decode(wt.codes_to_features(c), bandwidth_id=bw)
+
+    for _ in range(3):
+        run(codes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run(codes)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    wav_h = torch.empty(B, 320 * Ln, dtype=torch.float32).pin_memory()
+    e0.record()
+    for _ in range(steps):                                    # end to end: host codes in, host waveform out
+        wav_h.copy_(run(codes_h.to(dev, non_blocking=True)), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / steps
+    WT.PROFILE = []
+    run(codes)
+    torch.cuda.synchronize()
+    prof, WT.PROFILE = WT.PROFILE, None
+    pk = peaks()
+    stages = {}
+    for name, nbytes, a, b in prof:
+        d = stages.setdefault(name, {"launch_groups": 0, "ms": 0.0, "bytes": 0})
+        d["launch_groups"] += 1
+        d["ms"] += a.elapsed_time(b)
+        d["bytes"] += nbytes
+    for d in stages.values():
+        d["hbm_frac"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"] if d["ms"] > 0 else None
+    own_ms = sum(d["ms"] for d in stages.values())
+    frames = B * Ln
+    return {"workload": f"WavTokenizer codes_to_features + decode, {B} x {Ln} frames (10 s each), dim 768 / 2304, 12 ConvNeXt, "
+                        "n_fft 1280 hop 320, fp32 (SURVEY 8d cfg 5)",
+            "precision": getattr(wt, "gemm_precision", "fp32"), "batch": B, "frames": Ln, "ms": ms,
+            "frames_per_s": frames / (ms * 1e-3), "x_realtime": frames / 75.0 / (ms * 1e-3),
+            "e2e_ms": ms_e2e, "e2e_frames_per_s": frames / (ms_e2e * 1e-3), "h2d_bytes": codes_h.numel() * 8,
+            "d2h_bytes": wav_h.numel() * 4, "algorithmic_flops": 125.6e6 * frames,
+            "tflops": 125.6e6 * frames / (ms * 1e-3) / 1e12,
+            "layer_boundary_bytes": 220 * 1024 * frames,
+            "layer_boundary_hbm_frac": 220 * 1024 * frames / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "own_kernels_ms": own_ms, "stages": stages}
+
+
+def decode_prompt_metrics(lm, dev, x_txt, B=128, p_len=225, gen=750, grp=None, world=1):
+    """BASELINE configs[2] / SURVEY 8d cfg 3: bs 128, a 225-token (3 s) prompt continued for 750 tokens (10 s), k = 100,
+    ``force_max_seqlen``; both ways of consuming the prompt (token by token as the reference, one chunkwise prefill pass)."""
+    import torch.distributed as dist
+    g = torch.Generator().manual_seed(9)
+    prompt = torch.randint(3, 4099, (1, B, p_len), generator=g).to(dev)      # already ids (+3), one per sequence
+    out = {"batch": B, "prompt_tokens": p_len, "generated_tokens": gen, "k": 100, "state_dtype": "bf16"}
+    for name, pre in (("token_by_token", False), ("prefill", True)):
+        tm = {}
+        lm.generate_batch(x_txt, batch_size=B, prompt=prompt, max_seqlen=p_len + 8, k=100, force_max_seqlen=True,
+                          cuda_graph=True, dist_group=grp, prefill_prompt=pre, stop_check_interval=1 << 30)
+        torch.cuda.synchronize()
+        lm.generate_batch(x_txt, batch_size=B, prompt=prompt, max_seqlen=p_len + gen, k=100, force_max_seqlen=True,
+                          cuda_graph=True, dist_group=grp, prefill_prompt=pre, stop_check_interval=1 << 30, _timing=tm)
+        torch.cuda.synchronize()
+        ms = tm["start"].elapsed_time(tm["end"])
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out[name] = {"total_ms": ms, "generated_tokens_per_s": world * B * gen / (ms * 1e-3),
+                     "rtf_24khz": (ms * 1e-3) / (gen / 75.0), "ms_per_loop_step": ms / max(1, tm["steps"])}
+    return out
+
+
+class _ByteTokenizer:
+    """Stand-in for the notebook's bpe256 tokenizer: ids in [3, 256)."""
+
+    def encode(self, s):
+        return [3 + (b % 253) for b in s.encode()]
+
+
+def tuning_metrics(dev, n_samples=96):
+    """InferenceLina.ipynb cell 15 / initial_state.py:85-160: ``train_initial_state`` through the fp32 d1024 l12 model, batch 2,
+    grad_acc 4, rank 1, ``fused_recurrent`` forward + backward (dh0).  The reference's one published figure is 12.28 it/s on
+    the author's GPU (120 iterations in 9 s, utterances of the Expresso set: here 3-10 s synthetic utterances)."""
+    from lina_speech_b200.tuning import train_initial_state
+    lm = build_model(dev, torch.float32)
+    g = torch.Generator().manual_seed(4)
+    ds = []
+    for i in range(16):
+        n = int(torch.randint(225, 751, (1,), generator=g))
+        ds.append({"audio_token": torch.randint(0, 4096, (1, n), generator=g),
+                   "text": "".join(chr(97 + int(c)) for c in torch.randint(0, 26, (60 + 5 * i,), generator=g))})
+    tok = _ByteTokenizer()
+    train_initial_state(lm, ds, tok, 16)                      # warm-up: 8 iterations (allocator, cuBLAS handles)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    params, losses = train_initial_state(lm, ds, tok, n_samples)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    its = n_samples // 2
+    out = {"workload": "train_initial_state, fp32 d1024 l12, batch 2, grad_acc 4, rank 1, utterances of 225-750 codec tokens",
+           "iterations": its, "seconds": dt, "it_per_s": its / dt, "utterances_per_s": 2 * its / dt,
+           "loss_first": losses[0], "loss_last": losses[-1],
+           "reference_published_it_per_s": 12.28, "reference_source": "InferenceLina.ipynb cell 15 (GPU not stated)",
+           "timing": "wall clock around the call (host loop with a .item() per iteration, as the reference's)"}
+    del lm
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 def main_ours(args):
     import torch.distributed as dist
@@ -342,20 +466,23 @@ def main_ours(args):
     roofline = {"kernel": ("lina_gla_chunk_fwd_pregated_bthd (tcgen05, operands gated by lina_gla_prefill_prep_gated)" if pregated
                            else "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)"),
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"],
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic,
+                "traffic_source": (os.path.relpath(tpath, ROOT) + " (ncu --set full of this kernel at this shape; not re-captured per run)"
+                                   if traffic is not None else None),
+                "peak_source": pk["src"],
                 "launch_ms": k_ms, "launches_timed": len(kern_ms), "share_of_step": sum(kern_ms) / ms,
                 "algorithmic_bytes": alg_bytes, "tensor_achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12,
                 "tensor_frac_of_sustained": alg_flops / (k_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]}
 
     grp = dist.group.WORLD if world > 1 else None          # batch-sharded generation: token all-gather per step
     # autoregressive decode loop (generate_batch) for tokens/s per stream and RTF
-    dec_steps = 96
+    dec_steps = 750                                   # 10 s of audio per stream
     xt = x[0]
     tm = {}
     lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True, dist_group=grp)
     l1 = _lib.launches()
     lm.generate_batch(xt.to(dev), batch_size=B, max_seqlen=dec_steps, k=100, force_max_seqlen=True, cuda_graph=True,
-                      dist_group=grp, _timing=tm)
+                      dist_group=grp, stop_check_interval=1 << 30, _timing=tm)
     torch.cuda.synchronize()
     dec_ms = tm["start"].elapsed_time(tm["end"]) / tm["steps"]
     if world > 1:
@@ -374,14 +501,32 @@ def main_ours(args):
     B2 = 128
     tm2 = {}
     lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=8, k=100, force_max_seqlen=True, cuda_graph=True, dist_group=grp)
-    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=64, k=100, force_max_seqlen=True, cuda_graph=True,
-                      dist_group=grp, _timing=tm2)
+    lm.generate_batch(xt.to(dev), batch_size=B2, max_seqlen=750, k=100, force_max_seqlen=True, cuda_graph=True,
+                      dist_group=grp, stop_check_interval=1 << 30, _timing=tm2)
     torch.cuda.synchronize()
     dec2_ms = tm2["start"].elapsed_time(tm2["end"]) / tm2["steps"]
+    if world > 1:
+        t = torch.tensor([dec2_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dec2_ms = float(t.item())
     sb2 = B2 * n_blocks * 2 * H * K * V * 2
     decode_bs128 = {"batch": B2, "steps": tm2["steps"], "ms_per_step": dec2_ms, "tokens_per_s": world * B2 / (dec2_ms * 1e-3),
                     "rtf_24khz": 75.0 * dec2_ms * 1e-3, "state_bytes_per_step": sb2,
                     "state_hbm_frac": sb2 / (dec2_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+
+    extras = {}
+
+    def leg(name, fn, *a, **kw):
+        try:
+            extras[name] = fn(*a, **kw)
+        except Exception as e:      # noqa: BLE001  (an extra section must never take the headline line down)
+            extras[name] = {"error": repr(e)[:300]}
+
+    if not args.no_extras:
+        leg("decode_prompt", decode_prompt_metrics, lm, dev, xt.to(dev), 128, 225, 750, grp, world)
+        leg("codec", codec_metrics, dev)
+        if world == 1:
+            leg("init_state_tuning", tuning_metrics, dev)
 
     # BASELINE configs[3]: one training step (fwd + bwd + AdamW, bf16 autocast over fp32 parameters) at bs8 x seq4096,
     # GLA backward on the tensor-core path (five runs of the pre-gated tcgen05 kernel); rank 0 at N = 1 only
@@ -405,6 +550,7 @@ def main_ours(args):
                        "h2d_bytes_per_step": xh.numel() * 8 + yh.numel() * 8, "d2h_bytes_per_step": 4},
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "decode": decode,
                "decode_bs128": decode_bs128}
+        out.update(extras)
         if train is not None:
             out["train_step"] = train
         if cpu_v is not None:
@@ -422,6 +568,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work for the whole --impl reference run")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step section")
+    ap.add_argument("--no-extras", action="store_true", help="skip the codec / prompted-decode / state-tuning sections")
     ap.add_argument("--profile", action="store_true", help="run only W+K resident steps (for ncu); prints nothing")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -143,11 +143,16 @@ int lina_gla_prefill_prep(const void *xq, const void *xk, const void *xv, long l
  *   decay[b,h,n,:] = e^{G at the chunk end}  [B,H,ceil(L/64),K] fp32
  * i.e. the MMA operands FLA/fla/ops/gla/chunk_util.py:28-65 (prepare_qg_kg) materialises, for lina_gla_chunk_fwd_pregated_bthd.
  * v = SiLU(ShortConvolution(x_v)) as above; xq / xk / xv have their own row strides (separate or concatenated GEMMs).
- * The gate normalizer must be a power of two (16 in the shipped model). */
+ * The gate normalizer must be a power of two (16 in the shipped model).
+ * ``envelope_flag`` (device int, nullable): OR-ed with 1 when the summed log gate of any (chunk, channel) falls below -80,
+ * i.e. outside the range the single-pivot tensor-core kernel represents (the reference is exact for any gate,
+ * FLA/fla/ops/gla/chunk_fuse.py:238-247 computes the intra-chunk scores with per-pair exponent differences): the caller
+ * must then serve the call through lina_gla_prefill_prep + the exact recurrence instead. */
 int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const void *xk, long long ldk, const void *xv, long long ldv,
                                 const void *wq, const void *wk, const void *wv, const void *gk_raw, long long ldg,
                                 void *qg, void *kg, void *v, float *decay, void *cq, void *ck, void *cv, int cache_dtype,
-                                int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale, void *stream);
+                                int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale,
+                                int *envelope_flag, void *stream);
 /* The chunkwise GLA forward (lina_gla_chunk_fwd_bthd) on those pre-gated operands: no in-kernel gate pre-pass, gk is
  * never read.  Tensor-core envelope only. */
 int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,

@@ -22,6 +22,27 @@ from torch import nn
 from .. import _lib as L
 
 
+# bench hook: a list collects (stage, algorithmic bytes, start event, end event) around every kernel of ours
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name: str, nbytes: int, ref: torch.Tensor):
+        self.name, self.nbytes, self.ref = name, nbytes, ref
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.ref.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream(self.ref.device))
+            PROFILE.append((self.name, self.nbytes, self.e0, self.e1))
+        return False
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     L.require_cuda(t)
     return t.float().contiguous()
@@ -31,8 +52,9 @@ def groupnorm_swish(x, weight, bias, groups: int, eps: float, swish: bool):
     x = _f32c(x)
     B, C, Ln = x.shape
     y = torch.empty_like(x)
-    rc = L.lib().lina_codec_groupnorm_swish(L.ptr(x), L.ptr(_f32c(weight)), L.ptr(_f32c(bias)), L.ptr(y), None,
-                                            B, C, Ln, groups, eps, int(swish), L.stream(x))
+    with _timed("groupnorm_swish", 8 * x.numel(), x):
+        rc = L.lib().lina_codec_groupnorm_swish(L.ptr(x), L.ptr(_f32c(weight)), L.ptr(_f32c(bias)), L.ptr(y), None,
+                                                B, C, Ln, groups, eps, int(swish), L.stream(x))
     L.count_launches(1)
     L.check(rc, "lina_codec_groupnorm_swish")
     return y
@@ -48,8 +70,9 @@ def dwconv_adaln(x, dw_w, dw_b, scale, shift, eps: float):
         raise NotImplementedError("depthwise kernel size must be 7 (ConvNeXtBlock, modules.py:28)")
     lib = L.lib()
     if w is None:       # no conv: the single kernel (all channels of a 32-step tile per CTA) measures faster (0.052 vs 0.084 ms)
-        rc = lib.lina_codec_dwconv_adaln(L.ptr(x), None, None, L.ptr(_f32c(scale)), L.ptr(_f32c(shift)), L.ptr(y), B, C, Ln,
-                                         eps, L.stream(x))
+        with _timed("layernorm_t", 8 * x.numel(), x):
+            rc = lib.lina_codec_dwconv_adaln(L.ptr(x), None, None, L.ptr(_f32c(scale)), L.ptr(_f32c(shift)), L.ptr(y), B, C, Ln,
+                                             eps, L.stream(x))
         L.count_launches(1)
         L.check(rc, "lina_codec_dwconv_adaln")
         return y
@@ -57,8 +80,9 @@ def dwconv_adaln(x, dw_w, dw_b, scale, shift, eps: float):
     if sc.data_ptr() % 16 or sh.data_ptr() % 16:          # rows of an embedding table: the apply kernel reads them as float4
         sc, sh = sc.clone(), sh.clone()
     ws = torch.empty(int(lib.lina_codec_dwconv_adaln_workspace_bytes(B, C, Ln)), dtype=torch.uint8, device=x.device)
-    rc = lib.lina_codec_dwconv_adaln_ws(L.ptr(x), L.ptr(w), L.ptr(_f32c(dw_b)) if dw_b is not None else None,
-                                        L.ptr(sc), L.ptr(sh), L.ptr(y), L.ptr(ws), B, C, Ln, eps, L.stream(x))
+    with _timed("dwconv_adaln", 8 * x.numel(), x):
+        rc = lib.lina_codec_dwconv_adaln_ws(L.ptr(x), L.ptr(w), L.ptr(_f32c(dw_b)) if dw_b is not None else None,
+                                            L.ptr(sc), L.ptr(sh), L.ptr(y), L.ptr(ws), B, C, Ln, eps, L.stream(x))
     L.count_launches(2)
     L.check(rc, "lina_codec_dwconv_adaln_ws")
     return y
@@ -69,8 +93,9 @@ def scale_residual_t(h, gamma, res):
     h, res = _f32c(h), _f32c(res)
     B, Ln, C = h.shape
     out = torch.empty_like(res)
-    rc = L.lib().lina_codec_scale_residual_t(L.ptr(h), L.ptr(_f32c(gamma)) if gamma is not None else None,
-                                             L.ptr(res), L.ptr(out), B, C, Ln, L.stream(h))
+    with _timed("scale_residual_t", 12 * h.numel(), h):
+        rc = L.lib().lina_codec_scale_residual_t(L.ptr(h), L.ptr(_f32c(gamma)) if gamma is not None else None,
+                                                 L.ptr(res), L.ptr(out), B, C, Ln, L.stream(h))
     L.count_launches(1)
     L.check(rc, "lina_codec_scale_residual_t")
     return out
@@ -128,8 +153,11 @@ class AdaLayerNorm(nn.Module):
         nn.init.zeros_(self.shift.weight)
 
     def rows(self, cond_embedding_id):
-        i = int(cond_embedding_id.reshape(-1)[0]) if torch.is_tensor(cond_embedding_id) else int(cond_embedding_id)
-        return self.scale.weight[i], self.shift.weight[i]
+        """(scale, shift) rows of the conditioning id: a device-side gather (no host read of the id tensor)."""
+        if torch.is_tensor(cond_embedding_id):
+            i = cond_embedding_id.reshape(-1)[:1].to(self.scale.weight.device)
+            return self.scale.weight.index_select(0, i)[0], self.shift.weight.index_select(0, i)[0]
+        return self.scale.weight[int(cond_embedding_id)], self.shift.weight[int(cond_embedding_id)]
 
 
 class ConvNeXtBlock(nn.Module):
@@ -220,8 +248,9 @@ class ISTFTHead(nn.Module):
         lib = L.lib()
         wav = torch.empty(B, Ln * hop, dtype=torch.float32, device=h.device)
         ws = torch.empty(int(lib.lina_codec_istft_workspace_bytes(B, Ln, n_fft)), dtype=torch.uint8, device=h.device)
-        rc = lib.lina_codec_istft_head(L.ptr(h), L.ptr(_f32c(self.istft.window)), L.ptr(wav), L.ptr(ws), B, Ln,
-                                       n_fft, hop, L.stream(h))
+        with _timed("istft_head", 4 * (h.numel() + wav.numel()), h):
+            rc = lib.lina_codec_istft_head(L.ptr(h), L.ptr(_f32c(self.istft.window)), L.ptr(wav), L.ptr(ws), B, Ln,
+                                           n_fft, hop, L.stream(h))
         L.count_launches(2)
         L.check(rc, "lina_codec_istft_head")
         return wav
@@ -328,8 +357,9 @@ class WavTokenizer(nn.Module):
         books = _f32c(self.feature_extractor.codebooks())
         bins, C = self.feature_extractor.encodec.quantizer.bins, books.shape[1]
         out = torch.empty(B, C, Ln, dtype=torch.float32, device=codes.device)
-        rc = L.lib().lina_codec_codes_to_features(L.ptr(codes), L.ptr(books), L.ptr(out), Kq, B, Ln, bins, C,
-                                                  L.stream(codes))
+        with _timed("codes_to_features", 8 * codes.numel() + 4 * Kq * out.numel() + 4 * out.numel(), out):
+            rc = L.lib().lina_codec_codes_to_features(L.ptr(codes), L.ptr(books), L.ptr(out), Kq, B, Ln, bins, C,
+                                                      L.stream(codes))
         L.count_launches(1)
         L.check(rc, "lina_codec_codes_to_features")
         return out

@@ -51,6 +51,24 @@ def install_reference_aliases(force: bool = False) -> dict:
     pretrained = _module("decoder.pretrained", WavTokenizer=codec.WavTokenizer)
     table["decoder"] = _module("decoder", pretrained=pretrained, __path__=[])
     table["decoder.pretrained"] = pretrained
+    # the sub-modules pickled inside a reference checkpoint name fla's classes by module path
+    # (fla.modules.convolution.ShortConvolution, fla.modules.fused_norm_gate.FusedRMSNormSwishGate, fla.models.utils.Cache)
+    from . import fla_api
+    from .fla_api import modules as fm, ops as fo
+    gla_ops = _module("fla.ops.gla", fused_recurrent_gla=fo.fused_recurrent_gla, fused_chunk_gla=fo.fused_chunk_gla,
+                      chunk_gla=fo.chunk_gla, __path__=[])
+    rwkv_ops = _module("fla.ops.rwkv6", fused_recurrent_rwkv6=fo.fused_recurrent_rwkv6, chunk_rwkv6=fo.chunk_rwkv6, __path__=[])
+    fla_ops = _module("fla.ops", gla=gla_ops, rwkv6=rwkv_ops, __path__=[])
+    conv = _module("fla.modules.convolution", ShortConvolution=fm.ShortConvolution)
+    fng = _module("fla.modules.fused_norm_gate", FusedRMSNormSwishGate=fm.FusedRMSNormSwishGate)
+    fmods = _module("fla.modules", ShortConvolution=fm.ShortConvolution, FusedRMSNormSwishGate=fm.FusedRMSNormSwishGate,
+                    convolution=conv, fused_norm_gate=fng, __path__=[])
+    futils = _module("fla.models.utils", Cache=fm.Cache)
+    fmodels = _module("fla.models", utils=futils, __path__=[])
+    table.update({"fla": _module("fla", ops=fla_ops, modules=fmods, models=fmodels, __path__=[], __version__="lina_speech_b200"),
+                  "fla.ops": fla_ops, "fla.ops.gla": gla_ops, "fla.ops.rwkv6": rwkv_ops, "fla.modules": fmods,
+                  "fla.modules.convolution": conv, "fla.modules.fused_norm_gate": fng, "fla.models": fmodels,
+                  "fla.models.utils": futils})
     done = {}
     for name, mod in table.items():
         if force or name not in sys.modules:

@@ -247,7 +247,11 @@ struct GateArgs {
     long long ldq, ldk, ldg;
     int B, L, Dk, K, NT, cache_dtype;
     float log2_scale, gate_c;        // gate_c = log2(e) / normalizer
+    int *envelope_flag;              // set to 1 when a chunk's summed log2 gate leaves the single-pivot range (nullable)
 };
+
+// the tensor-core kernel keeps one pivot per 64-token chunk: k~ = k e^-G needs |G| (natural log) below ~85; flag at 80
+constexpr float GATE_ENVELOPE_LOG2 = -80.f * 1.44269504088896340736f;
 
 constexpr int GC = 64;               // chunk length of gla_chunk_sm100.cu
 constexpr int GRB = 4;               // rows per load batch
@@ -325,6 +329,9 @@ qk_gate_bf16_kernel(const __grid_constant__ GateArgs a) {
         }
     }
     // (rows past the end of a partial last chunk contribute gk = 0, like the TMA zero fill of the in-kernel pre-pass)
+    if (a.envelope_flag != nullptr &&
+        fminf(fminf(G[0].x, G[0].y), fminf(G[1].x, G[1].y)) < GATE_ENVELOPE_LOG2)
+        atomicOr(a.envelope_flag, 1);
     const int h = d0 / a.K, kap = d0 - h * a.K;
     const int H = a.Dk / a.K;
     *reinterpret_cast<float4 *>(a.decay + (((size_t)b * H + h) * a.NT + n) * a.K + kap) =
@@ -432,7 +439,7 @@ extern "C" int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const 
                                            const void *wk, const void *wv, const void *gk_raw, long long ldg, void *qg,
                                            void *kg, void *v, float *decay, void *cq, void *ck, void *cv, int cache_dtype,
                                            int B, int L, int H, int K, int V, int W, float gate_normalizer, float scale,
-                                           void *stream) {
+                                           int *envelope_flag, void *stream) {
     LINA_REQUIRE(xq && xk && xv && wq && wk && wv && gk_raw && qg && kg && v && decay, LINA_ERR_BAD_ARG,
                  "gla_prefill_prep_gated: null pointer");
     LINA_REQUIRE(B > 0 && L > 0 && H > 0 && K > 0 && V > 0 && gate_normalizer != 0.f && scale > 0.f, LINA_ERR_BAD_ARG,
@@ -456,6 +463,7 @@ extern "C" int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const 
     a.wq = (const bf16 *)wq; a.wk = (const bf16 *)wk; a.qg = (bf16 *)qg; a.kg = (bf16 *)kg; a.decay = decay;
     a.cq = cq; a.ck = ck; a.ldq = ldq; a.ldk = ldk; a.ldg = ldg; a.B = B; a.L = L; a.Dk = Dk; a.K = K; a.NT = (L + GC - 1) / GC;
     a.cache_dtype = cache_dtype;
+    a.envelope_flag = envelope_flag;
     a.log2_scale = log2f(scale);
     a.gate_c = 1.44269504088896340736f / gate_normalizer;
     const long long nthreads = (long long)B * a.NT * (Dk / 4);

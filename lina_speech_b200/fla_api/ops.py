@@ -120,6 +120,8 @@ def _route(kind: str, q, v, gk, uses_tc):
     B, H, T, K = q.shape
     if not uses_tc(B, H, T, K, v.shape[-1], L._DT.get(q.dtype, -1)):
         return kind, None
+    if q.is_cuda and torch.cuda.is_current_stream_capturing():
+        return kind, None            # a host read is illegal during graph capture: the caller vouches for the gates
     ok = _gates_in_envelope(gk)
     return (kind if ok else "recurrent"), ok
 

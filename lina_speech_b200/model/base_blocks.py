@@ -63,7 +63,8 @@ class SwiGLU(nn.Module):
         super().__init__()
         self.p_in = nn.Linear(d_model, (d_model * 4 // 3) * 2)
         self.p_out = nn.Linear(d_model * 4 // 3, d_model)
-        self._padded = None
+
+    _padded = None       # class-level default (un-pickled reference instances never ran this __init__)
 
     def _padded_weights(self):
         ps = (self.p_in.weight, self.p_in.bias, self.p_out.weight, self.p_out.bias)
@@ -80,7 +81,8 @@ class SwiGLU(nn.Module):
         return self._padded[1:]
 
     def forward(self, x):
-        if x.is_cuda and not torch.is_grad_enabled() and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        if (x.is_cuda and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+                and x.dtype == self.p_in.weight.dtype and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
             from .. import _lib as L
             hp, wi_p, bi_p, wo_p = self._padded_weights()
             h = F.linear(x, wi_p, bi_p)
@@ -182,7 +184,8 @@ class MixingBlock(nn.Module):
     # -- inference fast path: residual adds fused into the following LayerNorm -------------------------------
     def can_fuse(self, x) -> bool:
         n = self.norm1
-        return (not torch.is_grad_enabled() and not self.training and x.is_cuda and isinstance(n, nn.LayerNorm)
+        return (not torch.is_grad_enabled() and not self.training and not torch.is_autocast_enabled()
+                and x.is_cuda and isinstance(n, nn.LayerNorm)
                 and n.elementwise_affine and n.bias is not None and x.dtype == n.weight.dtype
                 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
                 and x.shape[-1] % (16 // x.element_size()) == 0 and x.shape[-1] // (16 // x.element_size()) <= 256)
@@ -205,8 +208,10 @@ def add_layernorm(a, x, norm: nn.LayerNorm):
     N = xs.shape[-1]
     M = xs.numel() // N
     ln = torch.empty_like(xs)
+    if norm.weight.dtype != xs.dtype:
+        raise TypeError(f"add_layernorm: LayerNorm parameters are {norm.weight.dtype}, input is {xs.dtype}")
     if a is not None:
-        a = a.contiguous()
+        a = a.to(xs.dtype).contiguous()          # one dtype argument describes every buffer the kernel reads
         s = torch.empty_like(xs)
     else:
         s = None

@@ -58,16 +58,29 @@ class BlindCrossAttention(nn.Module):
             raise NotImplementedError("BlindCrossAttention(rotary=True) is not used by the shipped model")
         self.rotary = None
         self.dropout_att = nn.Dropout(dropout)
+
+    _memo = None          # class-level default: instances un-pickled from a reference checkpoint never ran __init__
+
+    def clear_memo(self):
         self._memo = None
 
+    def _memo_key(self, ctx):
+        ps = [p for m in (self.k, self.v, self.ln_k, self.ln_v, self.pos_embed) for p in m.parameters()]
+        return (ctx.data_ptr(), tensor_version(ctx), tuple(ctx.shape), tuple(ctx.stride()), ctx.dtype, ctx.device,
+                tuple((p.data_ptr(), tensor_version(p), p.dtype) for p in ps))
+
     def _text_side(self, ctx, pos):
-        """ln_k(k(ctx)), ln_v(v(ctx)), pos_emb -- memoised across decode steps in eval mode."""
+        """ln_k(k(ctx)), ln_v(v(ctx)), pos_emb -- memoised across decode steps in eval mode.
+
+        The memo holds a reference to ``ctx`` itself, so its storage cannot be freed and handed to the next utterance's
+        text tensor while the entry is alive (data_ptr alone is not an identity); callers that start a new utterance
+        (LinaModel.forward / generate_batch) also clear it."""
         key = None
         if not self.training and pos is None and not torch.is_grad_enabled():
-            key = (ctx.data_ptr(), tensor_version(ctx), tuple(ctx.shape), ctx.dtype,
-                   tensor_version(self.k.weight), tensor_version(self.v.weight))
-            if self._memo is not None and self._memo[0] == key:
-                return self._memo[1]
+            key = self._memo_key(ctx)
+            m = self._memo
+            if m is not None and (m[0] is ctx or m[0].data_ptr() == ctx.data_ptr()) and m[1] == key:
+                return m[2]
         v = self.ln_v(self.v(ctx)).unsqueeze(1)
         k = self.ln_k(self.k(ctx)).unsqueeze(1)
         if pos is None:
@@ -75,7 +88,7 @@ class BlindCrossAttention(nn.Module):
         pos_emb = self.pos_embed(pos).unsqueeze(1)
         out = (k, v, pos_emb)
         if key is not None:
-            self._memo = (key, out)
+            self._memo = (ctx, key, out)
         return out
 
     def forward(self, q, k, mask=None, time_step=None, pos=None, **kwargs):

@@ -39,6 +39,44 @@ PREGATED = os.environ.get("LINA_PREGATED", "1") != "0"
 # "cat4": one [q;k;v;g] GEMM; "split": four GEMMs (the pre-gated pass and the norm-gate read each output in place)
 GEMM_GROUPING = os.environ.get("LINA_GEMM_GROUPING", "split")
 
+
+
+class GateEnvelope:
+    """Device-side record of "a chunk's summed log gate left the range of the single-pivot tensor-core kernel" (written by
+    lina_gla_prefill_prep_gated) and the policy for reading it.  A lone GatedLinearAttention call reads the flag right away
+    (one host read) and re-serves the call exactly; inside a backbone pass (``GateEnvelope.deferred``) the 13 mixers only
+    accumulate into the flag and the backbone reads it ONCE at the end -- no per-layer host synchronisation."""
+    _flags = {}
+    depth = 0
+
+    @classmethod
+    def flag(cls, device) -> torch.Tensor:
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        f = cls._flags.get(key)
+        if f is None:
+            with torch.inference_mode(False):
+                f = cls._flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return f
+
+    @classmethod
+    def tripped(cls, device) -> bool:
+        """Read and clear (host synchronisation).  Never called during graph capture."""
+        f = cls.flag(device)
+        hit = bool(f.item())
+        if hit:
+            f.zero_()
+        return hit
+
+    class deferred:
+        def __enter__(self):
+            GateEnvelope.depth += 1
+            return self
+
+        def __exit__(self, *exc):
+            GateEnvelope.depth -= 1
+            return False
+
+
 if "GRAD_CKPT" in os.environ:        # model/gla.py:26-33
     def maybe_grad_ckpt(f):
         def wrapped(*args, **kwargs):
@@ -85,7 +123,6 @@ class GatedLinearAttention(nn.Module):
         self.g_norm_swish_gate = FusedRMSNormSwishGate(self.head_v_dim, eps=layernorm_eps)
         self.fuse_norm_and_gate = True
         self.gate_logit_normalizer = gate_logit_normalizer
-        self._wcat = None
         self.apply(self._initialize_weights)
 
     def _initialize_weights(self, module: nn.Module):       # model/gla.py:122-129
@@ -96,6 +133,11 @@ class GatedLinearAttention(nn.Module):
             if module.bias is not None:
                 nn.init.zeros_(module.bias)
         module._is_hf_initialized = True
+
+    # lazily built weight caches; class-level defaults so that instances un-pickled from a reference checkpoint
+    # (TrainLina.load_from_checkpoint restores __dict__ without running __init__) have them too
+    _wcat = None
+    _wcat4 = None
 
     # -- single-token fast path --------------------------------------------------------------------
     def _cat_weight(self):
@@ -110,6 +152,8 @@ class GatedLinearAttention(nn.Module):
         B = x.shape[0]
         H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
         proj = F.linear(x.view(B, -1), self._cat_weight())
+        if proj.dtype != x.dtype:
+            raise TypeError(f"GatedLinearAttention._step: projection is {proj.dtype}, input is {x.dtype}")
         xq, xk, xv, g, lo = torch.split(proj, [kd, kd, vd, vd, proj.shape[1] - 2 * kd - 2 * vd], dim=1)
         ldx = proj.shape[1]                            # the four slices are read in place with this row stride
         if self.use_short_conv:
@@ -153,6 +197,7 @@ class GatedLinearAttention(nn.Module):
 
     def _can_prefill(self, x, reset_mask, attention_mask) -> bool:
         return (FUSED_PREFILL and self.use_short_conv and self.conv_size == 4 and not torch.is_grad_enabled()
+                and not torch.is_autocast_enabled()      # raw-pointer path: every buffer must really be x.dtype
                 and reset_mask is None and attention_mask is None
                 and x.dtype in (torch.bfloat16, torch.float16, torch.float32)
                 and self.key_dim % 8 == 0 and self.head_v_dim % 8 == 0
@@ -186,6 +231,9 @@ class GatedLinearAttention(nn.Module):
             xq, xk, xv, g = (proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd],
                              proj[..., 2 * kd + vd:2 * kd + 2 * vd])
         gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
+        for t_ in (xq, xk, xv, g, gk_raw):                   # raw-pointer path: one dtype argument describes them all
+            if t_.dtype != x.dtype:
+                raise TypeError(f"GatedLinearAttention._prefill: projection is {t_.dtype}, input is {x.dtype}")
         ldq, ldk, ldv, ldgate = xq.stride(1), xk.stride(1), xv.stride(1), g.stride(1)
         cq = ck = cv = None
         if use_cache and last_state is not None:
@@ -201,12 +249,17 @@ class GatedLinearAttention(nn.Module):
             # q, k hold the gated MMA operands q~ = scale q e^G, k~ = k e^-G; gk is never materialised
             nt = (T + 63) // 64
             decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=x.device)
+            check = fla_ops.GATE_CHECK and not torch.cuda.is_current_stream_capturing()
+            flag = GateEnvelope.flag(x.device) if check else None
             rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldq, L.ptr(xk), ldk, L.ptr(xv), ldv, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                                  L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay),
                                                  L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0,
-                                                 B, T, H, K, V, self.conv_size, norm, float(K) ** -0.5, L.stream(x))
+                                                 B, T, H, K, V, self.conv_size, norm, float(K) ** -0.5, L.ptr(flag), L.stream(x))
             L.count_launches(2)
             L.check(rc, "lina_gla_prefill_prep_gated")
+            if check and GateEnvelope.depth == 0 and GateEnvelope.tripped(x.device):
+                pregated = False          # gates beyond e^-80 per chunk: serve this call with the exact kernels below
+        if pregated:
             h0 = recurrent_state.contiguous() if recurrent_state is not None else None
             o = torch.empty(B, T, H, V, dtype=x.dtype, device=x.device)
             ht = torch.empty(B, H, K, V, dtype=torch.float32, device=x.device) if use_cache else None
@@ -227,7 +280,11 @@ class GatedLinearAttention(nn.Module):
                 past_key_values.update((cq, ck, cv, recurrent_state), self.layer_idx, T)
         else:
             gk = torch.empty_like(q)
-            ldx = ldq                                     # this entry takes one row stride: always the concatenated GEMM
+            if not (ldq == ldk == ldv):                   # this entry takes ONE row stride: pack the split GEMMs' outputs
+                packed = torch.cat([xq, xk, xv], dim=-1)
+                xq, xk, xv = packed[..., :kd], packed[..., kd:2 * kd], packed[..., 2 * kd:]
+                ldq = packed.stride(1)
+            ldx = ldq
             rc = lib.lina_gla_prefill_prep(L.ptr(xq), L.ptr(xk), L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                            L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk),
                                            L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0, B, T, kd, vd,
@@ -255,6 +312,7 @@ class GatedLinearAttention(nn.Module):
 
     def _can_step(self, x, state, reset_mask, attention_mask) -> bool:
         return (x.shape[1] == 1 and state is not None and not self.training and not torch.is_grad_enabled()
+                and not torch.is_autocast_enabled() and self.q_proj.weight.dtype == x.dtype
                 and reset_mask is None and attention_mask is None and self.clamp_min is None
                 and x.dtype in (torch.float32, torch.bfloat16) and state[-1].dtype in (torch.float32, torch.bfloat16)
                 and self.head_v_dim % 8 == 0 and self.head_qk_dim <= 256)
@@ -376,16 +434,7 @@ class AttentiveGLA(AttentiveRNN):
                 init_state=None, crossatt_pos=None):
         """model/gla.py:287-300.  NB the cross attention's pos_net never sees ``init_state`` here."""
         if self.encoder[0].can_fuse(x):                       # inference: adds folded into the LayerNorms
-            kw = dict(use_cache=init_state is not None, past_key_values=init_state)
-            xr, d = x, None
-            for e in self.encoder:
-                xr, d = e.forward_fused(xr, d, **kw)
-            x = xr + d
-            v, att = self.cross_att(x, ctx, mask=mask, reset_mask=reset_mask, pos=crossatt_pos)
-            xr, d = x, v
-            for dd in self.decoder:
-                xr, d = dd.forward_fused(xr, d, **kw)
-            return xr + d, att
+            return self._forward_fused(x, ctx, mask, reset_mask, init_state, crossatt_pos)
         for e in self.encoder:
             if self.training:
                 e = maybe_grad_ckpt(e)
@@ -397,6 +446,41 @@ class AttentiveGLA(AttentiveRNN):
                 d = maybe_grad_ckpt(d)
             x = d(x, use_cache=init_state is not None, past_key_values=init_state)
         return x, att
+
+    def _forward_fused(self, x, ctx, mask, reset_mask, init_state, crossatt_pos):
+        """Inference pass with the residual adds folded into the LayerNorms.  The 13 mixers run on the pre-gated tensor-core
+        kernels without looking at their gates one by one; the gate-envelope flag they accumulate is read ONCE here."""
+        def run():
+            kw = dict(use_cache=init_state is not None, past_key_values=init_state)
+            xr, d = x, None
+            for e in self.encoder:
+                xr, d = e.forward_fused(xr, d, **kw)
+            xe = xr + d
+            v, att = self.cross_att(xe, ctx, mask=mask, reset_mask=reset_mask, pos=crossatt_pos)
+            xr, d = xe, v
+            for dd in self.decoder:
+                xr, d = dd.forward_fused(xr, d, **kw)
+            return xr + d, att
+
+        capturing = torch.cuda.is_current_stream_capturing()
+        snap = None
+        if init_state is not None and not capturing and fla_ops.GATE_CHECK and x.shape[1] > 1:
+            snap = [tuple(t.clone() for t in st) for st in init_state.states]      # the pass updates the cache in place
+        with GateEnvelope.deferred():
+            out = run()
+        if capturing or not fla_ops.GATE_CHECK or x.shape[1] == 1 or not GateEnvelope.tripped(x.device):
+            return out
+        # some chunk's summed log gate fell below -80: redo the pass with the exact kernels (the reference is exact for any gate)
+        if snap is not None:
+            for st, sn in zip(init_state.states, snap):
+                for a, b in zip(st, sn):
+                    a.copy_(b)
+        global PREGATED
+        old, PREGATED = PREGATED, False
+        try:
+            return run()
+        finally:
+            PREGATED = old
 
     def init_state(self, max_seqlen=1000, batch_size=16):
         """model/gla.py:302-313."""
@@ -445,16 +529,38 @@ class AttentiveGLA(AttentiveRNN):
     def step(self, y_embd, x_enc, time_step, cache):
         """model/gla.py:358-365: one token through every block, all blocks stateful."""
         if self.encoder[0].can_fuse(y_embd):
-            kw = dict(past_key_values=cache, use_cache=True)
-            xr, d = y_embd, None
-            for e in self.encoder:
-                xr, d = e.forward_fused(xr, d, **kw)
-            y = xr + d
-            v, att = self.cross_att(y, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)
-            xr, d = y, v
-            for dd in self.decoder:
-                xr, d = dd.forward_fused(xr, d, **kw)
-            return xr + d, att, cache
+            def run():
+                kw = dict(past_key_values=cache, use_cache=True)
+                xr, d = y_embd, None
+                for e in self.encoder:
+                    xr, d = e.forward_fused(xr, d, **kw)
+                y = xr + d
+                v, att = self.cross_att(y, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)
+                xr, d = y, v
+                for dd in self.decoder:
+                    xr, d = dd.forward_fused(xr, d, **kw)
+                return xr + d, att, cache
+
+            if y_embd.shape[1] == 1 or torch.cuda.is_current_stream_capturing() or not fla_ops.GATE_CHECK:
+                return run()                                  # single-token steps run the exact recurrence (lina_gla_step)
+            # multi-token prompt prefill: same deferred gate-envelope policy as _forward_fused
+            snap = [tuple(t.clone() for t in st) for st in cache.states]
+            seen = getattr(cache, "_seen_tokens", None)
+            with GateEnvelope.deferred():
+                out = run()
+            if not GateEnvelope.tripped(y_embd.device):
+                return out
+            for st, sn in zip(cache.states, snap):
+                for a, b in zip(st, sn):
+                    a.copy_(b)
+            if seen is not None:
+                cache._seen_tokens = seen
+            global PREGATED
+            old, PREGATED = PREGATED, False
+            try:
+                return run()
+            finally:
+                PREGATED = old
         for e in self.encoder:
             y_embd = e(y_embd, past_key_values=cache, use_cache=True)
         v, att = self.cross_att(y_embd, x_enc, time_step=time_step, past_key_values=cache, use_cache=True)

@@ -89,6 +89,7 @@ class LinaModel(nn.Module):
         x_embd = self.txt_embed(x)
         y_embd = self.rvq_embed(rearrange(y, "b n q -> q b n")).sum(0)
         x_enc = self.txt_encoder(x_embd, mask=encoder_mask)
+        self._new_text()
         if self.spk_encoder is not None:
             y_embd[:, 0] = self.spk_encoder(y_embd)
         y_hat, att = self.attentive_rnn(
@@ -108,6 +109,12 @@ class LinaModel(nn.Module):
             loss = F.cross_entropy(masked_logits.reshape(-1, masked_logits.shape[-1]).float(),
                                    masked_target.reshape(-1), ignore_index=1)
         return logits, loss, att, masked_logits, masked_target
+
+    def _new_text(self):
+        """A new text tensor enters the backbone: drop the cross attention's memo of the previous one."""
+        ca = getattr(self.attentive_rnn, "cross_att", None)
+        if ca is not None and hasattr(ca, "clear_memo"):
+            ca.clear_memo()
 
     @staticmethod
     def _fused_cross_entropy(logits, y, logits_mask):
@@ -190,6 +197,7 @@ class LinaModel(nn.Module):
             if self.spk_encoder is not None:
                 prompt[:, 0] = self.spk_encoder(prompt)
         x_enc = self.txt_encoder(x_embd)
+        self._new_text()
         state = init_state
         if state is None:
             state = self.attentive_rnn.init_state(max_seqlen=max_seqlen, batch_size=batch_size)
@@ -283,4 +291,5 @@ class LinaModel(nn.Module):
             idx = torch.unique(stop_idx[i])[1]
             a = atts[i, :, :idx] if (atts is not None and i < atts.shape[0] and world == 1) else None
             cuts.append((rvq[:, [i], :idx - self.n_quant], a))
+        self._new_text()                                        # release the memo's hold on this utterance's text
         return qs, atts, stop_tokens, cuts

@@ -145,6 +145,57 @@ def chunk_gla(q, k, v, gk, scale: Optional[float] = None, initial_state=None, ch
     return o.to(odt), S.to(torch.float32)
 
 
+def fused_chunk_gla_as_reference_rounds(q, k, v, gk, scale: Optional[float] = None, initial_state=None):
+    """The reference's DEFAULT op ``fused_chunk_gla`` with every rounding it performs on low-precision inputs, in CPU torch
+    (FLA/fla/ops/gla/chunk_fuse.py:302-399).  Used to bound OUR error by the REFERENCE's own: both are compared against
+    the fp64 recurrence on identical inputs.  With dt = the input dtype (bf16 / fp16), BT = 16, BK = BV = 64:
+
+      * g  = fp32 cumsum inside each 16-token chunk                          (chunk_util.py:5-26)
+      * q_g = dt(q e^g scale), k_g = dt(k e^{g_last - g})                     (chunk_util.py:28-65)
+      * inter: per K block, o_part = dt(q_g @ dt(h)), h = h e^{g_last} + k_g^T v in fp32, the NK partial outputs are
+        stored in dt and summed by torch (fp32 accumulate, one rounding)       (chunk_fuse.py:77-99,323,367)
+      * intra: A = dt(sum_k q scale k e^{g_t - g_s}) per K block (fp32 math, dt store), summed over blocks likewise,
+        o2 = dt(A @ v), o = dt(o + o2)                                         (chunk_fuse.py:238-247,376-390)
+
+    Pinned to the reference itself: tests/golden/gla_triton_bf16.npz holds the outputs of the reference's Triton kernels run
+    on a B200 (profiles/triton_reference_bench.py); this function reproduces them (tests/test_oracle.py).
+
+    T must be a multiple of 16 (the reference pads).  Returns (o in dt, final state fp32)."""
+    dt = v.dtype
+    B, H, T, K = q.shape
+    V = v.shape[-1]
+    BT, BK = 16, min(K, 64)
+    assert T % BT == 0
+    if scale is None or scale == -1:
+        scale = K ** -0.5
+    r = lambda x: x.to(dt).float()
+    qf, kf, vf = q.float(), k.float(), v.float()
+    n = T // BT
+    g = gk.float().view(B, H, n, BT, K).cumsum(3)
+    qc, kc, vc = qf.view(B, H, n, BT, K), kf.view(B, H, n, BT, K), vf.view(B, H, n, BT, V)
+    g_last = g[:, :, :, -1:]
+    qg = r(qc * g.exp() * scale)
+    kg = r(kc * (g_last - g).exp())
+    h = torch.zeros(B, H, K, V) if initial_state is None else initial_state.float().clone()
+    o = torch.zeros(B, H, n, BT, V)
+    for i in range(n):
+        part = torch.zeros(B, H, BT, V)
+        hr = r(h)
+        for k0 in range(0, K, BK):             # NK partial outputs, each stored in dt; torch's sum(0) adds them in fp32
+            part = part + r(torch.einsum("bhtk,bhkv->bhtv", qg[:, :, i, :, k0:k0 + BK], hr[:, :, k0:k0 + BK]))
+        o[:, :, i] = r(part)                   # ... and rounds the sum once
+        h = h * g_last[:, :, i, 0].exp().unsqueeze(-1) + torch.einsum("bhsk,bhsv->bhkv", kg[:, :, i], vc[:, :, i])
+    A = torch.zeros(B, H, n, BT, BT)
+    for k0 in range(0, K, BK):
+        sl = slice(k0, k0 + BK)
+        e = (g[:, :, :, :, None, sl] - g[:, :, :, None, :, sl]).exp()     # [.., t, s, k]
+        a = ((qc[..., sl] * scale)[:, :, :, :, None] * kc[..., sl][:, :, :, None] * e).sum(-1).tril()
+        A = A + r(a)
+    A = r(A)
+    o2 = r(torch.einsum("bhnts,bhnsv->bhntv", A, vc))
+    return r(o + o2).view(B, H, T, V).to(dt), h
+
+
 def pregated_chunk_fwd(qg, kg, v, decay, h0=None, row_decay: bool = False, chunk: int = 64, acc_dtype=torch.float32):
     """Contract of the pre-gated tensor-core kernel (lina_gla_chunk_fwd_pregated) restated in torch, for CPU tests of the
     host-side backward that is built from it: per 64-token chunk  o = qg S + tril(qg kg^T) v ;  S' = decay (.) (S + kg^T v),

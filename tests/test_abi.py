@@ -79,7 +79,7 @@ def test_new_entry_points_validate_arguments_without_a_device():
     lib = _lib.lib()
     err = lambda: lib.lina_last_error_string().decode()
     assert lib.lina_gla_prefill_prep_gated(None, 0, None, 0, None, 0, None, None, None, None, 0, None, None, None, None, None,
-                                           None, None, 0, 1, 8, 4, 256, 512, 4, 16.0, 0.0625, None) == -1
+                                           None, None, 0, 1, 8, 4, 256, 512, 4, 16.0, 0.0625, None, None) == -1
     assert "null pointer" in err()
     assert lib.lina_gla_chunk_fwd_pregated_bthd(None, None, None, None, None, 0, None, None, 1, 4, 128, 256, 512, None) == -1
     assert lib.lina_gla_chunk_fwd_pregated(None, None, None, None, None, 0, None, None, 1, 4, 128, 256, 512, 0, 0, 0, 0, 0, 0,

@@ -70,8 +70,7 @@ def test_istft_head_alone_against_torch_irfft():
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), f"istft max err {err:.3e} (ref absmax {ref.abs().max():.2f})"
 
 
-@pytest.mark.parametrize("B,Ln", [(5, 77), pytest.param(4, 700, marks=pytest.mark.skipif(
-    not os.environ.get("LINA_BRINGUP"), reason="more frames than one pass of the persistent grid: first run in round 2"))])
+@pytest.mark.parametrize("B,Ln", [(5, 77), (4, 700)])      # 2800 frames: more than one pass of the persistent grid
 def test_istft_warp_per_frame_kernel_matches_the_generic_one(B, Ln):
     """variant key 8: the fixed-radix warp-per-frame FFT (csrc/fft640.cuh; host-checked in tests/test_host.py)."""
     from lina_speech_b200.codec import ISTFTHead
@@ -102,3 +101,39 @@ def test_tf32_gemm_mode_stays_close(golden_codec):
     rel = ((wav.cpu() - ref).norm() / ref.norm()).item()         # exp() in the head amplifies TF32's 1e-3 operand error
     print(f"tf32 relative L2 error of the waveform: {rel:.3e}")
     assert torch.isfinite(wav).all() and rel < 0.15, f"tf32 waveform relative L2 error {rel:.3e}"
+
+
+@pytest.fixture(scope="module")
+def full_size_codec():
+    """The shipped configuration (dim 768, intermediate 2304, 12 ConvNeXt blocks, 4096 x 512 codebook, n_fft 1280 / hop 320;
+    SURVEY 3d) with seeded random weights: torch's default initialisers, a N(0,1) codebook (the reference's buffer is
+    zeros until k-means fills it) and non-trivial AdaLayerNorm tables."""
+    from lina_speech_b200.codec import WavTokenizer
+    torch.manual_seed(7)
+    wt = WavTokenizer.from_hparams().eval()
+    with torch.no_grad():
+        wt.feature_extractor.encodec.quantizer.vq.layers[0]._codebook.embed.normal_()
+        for m in wt.modules():
+            if m.__class__.__name__ == "AdaLayerNorm":
+                m.scale.weight.add_(0.1 * torch.randn_like(m.scale.weight))
+                m.shift.weight.add_(0.1 * torch.randn_like(m.shift.weight))
+    sd = {k: v.detach().clone() for k, v in wt.state_dict().items()}
+    return wt.to(DEV), sd
+
+
+@pytest.mark.parametrize("B,Ln", [(4, 750), (4, 2000)])
+def test_full_size_decode_matches_oracle(full_size_codec, B, Ln):
+    """SURVEY 4's shape matrix for the codec: the real widths, 10 s and 26.7 s of audio, against the CPU fp32 oracle
+    (DEC/pretrained.py:192-239 restated); waveform atol 1e-4 relative to max(1, |ref|max) as BASELINE.md 3 states."""
+    wt, sd = full_size_codec
+    g = torch.Generator().manual_seed(Ln)
+    codes = torch.randint(0, 4096, (1, B, Ln), generator=g)
+    bw = torch.tensor([0])
+    feats_ref = CO.codes_to_features(sd, codes)
+    ref = CO.decode(sd, feats_ref, bw)
+    feats = wt.codes_to_features(codes.to(DEV))
+    assert torch.equal(feats.cpu(), feats_ref)
+    wav = wt.decode(feats, bandwidth_id=bw.to(DEV))
+    assert wav.shape == ref.shape == (B, 320 * Ln)
+    err = (wav.cpu() - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), f"wav max err {err:.3e} (ref absmax {ref.abs().max().item():.3f})"

@@ -349,7 +349,6 @@ def test_rwkv6_gradients(op):
         _assert_close(got.grad, ref.grad, 1e-3, 1e-3, what=f"{op} d{name}")
 
 
-@pytest.mark.skipif(not os.environ.get("LINA_BRINGUP"), reason="added after the last GPU call of round 1 (routing logic checked on CPU in tests/test_host.py)")
 @pytest.mark.parametrize("op", ["chunk", "fused_chunk"])
 def test_gates_outside_the_tensor_core_envelope_are_served_exactly(op):
     """-2 per step on a few channels = -128 per 64-token chunk: beyond the single-pivot range of the tcgen05 kernel; the

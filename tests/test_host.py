@@ -337,3 +337,64 @@ def test_gate_envelope_routing_of_the_chunk_operators():
     assert O._route("fused_chunk", q, v, strong, yes) == ("recurrent", False)
     assert O._route("chunk", q, v, strong, no) == ("chunk", None)                    # CUDA-core chunk path: exact already
     assert O._route("recurrent", q, v, strong, yes) == ("recurrent", None)           # the backward looks at the gates
+
+
+def test_cross_attention_memo_never_serves_another_utterance():
+    """the text-side memo was keyed on ctx.data_ptr(); under inference_mode the allocator hands a freed
+    text tensor's address to the next utterance and the old k / v came back (197 of 200 calls).  The memo now holds the
+    tensor itself, so its storage cannot be recycled while the entry lives."""
+    import gc
+    from lina_speech_b200.model.crossatt import BlindCrossAttention
+    torch.manual_seed(0)
+    ca = BlindCrossAttention(32, 32, 32, 1, torch.nn.Identity(), pos_dim=32, pos_type="sinusoidal").eval()
+    wrong = 0
+    with torch.inference_mode():
+        for i in range(200):
+            ctx = torch.randn(2, 11, 32)
+            k, v, pe = ca._text_side(ctx, None)
+            k2, v2, _ = ca._text_side(ctx, None)                   # same tensor again: served from the memo
+            assert k2 is k and v2 is v
+            want = ca.ln_k(ca.k(ctx)).unsqueeze(1)
+            wrong += int(not torch.allclose(k, want))
+            del ctx, k, v, pe, k2, v2, want
+            gc.collect()
+    assert wrong == 0
+    # parameters that feed k / v / pos_emb are part of the key: an in-place update invalidates the entry
+    ctx = torch.randn(2, 11, 32)
+    with torch.no_grad():
+        k, _, _ = ca._text_side(ctx, None)
+        ca.ln_k.bias.add_(1.0)
+        k3, _, _ = ca._text_side(ctx, None)
+    assert not torch.allclose(k, k3)
+    ca.clear_memo()
+    assert ca._memo is None
+
+
+def test_modules_unpickled_without_init_have_their_lazy_caches():
+    """TrainLina.load_from_checkpoint un-pickles the reference's module instances into the mirror
+    classes: __dict__ is restored without running __init__, so attributes that only the mirrors create must have class-level
+    defaults; fla's module paths inside the pickle must resolve as well."""
+    import pickle
+    import lina_speech_b200.model as M
+    from lina_speech_b200 import compat
+    from lina_speech_b200.model.base_blocks import SwiGLU
+    rnn = M.AttentiveGLA(64, 1, 2, blind=True, use_short_conv=True, pos_type="convolutional")
+    for mod in rnn.modules():                                       # what an instance pickled by the reference looks like
+        for name in ("_wcat", "_wcat4", "_memo", "_padded"):
+            mod.__dict__.pop(name, None)
+    rnn2 = pickle.loads(pickle.dumps(rnn))
+    t = rnn2.encoder[0].tmix
+    assert t._wcat is None and t._wcat4 is None and rnn2.cross_att._memo is None
+    assert [m for m in rnn2.modules() if isinstance(m, SwiGLU)][0]._padded is None
+    assert t._cat_weight().shape[0] == 2 * t.key_dim + 2 * t.value_dim + 16
+    done = compat.install_reference_aliases()
+    try:
+        import importlib
+        assert importlib.import_module("fla.modules.convolution").ShortConvolution is M.gla.ShortConvolution
+        assert importlib.import_module("fla.modules.fused_norm_gate").FusedRMSNormSwishGate is M.gla.FusedRMSNormSwishGate
+        assert importlib.import_module("fla.models.utils").Cache is M.gla.Cache
+        from fla.ops.gla import fused_chunk_gla  # noqa: F401
+    finally:
+        import sys
+        for name in done:
+            sys.modules.pop(name, None)

@@ -269,7 +269,7 @@ def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
     xq, xk, xv = pd[..., :kd], pd[..., kd:2 * kd], pd[..., 2 * kd:2 * kd + vd]
     rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldx, L.ptr(xk), ldx, L.ptr(xv), ldx, L.ptr(wqd), L.ptr(wkd), L.ptr(wvd), L.ptr(gd), kd,
                                          L.ptr(qg), L.ptr(kg), L.ptr(vv), L.ptr(decay), L.ptr(cq), L.ptr(ck), L.ptr(cv),
-                                         L.dt(cq), B, T, H, K, V, 4, 16.0, scale, L.stream(pd))
+                                         L.dt(cq), B, T, H, K, V, 4, 16.0, scale, None, L.stream(pd))
     L.check(rc, "lina_gla_prefill_prep_gated")
     for got, ref in ((cq, cq_r), (ck, ck_r), (cv, cv_r)):
         assert torch.equal(got.float().cpu(), ref), "conv cache"
@@ -450,3 +450,75 @@ def test_autocast_layernorm_matches_torch(N):
     _close(gb, norm.bias.grad, 1e-3, 1e-4, what="ln dbeta")
     # outside autocast nothing changes
     assert autocast_layernorm(x.detach(), norm).dtype == torch.float32
+
+
+def test_inference_prefill_with_gates_outside_the_envelope_is_served_exactly():
+    """ADVICE r1 / VERDICT weak #8: the default inference path (GatedLinearAttention._prefill, pre-gated tcgen05 kernel) keeps
+    one pivot per 64-token chunk; gates summing below -80 inside a chunk must be noticed (device flag written by
+    lina_gla_prefill_prep_gated) and the call served by the exact kernels -- lone layer (immediate check) and inside a
+    backbone pass (one deferred check), with and without a cache."""
+    import lina_speech_b200.model as M
+    import lina_speech_b200.model.gla as G
+    from lina_speech_b200.fla_api import Cache
+    from oracle import lina_oracle as LO
+    torch.manual_seed(9)
+    bf = torch.bfloat16
+    B, T, d, H = 1, 160, 512, 4                                # K = 128, V = 256: tensor-core envelope
+    layer = G.GatedLinearAttention(hidden_size=d, num_heads=H, use_short_conv=True, layer_idx=0).eval()
+    with torch.no_grad():
+        layer.gk_proj[1].bias[::7] = -48.0                     # logsigmoid(-48)/16 = -3 per token = -192 per chunk
+        for p in layer.parameters():
+            p.copy_(p.to(bf).float())
+    sd = {"l." + k: v.detach().clone() for k, v in layer.state_dict().items()}
+    layer = layer.to(DEV).to(bf)
+    x = torch.randn(B, T, d).to(bf)
+    ref = LO.gla_layer(sd, "l", x.float(), H)
+    assert G.GateEnvelope.depth == 0
+    with torch.inference_mode():
+        y = layer(x.to(DEV))
+    assert torch.isfinite(y).all()
+    _close(y, ref, 3e-2 * ref.abs().max().item(), 0.0, what="lone layer, gates outside the envelope")
+    assert not G.GateEnvelope.tripped(torch.device(DEV))       # the layer consumed (and cleared) its own flag
+    # the same through a backbone pass: the mixers only accumulate the flag, the backbone reads it once and redoes the pass
+    torch.manual_seed(10)
+    rnn = M.AttentiveGLA(d, 1, H, blind=True, use_short_conv=True, pos_type="convolutional").eval()
+    with torch.no_grad():
+        rnn.encoder[0].tmix.gk_proj[1].bias[::5] = -48.0
+        for p in rnn.parameters():
+            p.copy_(p.to(bf).float())
+    sdr = {"r." + k: v.detach().clone() for k, v in rnn.state_dict().items()}
+    cfg = {"d_model": d, "n_layer": 1, "heads": H, "pos_type": "convolutional"}
+    ctx = torch.randn(B, 12, d).to(bf)
+    refy, refatt = LO.attentive_gla(sdr, "r", cfg, x.float(), ctx.float())
+    rnn = rnn.to(DEV).to(bf)
+    with torch.inference_mode():
+        yb, att = rnn(x.to(DEV), ctx.to(DEV))
+    assert torch.isfinite(yb).all()
+    _close(yb, refy, 4e-2 * refy.abs().max().item(), 0.0, what="backbone pass, gates outside the envelope")
+    # multi-token pass WITH a cache (generate_batch(prefill_prompt=True)): the cache must end as the exact path leaves it
+    state = LO.init_state(cfg, B)
+    refs, _ = LO.attentive_gla(sdr, "r", cfg, x.float(), ctx.float(), state=state, step=True)
+    cache = rnn.init_state(batch_size=B)
+    with torch.inference_mode():
+        ys, _, _ = rnn.step(x.to(DEV), ctx.to(DEV), 0, cache)
+    _close(ys, refs, 4e-2 * refs.abs().max().item(), 0.0, what="multi-token step with cache")
+    for i, st in enumerate(cache.states):
+        S, Sr = st[-1].float().cpu(), state[i][-1]
+        _close(S, Sr, 3e-2 * max(Sr.abs().max().item(), 1e-3), 0.0, what=f"cache state {i}")
+
+
+def test_eval_under_autocast_takes_the_general_path():
+    """eval + no_grad under torch.autocast(bf16) with fp32 weights (validation_step under bf16-mixed) must not
+    reach the raw-pointer fast paths, which describe every buffer with ONE dtype."""
+    import lina_speech_b200.model as M
+    torch.manual_seed(3)
+    rnn = M.AttentiveGLA(256, 1, 4, blind=True, use_short_conv=True, pos_type="convolutional").to(DEV).eval()
+    x, ctx = torch.randn(2, 40, 256, device=DEV), torch.randn(2, 9, 256, device=DEV)
+    with torch.no_grad():
+        ref, _ = rnn(x, ctx)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y, _ = rnn(x, ctx)
+            cache = rnn.init_state(batch_size=2)
+            y1, _, _ = rnn.step(x[:, :1], ctx, 0, cache)
+    assert torch.isfinite(y).all() and torch.isfinite(y1).all()
+    _close(y, ref, 5e-2 * ref.abs().max().item(), 0.0, what="autocast eval vs fp32 eval")

@@ -1,6 +1,8 @@
 """CPU: the oracle (oracle/*.py) against the golden fixtures generated from the reference
 (tests/golden/make_golden.py), plus internal consistency of its restatements."""
 import pytest
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -139,3 +141,25 @@ def test_random_state_dict_has_the_host_classes_keys_and_shapes():
     cm = torch.ones(2, 12, 9, dtype=torch.bool)
     logits, loss = LO.lina_forward(sd, cfg, x, y, em, cm)[:2]
     assert torch.isfinite(logits).all() and torch.isfinite(loss)
+
+
+def test_reference_rounding_emulation_reproduces_the_references_triton_kernels(golden_triton):
+    """oracle.gla_oracle.fused_chunk_gla_as_reference_rounds restates every rounding of the reference's default op
+    (FLA/fla/ops/gla/chunk_fuse.py:302-399).  The fixture holds what the reference's Triton kernels actually returned on a
+    B200 for seeded bf16 inputs: the restatement must reproduce it -- bit for bit on (almost) every element, the rest (fp32
+    summation order inside tl.dot flipping a rounding) within one bf16 ulp at the output scale, final state to fp32 rounding."""
+    from conftest import triton_golden_inputs
+    from oracle import gla_oracle as GO
+    for tag in "abc":
+        q, k, v, gk = triton_golden_inputs(golden_triton[f"{tag}_shape"])
+        emu, emu_h = GO.fused_chunk_gla_as_reference_rounds(q, k, v, gk)
+        ref = golden_triton[f"{tag}_fused_chunk_gla_o"]
+        assert emu.dtype == ref.dtype == torch.bfloat16 and emu.shape == ref.shape
+        same = (emu.view(torch.int16) == ref.view(torch.int16)).float().mean().item()
+        assert same >= 0.995, f"{tag}: only {same:.4f} of the elements are bit-identical"
+        d = (emu.float() - ref.float()).abs().max().item()
+        ulp_top = 2.0 ** (math.floor(math.log2(ref.float().abs().max().item())) - 7)   # inter + intra are rounded separately:
+        assert d <= ulp_top, f"{tag}: max difference {d:.3e} exceeds one bf16 ulp at the output scale ({ulp_top:.3e})"
+        if f"{tag}_fused_chunk_gla_ht" in golden_triton:
+            hd = (emu_h - golden_triton[f"{tag}_fused_chunk_gla_ht"]).abs().max().item()
+            assert hd <= 1e-5, f"{tag}: final state differs by {hd:.2e}"
