@@ -288,6 +288,72 @@ int lina_codec_layernorm_t(const float *x, const float *gamma, const float *beta
 size_t lina_codec_istft_workspace_bytes(int B, int L, int n_fft);
 int lina_codec_istft_head(const float *h, const float *window, float *wav, void *ws,
                           int B, int L, int n_fft, int hop, void *stream);
+/* Same with a row stride (elements) for h: the head GEMM writes rows padded to a multiple of 4 floats. */
+int lina_codec_istft_head_ld(const float *h, long long ldh, const float *window, float *wav, void *ws,
+                             int B, int L, int n_fft, int hop, void *stream);
+
+/* Channels-last stages between the tensor-core contractions (csrc/codec_cl.cu); activations [B, L, C] fp32, outputs fp32
+ * and / or `n_parts` bf16 parts (hi [, mid], lo) of the fp32 result -- the A operand of the next lina_gemm_bf16_terms.
+ * codes -> sum over quantizers of codebook rows (DEC/pretrained.py:231-237), without the [B,C,L] feature tensor: */
+int lina_codec_cl_gather(const int64_t *codes, const float *codebooks, float *out_f32, void *const *out_parts, int n_parts,
+                         int Kq, int B, int L, int bins, int C, void *stream);
+/* GroupNorm(G, C) statistics of [B, L, C] (DEC/models.py:15-16): Welford partials per (batch, 64-row tile, group),
+ * merged by the consumer (lina_codec_cl_rows). */
+size_t lina_codec_cl_gn_partials_bytes(int B, int L, int G);
+int lina_codec_cl_gn_partials(const float *x, float *partials, int B, int L, int C, int G, void *stream);
+/* One pass per row: [depthwise Conv1d k=7, padding 3 (dw_w [C,7], dw_b [C]; DEC/modules.py:28,48)] ->
+ * [GroupNorm apply from the partials, affine gn_w / gn_b] -> [swish (DEC/models.py:10-12)] ->
+ * [LayerNorm over C without affine, * ln_scale + ln_shift (AdaLayerNorm DEC/modules.py:81-86; nn.LayerNorm with its
+ * weight / bias)].  Stages with a NULL first pointer are skipped. */
+int lina_codec_cl_rows(const float *x, const float *dw_w, const float *dw_b, const float *gn_partials, const float *gn_w,
+                       const float *gn_b, int G, float gn_eps, int swish, const float *ln_scale, const float *ln_shift,
+                       float ln_eps, float *out_f32, void *const *out_parts, int n_parts, int B, int L, int C, void *stream);
+/* softmax over the key axis of the attention scores S [rows, ldS] (row length n) -> bf16 parts [rows, ldP], columns
+ * n..ldP-1 zero (DEC/models.py:119-120). */
+int lina_codec_cl_softmax(const float *S, void *const *out_parts, int n_parts, long long rows, int n, long long ldS,
+                          long long ldP, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core contractions of the WavTokenizer decoder at fp32 fidelity (csrc/gemm_sm100.cu): replaces the cuDNN / cuBLAS
+ * fp32 calls behind nn.Conv1d k = 7 / k = 3 / 1x1 (DEC/models.py:177,203-216 -> 40-51,97-105), nn.Linear of ConvNeXtBlock
+ * (DEC/modules.py:33-37,52-56) and ISTFTHead.out (DEC/heads.py:39,53), and the two torch.bmm of AttnBlock
+ * (DEC/models.py:116-124).
+ *
+ *   D[b,l,n] = alpha * sum_tap sum_(pa,pb) sum_k A_pa[b, l + tap - pad, k] * B_pb[(b,) n, tap*K + k]
+ *   out      = act(D + bias[n]) * gamma[n] + residual[b,l,n]
+ *
+ * Operands are bf16 "parts" of fp32 tensors (x = part0 + part1 [+ part2], part0 = bf16(x), part i = bf16 of the remainder);
+ * `terms` lists the part products to accumulate (all in one fp32 accumulator): {(0,0)} is a plain bf16 GEMM,
+ * {(0,0),(0,1),(1,0)} carries 16 significand bits per operand, the six-term list over three parts 24 (fp32).
+ * A parts: [NB, L, lda] row-major (rows outside [0, L) of a batch read as zero: the convolution's zero padding);
+ * B parts: [N, ldb] (weights, [N][tap][K]) or, with b_batched, [NB, N, ldb]; with b_mn the transposed storage [K, ldb]
+ * (how the attention block's V sits in memory).  Strides in elements, multiples of 8.
+ * Outputs: out_f32 [NB*L, ld_out] and / or out_parts bf16 parts [NB*L, ld_split] of the result (the next GEMM's A).
+ * act: 0 none, 1 GELU (erf), 2 swish.  bias / gamma / residual may be NULL. */
+typedef struct {
+    const void *a[3];
+    long long lda, a_batch_stride;      /* a_batch_stride 0 = L * lda */
+    int a_parts;
+    const void *b[3];
+    long long ldb, b_batch_stride;      /* b_batch_stride 0 = N * ldb */
+    int b_parts, b_batched;
+    int n_terms, term_a[6], term_b[6];
+    int NB, L, N, K, taps, pad;
+    float alpha;
+    const float *bias, *gamma, *residual;
+    long long ld_res;
+    int act;
+    float *out_f32;
+    long long ld_out;
+    void *out_split[3];
+    long long ld_split;
+    int out_parts;
+    int b_mn;                           /* 1: B parts stored [K, ldb] (N contiguous) / [NB, K, ldb]; taps must be 1 */
+    int span;                           /* 64-wide K blocks accumulated on the tensor core between two promotions of the partial
+                                           sums to fp32 registers (0 = default 2: the tensor core's accumulator truncates after
+                                           every K = 16 step; a large span trades that error for fewer TMEM reads) */
+} lina_gemm_args;
+int lina_gemm_bf16_terms(const lina_gemm_args *args, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Debug / bring-up: one-CTA tcgen05 GEMM D[128,N] = A[128,KD] * B[N,KD]^T (fp32 in, bf16 math) with the
@@ -299,8 +365,8 @@ int lina_codec_istft_head(const float *h, const float *window, float *wav, void 
  * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16,
  * key 4 = 1 runs the pre-gated GLA kernel's state pass on one warpgroup, key 5 = 1 selects the round-1 short-conv backward,
  * key 6 = 1 gives the pre-gated GLA kernel three operand stages + one v stage (default 2 + 2), key 7 = 1 turns on its
- * cluster-multicast operand loads, key 8 = 1 routes lina_codec_istft_head (n_fft = 1280) to the warp-per-frame fixed-radix
- * FFT kernel (csrc/fft640.cuh; index arithmetic checked on the host, kernel not yet run on hardware). */
+ * cluster-multicast operand loads, key 8 = 2 routes lina_codec_istft_head (n_fft = 1280) back to the generic shared-memory
+ * FFT (default: the warp-per-frame fixed-radix kernel, csrc/fft640.cuh: 0.25 vs 0.69 ms at 32 x 750 frames). */
 int lina_debug_set_variant(int key, int value);
 int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
                           int swap, void *stream);

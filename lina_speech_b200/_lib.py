@@ -66,6 +66,12 @@ PROTOTYPES = {
     "lina_codec_layernorm_t_ws": (_i, [_p] * 5 + [_i] * 3 + [_f, _p]),
     "lina_codec_istft_workspace_bytes": (_sz, [_i] * 3),
     "lina_codec_istft_head": (_i, [_p] * 4 + [_i] * 4 + [_p]),
+    "lina_codec_istft_head_ld": (_i, [_p, C.c_longlong] + [_p] * 3 + [_i] * 4 + [_p]),
+    "lina_codec_cl_gather": (_i, [_p] * 4 + [_i] * 6 + [_p]),
+    "lina_codec_cl_gn_partials_bytes": (_sz, [_i] * 3),
+    "lina_codec_cl_gn_partials": (_i, [_p, _p] + [_i] * 4 + [_p]),
+    "lina_codec_cl_rows": (_i, [_p] * 6 + [_i, _f, _i, _p, _p, _f, _p, _p] + [_i] * 4 + [_p]),
+    "lina_codec_cl_softmax": (_i, [_p, _p, _i, C.c_longlong, _i, C.c_longlong, C.c_longlong, _p]),
     "lina_debug_set_variant": (_i, [_i, _i]),
     "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_debug_umma_probe_m": (_i, [_p] * 3 + [_i] * 3 + [_p]),
@@ -74,6 +80,19 @@ PROTOTYPES = {
     "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
     "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
 }
+
+class GemmArgs(C.Structure):
+    """``lina_gemm_args`` of include/lina_b200.h (field order and types are the header's)."""
+    _fields_ = [("a", _p * 3), ("lda", C.c_longlong), ("a_batch_stride", C.c_longlong), ("a_parts", _i),
+                ("b", _p * 3), ("ldb", C.c_longlong), ("b_batch_stride", C.c_longlong), ("b_parts", _i), ("b_batched", _i),
+                ("n_terms", _i), ("term_a", _i * 6), ("term_b", _i * 6),
+                ("NB", _i), ("L", _i), ("N", _i), ("K", _i), ("taps", _i), ("pad", _i),
+                ("alpha", _f), ("bias", _p), ("gamma", _p), ("residual", _p), ("ld_res", C.c_longlong), ("act", _i),
+                ("out_f32", _p), ("ld_out", C.c_longlong), ("out_split", _p * 3), ("ld_split", C.c_longlong),
+                ("out_parts", _i), ("b_mn", _i), ("span", _i)]
+
+
+PROTOTYPES["lina_gemm_bf16_terms"] = (_i, [C.POINTER(GemmArgs), _p])
 
 _lib: Optional[C.CDLL] = None
 

@@ -6,29 +6,39 @@ Mirrors ``3rdparty/decoder`` of the reference: WavTokenizer (pretrained.py:32-23
 names are the reference's, so its checkpoints load with ``load_state_dict`` (encoder-side keys, which
 decode never touches, are dropped by :func:`WavTokenizer.load_reference_state_dict`).
 
-Dense convolutions and linears are library GEMMs (cuDNN / cuBLAS through torch); every stage between
-them -- codebook gather+transpose, GroupNorm+swish, depthwise conv + transpose + AdaLayerNorm,
-layer-scale + transpose + residual, final LayerNorm, and the whole ISTFT head tail (polar, inverse real
-FFT, window, overlap-add, envelope normalisation) -- runs in liblina_b200.so.  fp32 like the reference.
+Every arithmetic stage runs in liblina_b200.so -- no cuDNN / cuBLAS call on this path:
+
+  * activations are channels-last ``[B, L, C]`` fp32 from end to end (the reference's [B, C, L] <-> [B, L, C] transposes
+    around every ConvNeXt block and norm disappear);
+  * every contraction -- the k = 7 embed conv, the eight k = 3 ResnetBlock convs, the attention block's 1x1 convs and its two
+    batched products, the 24 point-wise linears, the head's linear -- is ``lina_gemm_bf16_terms`` (tcgen05 / TMEM / TMA,
+    csrc/gemm_sm100.cu) on bf16 SPLITS of the fp32 tensors: with three parts and six part products per contraction
+    (``gemm_precision = "bf16x3"``, the default) all 24 significand bits of both operands take part, i.e. the reference's
+    fp32 arithmetic; ``"bf16x2"`` (two parts, three products) keeps 16 bits at half the tensor-core time;
+  * bias, GELU, layer scale gamma and the residual add are GEMM epilogues; conv taps are stretches of the GEMM's K loop whose
+    A tile is shifted by the tap (TMA zero fill = the conv's padding); the stages in between (GroupNorm, swish, depthwise conv,
+    AdaLayerNorm, softmax, codebook gather) are one-pass row kernels (csrc/codec_cl.cu) that write the next GEMM's operand
+    parts directly; the ISTFT head's tail is the warp-per-frame FFT + overlap-add of csrc/codec.cu.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Any, Optional
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from .. import _lib as L
+from . import gemm as G
 
-
-# bench hook: a list collects (stage, algorithmic bytes, start event, end event) around every kernel of ours
+# bench hook: a list collects (stage, algorithmic bytes, flops, start event, end event) around every launch group
 PROFILE = None
+PRECISIONS = {"bf16x3": 3, "bf16x2": 2}
 
 
 class _timed:
-    def __init__(self, name: str, nbytes: int, ref: torch.Tensor):
-        self.name, self.nbytes, self.ref = name, nbytes, ref
+    def __init__(self, name: str, nbytes: int, flops: int, ref: torch.Tensor):
+        self.name, self.nbytes, self.flops, self.ref = name, nbytes, flops, ref
 
     def __enter__(self):
         if PROFILE is not None:
@@ -39,70 +49,62 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record(torch.cuda.current_stream(self.ref.device))
-            PROFILE.append((self.name, self.nbytes, self.e0, self.e1))
+            PROFILE.append((self.name, self.nbytes, self.flops, self.e0, self.e1))
         return False
+
+
+def _ptr_array(ts):
+    arr = (C.c_void_p * 3)()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     L.require_cuda(t)
-    return t.float().contiguous()
+    return t.detach().float().contiguous()
 
 
-def groupnorm_swish(x, weight, bias, groups: int, eps: float, swish: bool):
-    x = _f32c(x)
-    B, C, Ln = x.shape
-    y = torch.empty_like(x)
-    with _timed("groupnorm_swish", 8 * x.numel(), x):
-        rc = L.lib().lina_codec_groupnorm_swish(L.ptr(x), L.ptr(_f32c(weight)), L.ptr(_f32c(bias)), L.ptr(y), None,
-                                                B, C, Ln, groups, eps, int(swish), L.stream(x))
+def rows(x, *, dw=None, gn=None, swish=False, ln=None, ln_eps=1e-6, out_f32=False, parts=0, name="rows"):
+    """One pass per row of x [B, L, C] (lina_codec_cl_rows): dw = (weight [C,7], bias [C]); gn = (partials, weight, bias,
+    groups, eps); ln = (scale [C], shift [C]).  Returns (fp32 [B,L,C] or None, tuple of bf16 parts)."""
+    B, Ln, Cc = x.shape
+    o32 = torch.empty_like(x) if out_f32 else None
+    ps = tuple(torch.empty(B, Ln, Cc, dtype=torch.bfloat16, device=x.device) for _ in range(parts))
+    dw_w, dw_b = dw if dw is not None else (None, None)
+    gp, gw, gb, groups, geps = gn if gn is not None else (None, None, None, 0, 0.0)
+    sc, sh = ln if ln is not None else (None, None)
+    nbytes = x.numel() * 4 + (x.numel() * 4 if out_f32 else 0) + x.numel() * 2 * parts
+    with _timed(name, nbytes, 0, x):
+        rc = L.lib().lina_codec_cl_rows(L.ptr(x), L.ptr(dw_w), L.ptr(dw_b), L.ptr(gp), L.ptr(gw), L.ptr(gb), groups, geps,
+                                        int(swish), L.ptr(sc), L.ptr(sh), ln_eps, L.ptr(o32), _ptr_array(ps), parts, B, Ln, Cc,
+                                        L.stream(x))
     L.count_launches(1)
-    L.check(rc, "lina_codec_groupnorm_swish")
-    return y
+    L.check(rc, "lina_codec_cl_rows")
+    return o32, ps
 
 
-def dwconv_adaln(x, dw_w, dw_b, scale, shift, eps: float):
-    """x [B,C,L] -> [B,L,C]; dw_w None = no conv (plain transposing AdaLN / LayerNorm)."""
-    x = _f32c(x)
-    B, C, Ln = x.shape
-    y = torch.empty(B, Ln, C, dtype=torch.float32, device=x.device)
-    w = _f32c(dw_w).view(C, -1) if dw_w is not None else None
-    if w is not None and w.shape[1] != 7:
-        raise NotImplementedError("depthwise kernel size must be 7 (ConvNeXtBlock, modules.py:28)")
-    lib = L.lib()
-    if w is None:       # no conv: the single kernel (all channels of a 32-step tile per CTA) measures faster (0.052 vs 0.084 ms)
-        with _timed("layernorm_t", 8 * x.numel(), x):
-            rc = lib.lina_codec_dwconv_adaln(L.ptr(x), None, None, L.ptr(_f32c(scale)), L.ptr(_f32c(shift)), L.ptr(y), B, C, Ln,
-                                             eps, L.stream(x))
-        L.count_launches(1)
-        L.check(rc, "lina_codec_dwconv_adaln")
-        return y
-    sc, sh = _f32c(scale), _f32c(shift)
-    if sc.data_ptr() % 16 or sh.data_ptr() % 16:          # rows of an embedding table: the apply kernel reads them as float4
-        sc, sh = sc.clone(), sh.clone()
-    ws = torch.empty(int(lib.lina_codec_dwconv_adaln_workspace_bytes(B, C, Ln)), dtype=torch.uint8, device=x.device)
-    with _timed("dwconv_adaln", 8 * x.numel(), x):
-        rc = lib.lina_codec_dwconv_adaln_ws(L.ptr(x), L.ptr(w), L.ptr(_f32c(dw_b)) if dw_b is not None else None,
-                                            L.ptr(sc), L.ptr(sh), L.ptr(y), L.ptr(ws), B, C, Ln, eps, L.stream(x))
-    L.count_launches(2)
-    L.check(rc, "lina_codec_dwconv_adaln_ws")
-    return y
-
-
-def scale_residual_t(h, gamma, res):
-    """h [B,L,C], res [B,C,L] -> res + gamma * h^T."""
-    h, res = _f32c(h), _f32c(res)
-    B, Ln, C = h.shape
-    out = torch.empty_like(res)
-    with _timed("scale_residual_t", 12 * h.numel(), h):
-        rc = L.lib().lina_codec_scale_residual_t(L.ptr(h), L.ptr(_f32c(gamma)) if gamma is not None else None,
-                                                 L.ptr(res), L.ptr(out), B, C, Ln, L.stream(h))
+def gn_partials(x, groups: int):
+    B, Ln, Cc = x.shape
+    ws = torch.empty(int(L.lib().lina_codec_cl_gn_partials_bytes(B, Ln, groups)) // 4, dtype=torch.float32, device=x.device)
+    with _timed("gn_stats", x.numel() * 4, 0, x):
+        rc = L.lib().lina_codec_cl_gn_partials(L.ptr(x), L.ptr(ws), B, Ln, Cc, groups, L.stream(x))
     L.count_launches(1)
-    L.check(rc, "lina_codec_scale_residual_t")
-    return out
+    L.check(rc, "lina_codec_cl_gn_partials")
+    return ws
+
+
+def gemm(a, w, *, name, NB, Ln, N, K, **kw):
+    """lina_gemm_bf16_terms with the bench hook: flops = 2 * rows * N * K * taps * terms (tensor-core work actually issued)."""
+    terms = kw.get("terms") or G.TERMS[min(len(a), len(w))]
+    flops = 2 * NB * Ln * N * K * kw.get("taps", 1) * len(terms)
+    with _timed(name, 0, flops, a[0]):
+        return G.gemm_terms(a, w, NB=NB, Ln=Ln, N=N, K=K, **kw)
 
 
 class ResnetBlock(nn.Module):
-    """models.py:19-78 with in == out channels, temb unused, dropout in eval."""
+    """models.py:19-78 with in == out channels, temb unused, dropout in eval (parameters; the arithmetic is in
+    VocosBackbone.forward)."""
 
     def __init__(self, *, in_channels, out_channels=None, conv_shortcut=False, dropout=0.1, temb_channels=0):
         super().__init__()
@@ -115,14 +117,9 @@ class ResnetBlock(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.conv2 = nn.Conv1d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
 
-    def forward(self, x, temb=None):
-        h = self.conv1(groupnorm_swish(x, self.norm1.weight, self.norm1.bias, 32, 1e-6, True))
-        h = self.conv2(groupnorm_swish(h, self.norm2.weight, self.norm2.bias, 32, 1e-6, True))
-        return x + h
-
 
 class AttnBlock(nn.Module):
-    """models.py:80-127: single-head full softmax attention over the sequence."""
+    """models.py:80-127: single-head full softmax attention over the sequence (parameters)."""
 
     def __init__(self, in_channels):
         super().__init__()
@@ -133,16 +130,9 @@ class AttnBlock(nn.Module):
         self.v = nn.Conv1d(in_channels, in_channels, 1)
         self.proj_out = nn.Conv1d(in_channels, in_channels, 1)
 
-    def forward(self, x):
-        h = groupnorm_swish(x, self.norm.weight, self.norm.bias, 32, 1e-6, False)
-        q, k, v = self.q(h), self.k(h), self.v(h)
-        c = q.shape[1]
-        w = torch.softmax(torch.bmm(q.permute(0, 2, 1), k) * (int(c) ** -0.5), dim=2)
-        return x + self.proj_out(torch.bmm(v, w.permute(0, 2, 1)))
-
 
 class AdaLayerNorm(nn.Module):
-    """modules.py:63-86 (parameters only; the arithmetic is fused into dwconv_adaln)."""
+    """modules.py:63-86 (parameters only; the arithmetic is the LayerNorm stage of lina_codec_cl_rows)."""
 
     def __init__(self, num_embeddings: int, embedding_dim: int, eps: float = 1e-6):
         super().__init__()
@@ -156,12 +146,14 @@ class AdaLayerNorm(nn.Module):
         """(scale, shift) rows of the conditioning id: a device-side gather (no host read of the id tensor)."""
         if torch.is_tensor(cond_embedding_id):
             i = cond_embedding_id.reshape(-1)[:1].to(self.scale.weight.device)
-            return self.scale.weight.index_select(0, i)[0], self.shift.weight.index_select(0, i)[0]
-        return self.scale.weight[int(cond_embedding_id)], self.shift.weight[int(cond_embedding_id)]
+            return (self.scale.weight.index_select(0, i)[0].float().contiguous(),
+                    self.shift.weight.index_select(0, i)[0].float().contiguous())
+        return (self.scale.weight[int(cond_embedding_id)].float().contiguous(),
+                self.shift.weight[int(cond_embedding_id)].float().contiguous())
 
 
 class ConvNeXtBlock(nn.Module):
-    """modules.py:8-60."""
+    """modules.py:8-60 (parameters)."""
 
     def __init__(self, dim: int, intermediate_dim: int, layer_scale_init_value: Optional[float] = None,
                  adanorm_num_embeddings: Optional[int] = None):
@@ -175,15 +167,12 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = (nn.Parameter(layer_scale_init_value * torch.ones(dim))
                       if layer_scale_init_value is not None and layer_scale_init_value > 0 else None)
 
-    def forward(self, x, cond_embedding_id=None):
-        if self.adanorm:
-            assert cond_embedding_id is not None
-            scale, shift = self.norm.rows(cond_embedding_id)
-        else:
-            scale, shift = self.norm.weight, self.norm.bias
-        h = dwconv_adaln(x, self.dwconv.weight, self.dwconv.bias, scale, shift, 1e-6)     # [B,L,C]
-        h = self.pwconv2(self.act(self.pwconv1(h)))
-        return scale_residual_t(h, self.gamma, x)
+
+def _ver(t) -> int:
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
 
 
 class VocosBackbone(nn.Module):
@@ -204,22 +193,99 @@ class VocosBackbone(nn.Module):
                                      ResnetBlock(in_channels=dim), ResnetBlock(in_channels=dim),
                                      nn.GroupNorm(32, dim, eps=1e-6, affine=True))
 
-    def forward(self, x: torch.Tensor, bandwidth_id: Optional[torch.Tensor] = None) -> torch.Tensor:
-        x = self.embed(_f32c(x))
-        for i in range(5):
-            x = self.pos_net[i](x)
+    _prepared = None      # class-level default: (key, parts, dict of split weights)
+
+    # -- weights as GEMM operands: [N][tap][K] bf16 parts, built once per (parameters, precision) ----------------------
+    def prepared(self, parts: int):
+        ps = list(self.parameters())
+        key = (parts, tuple((p.data_ptr(), _ver(p), p.dtype, p.device) for p in ps))
+        if self._prepared is not None and self._prepared[0] == key:
+            return self._prepared[1]
+
+        def conv_w(m):          # [Co, Ci, k] -> [Co, k * Ci]: tap-major along K
+            w = m.weight.detach().float()
+            return G.split(w.permute(0, 2, 1).reshape(w.shape[0], -1), parts)
+
+        def lin_w(m):
+            return G.split(m.weight.detach().float(), parts)
+
+        W = {"embed": (conv_w(self.embed), _f32c(self.embed.bias))}
+        for i in (0, 1, 3, 4):
+            b = self.pos_net[i]
+            W[f"res{i}"] = dict(n1=(_f32c(b.norm1.weight), _f32c(b.norm1.bias)), c1=(conv_w(b.conv1), _f32c(b.conv1.bias)),
+                                n2=(_f32c(b.norm2.weight), _f32c(b.norm2.bias)), c2=(conv_w(b.conv2), _f32c(b.conv2.bias)))
+        at = self.pos_net[2]
+        wqkv = torch.cat([m.weight.detach().float()[:, :, 0] for m in (at.q, at.k, at.v)], dim=0)
+        W["attn"] = dict(n=(_f32c(at.norm.weight), _f32c(at.norm.bias)),
+                         qkv=(G.split(wqkv, parts), torch.cat([_f32c(m.bias) for m in (at.q, at.k, at.v)]).contiguous()),
+                         proj=(G.split(at.proj_out.weight.detach().float()[:, :, 0], parts), _f32c(at.proj_out.bias)))
         gn = self.pos_net[5]
-        x = groupnorm_swish(x, gn.weight, gn.bias, 32, 1e-6, False)
+        W["gn5"] = (_f32c(gn.weight), _f32c(gn.bias))
+        for i, blk in enumerate(self.convnext):
+            W[f"cnx{i}"] = dict(dw=(_f32c(blk.dwconv.weight).view(blk.dwconv.weight.shape[0], -1), _f32c(blk.dwconv.bias)),
+                                p1=(lin_w(blk.pwconv1), _f32c(blk.pwconv1.bias)),
+                                p2=(lin_w(blk.pwconv2), _f32c(blk.pwconv2.bias)),
+                                gamma=_f32c(blk.gamma) if blk.gamma is not None else None)
+        W["final"] = (_f32c(self.final_layer_norm.weight), _f32c(self.final_layer_norm.bias))
+        self._prepared = (key, W)
+        return W
+
+    def forward(self, x: torch.Tensor, bandwidth_id: Optional[torch.Tensor] = None, parts: int = 3, f_parts=None):
+        """x: features, channels-last [B, L, C_in] fp32 (``f_parts``: their bf16 parts when the gather already wrote them).
+        Returns the bf16 parts of final_layer_norm(...) [B, L, dim] -- the head GEMM's operand."""
+        B, Ln, Cin = x.shape
+        D = self.embed.out_channels
+        W = self.prepared(parts)
+        if f_parts is None:
+            _, f_parts = rows(x, parts=parts, name="split_features")
+        kw = dict(NB=B, Ln=Ln)
+        # embed: Conv1d(C_in, dim, 7, padding 3)                                       models.py:224
+        w, b = W["embed"]
+        x, _ = gemm(f_parts, w, name="embed_conv7", N=D, K=Cin, taps=7, pad=3, bias=b, **kw)
+        for i in (0, 1, 2, 3, 4):
+            if i == 2:                                                                 # AttnBlock, models.py:107-127
+                A = W["attn"]
+                _, h = rows(x, gn=(gn_partials(x, 32), *A["n"], 32, 1e-6), parts=parts, name="groupnorm")
+                _, qkv = gemm(h, A["qkv"][0], name="attn_qkv", N=3 * D, K=D, bias=A["qkv"][1], out_f32=False, out_parts=parts, **kw)
+                q = tuple(t[..., :D] for t in qkv)
+                k = tuple(t[..., D:2 * D] for t in qkv)
+                v = tuple(t[..., 2 * D:] for t in qkv)
+                Lp = (Ln + 7) // 8 * 8
+                S = torch.empty(B, Ln, Lp, dtype=torch.float32, device=x.device)
+                gemm(q, k, name="attn_scores", N=Ln, K=D, b_batched=True, alpha=float(int(D) ** -0.5), lda=3 * D, ldb=3 * D,
+                     a_batch_stride=Ln * 3 * D, b_batch_stride=Ln * 3 * D, out=S, **kw)
+                P = tuple(torch.empty(B, Ln, Lp, dtype=torch.bfloat16, device=x.device) for _ in range(parts))
+                with _timed("attn_softmax", S.numel() * 4 + P[0].numel() * 2 * parts, 0, S):
+                    rc = L.lib().lina_codec_cl_softmax(L.ptr(S), _ptr_array(P), parts, B * Ln, Ln, Lp, Lp, L.stream(S))
+                L.count_launches(1)
+                L.check(rc, "lina_codec_cl_softmax")
+                _, o = gemm(P, v, name="attn_pv", N=D, K=Ln, b_batched=True, b_mn=True, ldb=3 * D, b_batch_stride=Ln * 3 * D,
+                            out_f32=False, out_parts=parts, **kw)
+                gemm(o, A["proj"][0], name="attn_proj", N=D, K=D, bias=A["proj"][1], residual=x, out=x, **kw)
+                continue
+            R = W[f"res{i}"]                                                           # ResnetBlock, models.py:58-78
+            _, h = rows(x, gn=(gn_partials(x, 32), *R["n1"], 32, 1e-6), swish=True, parts=parts, name="groupnorm_swish")
+            t, _ = gemm(h, R["c1"][0], name="res_conv3", N=D, K=D, taps=3, pad=1, bias=R["c1"][1], **kw)
+            _, h = rows(t, gn=(gn_partials(t, 32), *R["n2"], 32, 1e-6), swish=True, parts=parts, name="groupnorm_swish")
+            gemm(h, R["c2"][0], name="res_conv3", N=D, K=D, taps=3, pad=1, bias=R["c2"][1], residual=x, out=x, **kw)
+        # pos_net[5] GroupNorm, then backbone.norm (AdaLayerNorm / LayerNorm) in the same pass      models.py:226-230
         if self.adanorm:
             assert bandwidth_id is not None
-            scale, shift = self.norm.rows(bandwidth_id)
+            ln = self.norm.rows(bandwidth_id)
         else:
-            scale, shift = self.norm.weight, self.norm.bias
-        x = dwconv_adaln(x, None, None, scale, shift, 1e-6).transpose(1, 2).contiguous()       # [B,C,L]
-        for blk in self.convnext:
-            x = blk(x, cond_embedding_id=bandwidth_id)
-        fl = self.final_layer_norm
-        return dwconv_adaln(x, None, None, fl.weight, fl.bias, 1e-6)                           # [B,L,C]
+            ln = (_f32c(self.norm.weight), _f32c(self.norm.bias))
+        x, _ = rows(x, gn=(gn_partials(x, 32), *W["gn5"], 32, 1e-6), ln=ln, out_f32=True, name="groupnorm_adaln")
+        for i, blk in enumerate(self.convnext):                                        # ConvNeXtBlock, modules.py:43-60
+            Cx = W[f"cnx{i}"]
+            ln = blk.norm.rows(bandwidth_id) if blk.adanorm else (_f32c(blk.norm.weight), _f32c(blk.norm.bias))
+            _, h = rows(x, dw=Cx["dw"], ln=ln, parts=parts, name="dwconv_adaln")
+            I = blk.pwconv1.out_features
+            _, g = gemm(h, Cx["p1"][0], name="pwconv1_gelu", N=I, K=D, bias=Cx["p1"][1], act="gelu", out_f32=False,
+                        out_parts=parts, **kw)
+            gemm(g, Cx["p2"][0], name="pwconv2_scale_residual", N=D, K=I, bias=Cx["p2"][1], gamma=Cx["gamma"], residual=x,
+                 out=x, lda=g[0].stride(-2), **kw)
+        _, y = rows(x, ln=W["final"], parts=parts, name="final_layernorm")
+        return y
 
 
 class ISTFT(nn.Module):
@@ -241,18 +307,34 @@ class ISTFTHead(nn.Module):
         self.out = nn.Linear(dim, n_fft + 2)
         self.istft = ISTFT(n_fft=n_fft, hop_length=hop_length, win_length=n_fft, padding=padding)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = _f32c(self.out(x))                                   # [B,L,n_fft+2]
-        B, Ln, _ = h.shape
+    _prepared = None
+
+    def _weights(self, parts: int):
+        w, b = self.out.weight, self.out.bias
+        key = (parts, w.data_ptr(), _ver(w), b.data_ptr(), _ver(b), w.device)
+        if self._prepared is None or self._prepared[0] != key:
+            self._prepared = (key, G.split(w.detach().float(), parts), _f32c(b))
+        return self._prepared[1], self._prepared[2]
+
+    def forward(self, x, parts: int = 3) -> torch.Tensor:
+        """x: [B, L, dim] fp32, or the tuple of its bf16 parts (what the backbone hands over)."""
+        if torch.is_tensor(x):
+            L.require_cuda(x)
+            _, x = rows(x.float().contiguous(), parts=parts, name="split_head_input")
+        B, Ln, D = x[0].shape
         n_fft, hop = self.istft.n_fft, self.istft.hop_length
+        w, b = self._weights(len(x))
+        ldh = (n_fft + 2 + 3) // 4 * 4
+        h = torch.empty(B, Ln, ldh, dtype=torch.float32, device=x[0].device)
+        gemm(x, w, name="head_linear", NB=B, Ln=Ln, N=n_fft + 2, K=D, bias=b, out=h)
         lib = L.lib()
         wav = torch.empty(B, Ln * hop, dtype=torch.float32, device=h.device)
         ws = torch.empty(int(lib.lina_codec_istft_workspace_bytes(B, Ln, n_fft)), dtype=torch.uint8, device=h.device)
-        with _timed("istft_head", 4 * (h.numel() + wav.numel()), h):
-            rc = lib.lina_codec_istft_head(L.ptr(h), L.ptr(_f32c(self.istft.window)), L.ptr(wav), L.ptr(ws), B, Ln,
-                                           n_fft, hop, L.stream(h))
+        with _timed("istft_head", 4 * (B * Ln * (n_fft + 2) + wav.numel()), 0, h):
+            rc = lib.lina_codec_istft_head_ld(L.ptr(h), ldh, L.ptr(_f32c(self.istft.window)), L.ptr(wav), L.ptr(ws), B, Ln,
+                                              n_fft, hop, L.stream(h))
         L.count_launches(2)
-        L.check(rc, "lina_codec_istft_head")
+        L.check(rc, "lina_codec_istft_head_ld")
         return wav
 
 
@@ -292,10 +374,9 @@ class WavTokenizer(nn.Module):
     def __init__(self, feature_extractor: CodebookFeatures, backbone: VocosBackbone, head: ISTFTHead):
         super().__init__()
         self.feature_extractor, self.backbone, self.head = feature_extractor, backbone, head
-        # "fp32": library GEMMs / convolutions in full fp32 (bit-for-bit the reference's default math);
-        # "tf32": let cuBLAS / cuDNN use TF32 tensor cores for them (10-bit mantissa operands, fp32 accumulate) --
-        #         ~10x faster GEMMs, waveform error ~1e-3 relative.  The kernels of liblina_b200 are fp32 either way.
-        self.gemm_precision = "fp32"
+        # "bf16x3": every contraction as six bf16 part products (24 significand bits per operand = the reference's fp32);
+        # "bf16x2": three part products (16 bits per operand), half the tensor-core time.
+        self.gemm_precision = "bf16x3"
 
     @classmethod
     def from_hparams(cls, *, num_quantizers=1, vq_bins=4096, input_channels=512, dim=768, intermediate_dim=2304,
@@ -335,31 +416,49 @@ class WavTokenizer(nn.Module):
                 if k.startswith(("backbone.", "head.")) or (k.startswith("feature_extractor.") and k.endswith("_codebook.embed"))}
         return self.load_state_dict(keep, strict=True)
 
+    def _parts(self) -> int:
+        try:
+            return PRECISIONS[self.gemm_precision]
+        except KeyError:
+            raise ValueError(f"gemm_precision must be one of {sorted(PRECISIONS)}") from None
+
     @torch.inference_mode()
     def decode(self, features_input: torch.Tensor, **kwargs: Any) -> torch.Tensor:
-        if self.gemm_precision not in ("fp32", "tf32"):
-            raise ValueError("gemm_precision must be 'fp32' or 'tf32'")
-        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-        tf32 = self.gemm_precision == "tf32"
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32, tf32
-        try:
-            return self.head(self.backbone(features_input, **kwargs))
-        finally:
-            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        """features [B, C, L] (what ``codes_to_features`` returns) -> waveform [B, L * hop]."""
+        L.require_cuda(features_input)
+        parts = self._parts()
+        x = features_input
+        if x.dim() != 3:
+            raise ValueError("decode expects features [B, C, L]")
+        xt = x.transpose(1, 2)                                  # channels-last view
+        f_parts = getattr(features_input, "_lina_parts", None)
+        if xt.dtype != torch.float32 or not xt.is_contiguous():
+            xt, f_parts = xt.float().contiguous(), None
+        if f_parts is not None and (len(f_parts) != parts or f_parts[0].shape != xt.shape):
+            f_parts = None
+        y = self.backbone(xt, parts=parts, f_parts=f_parts, **kwargs)
+        return self.head(y, parts=parts)
 
     @torch.inference_mode()
     def codes_to_features(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [K, L] or [K, B, L] -> features [B, C, L] (pretrained.py:209-239).  The memory behind the returned tensor
+        is channels-last ([B, L, C], what the decoder's first contraction reads); the bf16 parts of the same values ride
+        along on the tensor object, so ``decode(codes_to_features(c))`` never re-reads the features to split them."""
         L.require_cuda(codes)
         if codes.dim() == 2:
             codes = codes.unsqueeze(1)
         codes = codes.long().contiguous()
         Kq, B, Ln = codes.shape
         books = _f32c(self.feature_extractor.codebooks())
-        bins, C = self.feature_extractor.encodec.quantizer.bins, books.shape[1]
-        out = torch.empty(B, C, Ln, dtype=torch.float32, device=codes.device)
-        with _timed("codes_to_features", 8 * codes.numel() + 4 * Kq * out.numel() + 4 * out.numel(), out):
-            rc = L.lib().lina_codec_codes_to_features(L.ptr(codes), L.ptr(books), L.ptr(out), Kq, B, Ln, bins, C,
-                                                      L.stream(codes))
+        bins, Cc = self.feature_extractor.encodec.quantizer.bins, books.shape[1]
+        parts = self._parts()
+        out = torch.empty(B, Ln, Cc, dtype=torch.float32, device=codes.device)
+        ps = tuple(torch.empty(B, Ln, Cc, dtype=torch.bfloat16, device=codes.device) for _ in range(parts))
+        with _timed("codes_to_features", 8 * codes.numel() + 4 * Kq * out.numel() + 4 * out.numel() + 2 * parts * out.numel(), 0, out):
+            rc = L.lib().lina_codec_cl_gather(L.ptr(codes), L.ptr(books), L.ptr(out), _ptr_array(ps), parts, Kq, B, Ln, bins, Cc,
+                                              L.stream(codes))
         L.count_launches(1)
-        L.check(rc, "lina_codec_codes_to_features")
-        return out
+        L.check(rc, "lina_codec_cl_gather")
+        feats = out.transpose(1, 2)
+        feats._lina_parts = ps
+        return feats

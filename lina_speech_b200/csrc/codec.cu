@@ -428,7 +428,7 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y *
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
 
 __global__ void __launch_bounds__(128)
-istft_frames_kernel(const float *__restrict__ h, const float *__restrict__ window, float *__restrict__ frames,
+istft_frames_kernel(const float *__restrict__ h, long long ldh, const float *__restrict__ window, float *__restrict__ frames,
                     int nframes, FftPlan plan) {
     extern __shared__ float smem[];
     const int M = plan.M, N = 2 * M;
@@ -446,7 +446,7 @@ istft_frames_kernel(const float *__restrict__ h, const float *__restrict__ windo
     }
     for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
         __syncthreads();
-        const float *hf = h + (size_t)f * (N + 2);
+        const float *hf = h + (size_t)f * ldh;
         // X[k] = min(exp(m_k), 100) * (cos p_k + i sin p_k)        (DEC/heads.py:54-66)
         for (int k = tid; k <= M; k += 128) {
             const float mag = fminf(expf(hf[k]), 100.f);
@@ -506,7 +506,8 @@ constexpr int F640_WARPS = 8;
 constexpr size_t F640_SMEM = (size_t)(fft640::TABLE_FLOATS + F640_WARPS * fft640::WARP_FLOATS) * sizeof(float);
 
 __global__ void __launch_bounds__(F640_WARPS * 32)
-istft_frames_1280_kernel(const float *__restrict__ h, const float *__restrict__ window, float *__restrict__ frames, int nframes) {
+istft_frames_1280_kernel(const float *__restrict__ h, long long ldh, const float *__restrict__ window, float *__restrict__ frames,
+                         int nframes) {
     using namespace fft640;
     extern __shared__ float smem[];
     float *tab = smem;
@@ -515,7 +516,7 @@ istft_frames_1280_kernel(const float *__restrict__ h, const float *__restrict__ 
     __syncthreads();
     float *re0 = smem + TABLE_FLOATS + warp * WARP_FLOATS, *im0 = re0 + NBINS, *re1 = im0 + NBINS, *im1 = re1 + M;
     for (int f = blockIdx.x * F640_WARPS + warp; f < nframes; f += gridDim.x * F640_WARPS) {
-        phase_polar(lane, h + (size_t)f * (N + 2), re0, im0);
+        phase_polar(lane, h + (size_t)f * ldh, re0, im0);
         __syncwarp();
         phase_r10(lane, re0, im0, tab, re1, im1);
         __syncwarp();
@@ -692,7 +693,13 @@ extern "C" size_t lina_codec_istft_workspace_bytes(int B, int L, int n_fft) {
 
 extern "C" int lina_codec_istft_head(const float *h, const float *window, float *wav, void *ws, int B, int L,
                                      int n_fft, int hop, void *stream) {
+    return lina_codec_istft_head_ld(h, (long long)n_fft + 2, window, wav, ws, B, L, n_fft, hop, stream);
+}
+
+extern "C" int lina_codec_istft_head_ld(const float *h, long long ldh, const float *window, float *wav, void *ws, int B, int L,
+                                        int n_fft, int hop, void *stream) {
     LINA_REQUIRE(h && window && wav && ws, LINA_ERR_BAD_ARG, "istft_head: null pointer");
+    LINA_REQUIRE(ldh >= n_fft + 2, LINA_ERR_BAD_ARG, "istft_head: row stride %lld < n_fft + 2", ldh);
     LINA_REQUIRE(B > 0 && L > 0 && n_fft > 0 && hop > 0, LINA_ERR_BAD_ARG, "istft_head: bad size");
     LINA_REQUIRE(n_fft % 4 == 0 && hop <= n_fft && (n_fft - hop) % 2 == 0, LINA_ERR_UNSUPPORTED,
                  "istft_head: need n_fft %% 4 == 0, hop <= n_fft, (n_fft-hop) even (n_fft=%d hop=%d)", n_fft, hop);
@@ -705,12 +712,12 @@ extern "C" int lina_codec_istft_head(const float *h, const float *window, float 
     LINA_REQUIRE(B <= 65535, LINA_ERR_UNSUPPORTED, "istft_head: B > 65535");
     cudaStream_t st = (cudaStream_t)stream;
     const int nframes = B * L;
-    if (g_lina_variant[8] == 1 && n_fft == fft640::N && (uintptr_t)ws % 8 == 0) {
+    if (g_lina_variant[8] != 2 && n_fft == fft640::N && (uintptr_t)ws % 8 == 0) {     // key 8 = 2: the generic FFT (A/B)
         static thread_local uint64_t configured = 0;
         if (lina_first_use_on_device(&configured))
             LINA_CUDA_OK(cudaFuncSetAttribute(istft_frames_1280_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F640_SMEM));
         const int want = (nframes + F640_WARPS - 1) / F640_WARPS;
-        istft_frames_1280_kernel<<<want < 148 * 2 ? want : 148 * 2, F640_WARPS * 32, F640_SMEM, st>>>(h, window, (float *)ws, nframes);
+        istft_frames_1280_kernel<<<want < 148 * 2 ? want : 148 * 2, F640_WARPS * 32, F640_SMEM, st>>>(h, ldh, window, (float *)ws, nframes);
         LINA_LAUNCH_OK("istft_frames_1280_kernel");
         dim3 g2((L * hop + 255) / 256, B);
         istft_ola_kernel<<<g2, 256, 0, st>>>((const float *)ws, window, wav, L, n_fft, hop);
@@ -718,7 +725,7 @@ extern "C" int lina_codec_istft_head(const float *h, const float *window, float 
         return LINA_OK;
     }
     const int grid = nframes < 148 * 16 ? nframes : 148 * 16;
-    istft_frames_kernel<<<grid, 128, smem, st>>>(h, window, (float *)ws, nframes, plan);
+    istft_frames_kernel<<<grid, 128, smem, st>>>(h, ldh, window, (float *)ws, nframes, plan);
     LINA_LAUNCH_OK("istft_frames_kernel");
     dim3 g2((L * hop + 255) / 256, B);
     istft_ola_kernel<<<g2, 256, 0, st>>>((const float *)ws, window, wav, L, n_fft, hop);

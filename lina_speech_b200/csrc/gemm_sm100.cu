@@ -1,0 +1,368 @@
+// Persistent tcgen05 GEMM with "term lists" and fused epilogues -- the contraction kernel of the WavTokenizer decode path
+// (Conv1d k = 7 / k = 3 as implicit GEMMs, 1x1 convs, the ConvNeXt point-wise linears, the attention block's two batched
+// products, the ISTFT head's linear: DEC/models.py:177,203-216,107-127, DEC/modules.py:43-60, DEC/heads.py:53-67).
+//
+//   D[b, l, n] = alpha * sum_{tap} sum_{(pa, pb) in terms} sum_k  A_pa[b, l + tap - pad, k] * B_pb[(b,) n, tap * K + k]
+//   out        = act(D + bias[n]) * gamma[n] + residual[b, l, n]        -> fp32 and / or a bf16 split (hi [, mid], lo)
+//
+// fp32 fidelity on bf16 tensor cores: an fp32 tensor x is carried as 2 (or 3) bf16 parts, x = hi + lo (+ ...) with
+// hi = bf16(x), lo = bf16(x - hi): 16 (24) significand bits.  The product of two such tensors is the sum of the part products
+// whose combined weight matters -- (hi,hi), (hi,lo), (lo,hi) [, (hi,lo2), (lo2,hi), (lo,lo)] -- all accumulated in the SAME
+// fp32 TMEM accumulator, so "3-pass" costs three times the MMAs of a bf16 GEMM but no extra epilogue or memory traffic:
+// a term is just another stretch of the K loop with different tensor maps.  Conv taps are the same mechanism: tap t is a
+// stretch of the K loop whose A tile starts t - pad rows later (TMA zero-fills rows outside [0, L) of the batch: the conv's
+// zero padding) and whose B tile starts at column t * K of the [N, taps * K] weight.
+//
+// Structure (the canonical Blackwell shape): 128 x 256 output tile per CTA, 64-wide K blocks, 4-stage TMA ring
+// (SWIZZLE_128B K-major operands), one elected thread issues M128 N256 K16 tcgen05.mma, eight epilogue warps; persistent
+// grid with a static round-robin tile scheduler (N tiles of the same rows adjacent, so the A rows are L2 hits).
+//
+// Accumulation is PROMOTED to fp32 registers: the tensor core's own fp32 accumulator truncates after every K = 16 step
+// (measured here: relative error ~ steps * 2^-24, 2.5e-5 after 432 steps -- 30 x what an fp32 SIMT GEMM leaves, and a
+// bias, not noise: it survives averaging and the ISTFT head's exp() amplifies it).  So the two 256-column TMEM accumulators
+// are a ping-pong STAGE: the issuer accumulates `span` K blocks (default 2 = 8 MMA steps) into one of them, commits, and
+// moves to the other; the epilogue warps drain each finished span with tcgen05.ld and add it into 128 fp32 registers per
+// thread with IEEE round-to-nearest adds -- the same two-level scheme fp8 GEMMs use on Hopper.  The tile's epilogue math
+// and stores then run from those registers while the issuer is already two spans into the next tile.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "tma.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int STAGES = 4;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t OFF_BAR = STAGES * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;          // + barriers / TMEM slot, + slack for the 1024-byte round-up
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = 64 + EPI_WARPS * 32;                  // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-9: epilogue
+constexpr int MAX_PARTS = 3, MAX_TERMS = 6;
+
+struct GemmParams {
+    CUtensorMap ta[MAX_PARTS], tb[MAX_PARTS];
+    int n_terms, term_a[MAX_TERMS], term_b[MAX_TERMS];
+    int taps, pad, kblocks, K, span;
+    int L, NB, N;
+    int tiles_m_per_batch, tiles_n, total_tiles;
+    int b_batched, b_mn;
+    float alpha;
+    const float *bias, *gamma, *residual;
+    long long ld_res;
+    int act;
+    float *out_f32;
+    long long ld_out;
+    bf16 *out_split[MAX_PARTS];
+    long long ld_split;
+    int out_parts;
+    int vec_f32, vec_split, vec_res;
+};
+
+__device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("gemm_sm100: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+struct TileCoord { int batch, l0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams &p, int tile) {
+    const int n_t = tile % p.tiles_n, m_t = tile / p.tiles_n;
+    TileCoord c;
+    c.batch = m_t / p.tiles_m_per_batch;
+    c.l0 = (m_t - c.batch * p.tiles_m_per_batch) * BM;
+    c.n0 = n_t * BN;
+    return c;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tfull = empty + STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int iters = p.n_terms * p.taps * p.kblocks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one_sync()) {
+            for (int i = 0; i < MAX_PARTS; ++i) { tma_prefetch_desc(&p.ta[i]); tma_prefetch_desc(&p.tb[i]); }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord c = tile_coord(p, tile);
+                for (int tap = 0; tap < p.taps; ++tap)
+                    for (int t = 0; t < p.n_terms; ++t)
+                        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                            wait_bar(&empty[s], ph ^ 1u);
+                            mbar_expect_tx(&full[s], STAGE_BYTES);
+                            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                            tma_load_3d(sa, &p.ta[p.term_a[t]], kb * BK, c.l0 + tap - p.pad, c.batch, &full[s]);
+                            const int bb = p.b_batched ? c.batch : 0;
+                            if (!p.b_mn) {
+                                tma_load_3d(sb, &p.tb[p.term_b[t]], tap * p.K + kb * BK, c.n0, bb, &full[s]);
+                            } else {            // B stored [K][N] (N contiguous): four [64 k][64 n] swizzled blocks
+#pragma unroll
+                                for (int nb = 0; nb < BN / 64; ++nb)
+                                    tma_load_3d(sb + nb * 8192, &p.tb[p.term_b[t]], c.n0 + nb * 64, kb * BK, bb, &full[s]);
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one_sync()) {
+            const uint32_t idesc = idesc_bf16(BM, BN, 0, p.b_mn ? 1 : 0);
+            uint32_t it = 0, sp = 0;                     // global K-iteration / span counters (ring and ping-pong phases)
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                for (int i0 = 0; i0 < iters; i0 += p.span, ++sp) {
+                    const uint32_t as = sp & 1u, aph = (sp >> 1) & 1u;
+                    wait_bar(&tempty[as], aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    const int i1 = min(iters, i0 + p.span);
+                    for (int i = i0; i < i1; ++i, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                        wait_bar(&full[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            // K-major: +32 B per K = 16 step inside the 128-byte swizzle row; MN-major: 16 k rows = 2048 B,
+                            // the next 64-wide N block 8192 B further (LBO)
+                            const uint64_t bd = p.b_mn ? smem_desc_sw128(sb + k * 2048, 8192, 1024) : smem_desc_sw128(sb + k * 32, 0, 1024);
+                            mma_ss(d_tmem, smem_desc_sw128(sa + k * 32, 0, 1024), bd, idesc, (uint32_t)((i > i0) | (k != 0)));
+                        }
+                        mma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+                    }
+                    mma_commit(&tfull[as]);             // this span's partial sums are complete
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: drain spans into registers (fp32 promotion), then the fused epilogue from registers =====
+        const int quarter = warp & 3;                   // TMEM lanes this warp may read: 32 * (warp % 4) ...
+        const int half = (warp - 2) >> 2;               // columns [128 * half, 128 * half + 128) of the tile
+        const int r = quarter * 32 + lane;
+        uint32_t sp = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord c = tile_coord(p, tile);
+            float acc[128];
+#pragma unroll
+            for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+            const bool cols_live = c.n0 + half * 128 < p.N;     // warp-uniform: this half of the tile has columns inside N
+            for (int i0 = 0; i0 < iters; i0 += p.span, ++sp) {
+                const uint32_t as = sp & 1u, aph = (sp >> 1) & 1u;
+                wait_bar(&tfull[as], aph);
+                tc_fence_after();
+                if (cols_live) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * 128;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        uint32_t raw[32];
+                        tmem_ld32(taddr + cc * 32, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(raw[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+            const int l = c.l0 + r;
+            if (l >= p.L || !cols_live) continue;
+            const long long grow = (long long)c.batch * p.L + l;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int n = c.n0 + half * 128 + cc * 32;
+                if (n >= p.N) break;
+                float *v = &acc[cc * 32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                const bool full_chunk = n + 32 <= p.N;
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) v[j] += __ldg(p.bias + n + j);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+                }
+                if (p.gamma != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) v[j] *= __ldg(p.gamma + n + j);
+                }
+                if (p.residual != nullptr) {
+                    const float *rp = p.residual + grow * p.ld_res + n;
+                    if (p.vec_res && full_chunk) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(rp) + j);
+                            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rp + j);
+                    }
+                }
+                if (p.out_f32 != nullptr) {
+                    float *op = p.out_f32 + grow * p.ld_out + n;
+                    if (p.vec_f32 && full_chunk) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4 *>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n + j < p.N) op[j] = v[j];
+                    }
+                }
+                if (p.out_parts > 0) {
+                    // bf16 split of the result: part 0 = bf16(v), part i = bf16(remainder)
+#pragma unroll
+                    for (int part = 0; part < MAX_PARTS; ++part) {
+                        if (part >= p.out_parts) break;
+                        bf16 *spp = p.out_split[part] + grow * p.ld_split + n;
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const bf16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
+                            v[2 * j] -= __bfloat162float(a);
+                            v[2 * j + 1] -= __bfloat162float(b);
+                            pk[j] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+                        }
+                        if (p.vec_split && full_chunk) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<uint4 *>(spp)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n + j < p.N) spp[j] = __ushort_as_bfloat16((unsigned short)((pk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+bool aligned16(const void *ptr) { return ((uintptr_t)ptr & 15u) == 0; }
+
+}  // namespace
+
+extern "C" int lina_gemm_bf16_terms(const lina_gemm_args *g, void *stream) {
+    LINA_REQUIRE(g != nullptr, LINA_ERR_BAD_ARG, "gemm: null argument block");
+    LINA_REQUIRE(g->NB > 0 && g->L > 0 && g->N > 0 && g->K > 0 && g->taps > 0 && g->pad >= 0, LINA_ERR_BAD_ARG,
+                 "gemm: non-positive size (NB %d L %d N %d K %d taps %d)", g->NB, g->L, g->N, g->K, g->taps);
+    LINA_REQUIRE(g->a_parts >= 1 && g->a_parts <= MAX_PARTS && g->b_parts >= 1 && g->b_parts <= MAX_PARTS, LINA_ERR_BAD_ARG,
+                 "gemm: 1..3 operand parts");
+    LINA_REQUIRE(g->n_terms >= 1 && g->n_terms <= MAX_TERMS, LINA_ERR_BAD_ARG, "gemm: 1..6 terms");
+    LINA_REQUIRE(g->out_parts >= 0 && g->out_parts <= MAX_PARTS, LINA_ERR_BAD_ARG, "gemm: 0..3 output parts");
+    LINA_REQUIRE(g->out_f32 != nullptr || g->out_parts > 0, LINA_ERR_BAD_ARG, "gemm: no output requested");
+    LINA_REQUIRE(g->act >= 0 && g->act <= 2, LINA_ERR_BAD_ARG, "gemm: act must be 0 (none), 1 (gelu) or 2 (swish)");
+    LINA_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->lda >= g->K &&
+                     g->ldb >= (g->b_mn ? (long long)g->N : (long long)g->taps * g->K), LINA_ERR_UNSUPPORTED,
+                 "gemm: operand row strides must be multiples of 8 elements and cover a row (lda %lld ldb %lld K %d taps %d)",
+                 g->lda, g->ldb, g->K, g->taps);
+    LINA_REQUIRE(!g->b_mn || g->taps == 1, LINA_ERR_UNSUPPORTED, "gemm: a [K][N] B operand takes no taps");
+    for (int i = 0; i < g->n_terms; ++i)
+        LINA_REQUIRE(g->term_a[i] >= 0 && g->term_a[i] < g->a_parts && g->term_b[i] >= 0 && g->term_b[i] < g->b_parts,
+                     LINA_ERR_BAD_ARG, "gemm: term %d names a missing operand part", i);
+    GemmParams p{};
+    const long long a_batch = g->a_batch_stride ? g->a_batch_stride : (long long)g->L * g->lda;
+    const long long b_batch = g->b_batch_stride ? g->b_batch_stride : (long long)(g->b_mn ? g->K : g->N) * g->ldb;
+    LINA_REQUIRE(a_batch % 8 == 0 && b_batch % 8 == 0, LINA_ERR_UNSUPPORTED, "gemm: batch strides must be multiples of 8 elements");
+    for (int i = 0; i < g->a_parts; ++i) {
+        LINA_REQUIRE(g->a[i] != nullptr && aligned16(g->a[i]), LINA_ERR_BAD_ARG, "gemm: A part %d null or not 16-byte aligned", i);
+        const uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->L, (uint64_t)g->NB};
+        const uint64_t str[3] = {2, (uint64_t)g->lda * 2, (uint64_t)a_batch * 2};
+        const uint32_t box[3] = {BK, BM, 1};
+        int rc = lina_make_tmap_bf16(&p.ta[i], g->a[i], 3, dims, str, box);
+        if (rc) return rc;
+    }
+    for (int i = g->a_parts; i < MAX_PARTS; ++i) p.ta[i] = p.ta[0];
+    for (int i = 0; i < g->b_parts; ++i) {
+        LINA_REQUIRE(g->b[i] != nullptr && aligned16(g->b[i]), LINA_ERR_BAD_ARG, "gemm: B part %d null or not 16-byte aligned", i);
+        int rc;
+        if (!g->b_mn) {
+            const uint64_t dims[3] = {(uint64_t)g->taps * g->K, (uint64_t)g->N, (uint64_t)(g->b_batched ? g->NB : 1)};
+            const uint64_t str[3] = {2, (uint64_t)g->ldb * 2, (uint64_t)b_batch * 2};
+            const uint32_t box[3] = {BK, BN, 1};
+            rc = lina_make_tmap_bf16(&p.tb[i], g->b[i], 3, dims, str, box);
+        } else {                                   // [K][N]: N innermost
+            const uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->K, (uint64_t)(g->b_batched ? g->NB : 1)};
+            const uint64_t str[3] = {2, (uint64_t)g->ldb * 2, (uint64_t)b_batch * 2};
+            const uint32_t box[3] = {64, BK, 1};
+            rc = lina_make_tmap_bf16(&p.tb[i], g->b[i], 3, dims, str, box);
+        }
+        if (rc) return rc;
+    }
+    for (int i = g->b_parts; i < MAX_PARTS; ++i) p.tb[i] = p.tb[0];
+    p.n_terms = g->n_terms;
+    for (int i = 0; i < g->n_terms; ++i) { p.term_a[i] = g->term_a[i]; p.term_b[i] = g->term_b[i]; }
+    p.taps = g->taps; p.pad = g->pad; p.K = g->K; p.kblocks = (g->K + BK - 1) / BK;
+    p.span = g->span > 0 ? g->span : 2;
+    p.L = g->L; p.NB = g->NB; p.N = g->N;
+    p.tiles_m_per_batch = (g->L + BM - 1) / BM;
+    p.tiles_n = (g->N + BN - 1) / BN;
+    const long long total = (long long)p.tiles_m_per_batch * g->NB * p.tiles_n;
+    LINA_REQUIRE(total <= 2147483647LL, LINA_ERR_UNSUPPORTED, "gemm: too many tiles");
+    p.total_tiles = (int)total;
+    p.b_batched = g->b_batched;
+    p.b_mn = g->b_mn;
+    p.alpha = g->alpha;
+    p.bias = g->bias; p.gamma = g->gamma; p.residual = g->residual; p.ld_res = g->ld_res;
+    p.act = g->act;
+    p.out_f32 = g->out_f32; p.ld_out = g->ld_out;
+    for (int i = 0; i < MAX_PARTS; ++i) p.out_split[i] = i < g->out_parts ? (bf16 *)g->out_split[i] : nullptr;
+    for (int i = 0; i < g->out_parts; ++i)
+        LINA_REQUIRE(g->out_split[i] != nullptr, LINA_ERR_BAD_ARG, "gemm: output part %d is null", i);
+    p.ld_split = g->ld_split; p.out_parts = g->out_parts;
+    LINA_REQUIRE(g->out_f32 == nullptr || g->ld_out >= g->N, LINA_ERR_BAD_ARG, "gemm: ld_out < N");
+    LINA_REQUIRE(g->out_parts == 0 || g->ld_split >= g->N, LINA_ERR_BAD_ARG, "gemm: ld_split < N");
+    LINA_REQUIRE(g->residual == nullptr || g->ld_res >= g->N, LINA_ERR_BAD_ARG, "gemm: ld_res < N");
+    p.vec_f32 = g->out_f32 != nullptr && aligned16(g->out_f32) && g->ld_out % 4 == 0;
+    p.vec_res = g->residual != nullptr && aligned16(g->residual) && g->ld_res % 4 == 0;
+    p.vec_split = g->out_parts > 0 && g->ld_split % 8 == 0;
+    for (int i = 0; i < g->out_parts; ++i) p.vec_split = p.vec_split && aligned16(g->out_split[i]);
+
+    static thread_local uint64_t configured = 0;
+    if (lina_first_use_on_device(&configured))
+        LINA_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    static thread_local int n_sm[64] = {0};
+    int dev = 0;
+    LINA_CUDA_OK(cudaGetDevice(&dev));
+    if (n_sm[dev & 63] == 0) LINA_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    const int grid = p.total_tiles < n_sm[dev & 63] ? p.total_tiles : n_sm[dev & 63];
+    gemm_sm100_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    LINA_LAUNCH_OK("gemm_sm100_kernel");
+    return LINA_OK;
+}

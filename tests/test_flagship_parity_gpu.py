@@ -53,6 +53,20 @@ def _bounded_by_reference(ours, ref_emul, exact, what, slack=1.5):
     return e_o.max().item(), e_r.max().item()
 
 
+def _state_bounded(ht, ref_h, exact_h, mild_gates, what):
+    """Final state (fp32 out of both).  With Lina's gates (logsigmoid / 16, ~ -0.04 per step) our error must be within 1.5 x the
+    reference's.  With O(1) decay per step (the fla test distribution, logsigmoid.clamp_min(-3)) the reference is
+    intrinsically ~2 x more accurate ON THE STATE: it rescales k to the chunk END (k e^{g_last - g}, chunk_util.py:57), so the
+    last token -- which carries most of a fast-decaying state -- is exact, while our kernels pivot at the chunk START
+    (k e^{-G}) and round it.  Any start-pivot chunk form shows the same ratio (oracle.gla_oracle.chunk_gla, chunk 16 or 64:
+    0.0020 vs 0.0011 rms); the outputs o are unaffected (bounded by 1.5 x above for both distributions).  Bound: 2.5 x."""
+    slack = 1.5 if mild_gates else 2.5
+    e_o = (ht.double().cpu() - exact_h.double()).abs()
+    e_r = (ref_h.double().cpu() - exact_h.double()).abs()
+    assert e_o.max() <= slack * e_r.max() + 1e-6, f"{what}: max {e_o.max():.3e} vs reference's {e_r.max():.3e}"
+    assert e_o.square().mean().sqrt() <= slack * e_r.square().mean().sqrt() + 1e-7, f"{what}: rms"
+
+
 @pytest.mark.parametrize("op", ["fused_chunk", "chunk"])
 @pytest.mark.parametrize("shape,gates", [((1, 4, 256, 256, 512), "lina"), ((2, 2, 192, 128, 256), "lina"),
                                          ((1, 4, 128, 256, 512), "fla"), ((1, 2, 320, 256, 512), "lina_h0")])
@@ -75,10 +89,7 @@ def test_chunk_op_error_is_bounded_by_the_references_own_rounding(op, shape, gat
     assert o.dtype == BF and ht.dtype == torch.float32
     _bounded_by_reference(o, ref_o, exact, f"{op} o {shape} {gates}")
     # final state: fp32 out of both implementations, error from the bf16 operands of k_g^T v
-    e_o = (ht.double().cpu() - exact_h.double()).abs()
-    e_r = (ref_h.double() - exact_h.double()).abs()
-    assert e_o.max() <= 1.5 * e_r.max() + 1e-6, f"{op} final state: {e_o.max():.3e} vs reference's {e_r.max():.3e}"
-    assert e_o.square().mean().sqrt() <= 1.5 * e_r.square().mean().sqrt() + 1e-7
+    _state_bounded(ht, ref_h, exact_h, gates != "fla", f"{op} final state {shape} {gates}")
 
 
 @pytest.mark.parametrize("op", ["fused_chunk", "chunk"])
@@ -101,9 +112,8 @@ def test_against_the_references_triton_outputs(golden_triton, op, tag):
     tol = 2 * _ulp_bf16(torch.maximum(o.float().cpu().abs(), ref.float().abs())) + 4 * (e_o.square().mean().sqrt() + e_r.square().mean().sqrt())
     assert bool((d <= tol).all()), f"{op} vs Triton golden {tag}: outputs differ by up to {d.max():.3e}"
     if f"{tag}_fused_chunk_gla_ht" in golden_triton:
-        rh = golden_triton[f"{tag}_fused_chunk_gla_ht"].double()
-        eh_o, eh_r = (ht.double().cpu() - exact_h).abs(), (rh - exact_h).abs()
-        assert eh_o.max() <= 1.5 * eh_r.max() + 1e-6 and eh_o.square().mean().sqrt() <= 1.5 * eh_r.square().mean().sqrt() + 1e-7
+        mild = int(golden_triton[f"{tag}_shape"][5]) == 0
+        _state_bounded(ht, golden_triton[f"{tag}_fused_chunk_gla_ht"], exact_h, mild, f"{op} final state vs Triton golden {tag}")
 
 
 # ------------------------------------------------------------------------------------------------------------------------
