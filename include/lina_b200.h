@@ -350,7 +350,7 @@ typedef struct {
     int out_parts;
     int b_mn;                           /* 1: B parts stored [K, ldb] (N contiguous) / [NB, K, ldb]; taps must be 1 */
     int span;                           /* 64-wide K blocks accumulated on the tensor core between two promotions of the partial
-                                           sums to fp32 registers (0 = default 2: the tensor core's accumulator truncates after
+                                           sums to fp32 registers (0 = default 8: the tensor core's accumulator truncates after
                                            every K = 16 step; a large span trades that error for fewer TMEM reads) */
 } lina_gemm_args;
 int lina_gemm_bf16_terms(const lina_gemm_args *args, void *stream);

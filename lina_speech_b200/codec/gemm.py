@@ -6,6 +6,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -15,6 +16,8 @@ from .. import _lib as L
 # (a part, b part) products, most significant first
 TERMS = {1: ((0, 0),), 2: ((0, 0), (0, 1), (1, 0)), 3: ((0, 0), (0, 1), (1, 0), (0, 2), (2, 0), (1, 1))}
 ACT = {None: 0, "none": 0, "gelu": 1, "swish": 2}
+# K blocks (of 64) between two promotions of the tensor core's partial sums to fp32 registers; 0 = the library's default
+DEFAULT_SPAN = int(os.environ.get("LINA_GEMM_SPAN", "0"))
 
 
 def split(x: torch.Tensor, parts: int) -> Tuple[torch.Tensor, ...]:
@@ -56,7 +59,7 @@ def gemm_terms(a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], *, NB: int,
     g.a_batch_stride, g.b_batch_stride = a_batch_stride, b_batch_stride
     g.b_batched = int(b_batched)
     g.b_mn = int(b_mn)
-    g.span = int(span)
+    g.span = int(span) if span else DEFAULT_SPAN
     g.n_terms = len(terms)
     for i, (pa, pb) in enumerate(terms):
         g.term_a[i], g.term_b[i] = pa, pb

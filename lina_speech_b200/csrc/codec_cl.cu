@@ -76,13 +76,18 @@ cl_gn_partials_kernel(const float *__restrict__ x, float *__restrict__ partials,
     const int b = blockIdx.y, tile = blockIdx.x, c = threadIdx.x;
     const int l0 = tile * GN_ROWS, nrow = min(GN_ROWS, L - l0);
     const float *xp = x + ((size_t)b * L + l0) * C + c;
-    float mean = 0.f, m2 = 0.f;
+    // shifted sums (shift = the channel's first sample of the tile): sum (x - K), sum (x - K)^2 carry no cancellation
+    // problem in fp32 and need no division per element; (mean, M2) follow exactly as for Welford
+    const float K0 = xp[0];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
     for (int r = 0; r < nrow; ++r) {
-        const float v = xp[(size_t)r * C];
-        const float d = v - mean;
-        mean += d / (float)(r + 1);
-        m2 = fmaf(d, v - mean, m2);
+        const float d = xp[(size_t)r * C] - K0;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
     }
+    const float mean = K0 + s1 / (float)nrow;
+    const float m2 = fmaxf(s2 - s1 * s1 / (float)nrow, 0.f);
     sm[2 * c] = mean; sm[2 * c + 1] = m2;
     __syncthreads();
     if (c < G) {
@@ -113,19 +118,24 @@ struct RowArgs {
 };
 
 constexpr int ROW_WARPS = 8;
+constexpr int ROWS_PER_WARP = 4;                 // consecutive rows of one warp (the CTA covers 32 consecutive rows)
 
 template <int VEC>      // 4: C % 128 == 0 (float4 per lane and step); 1: any C
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 cl_rows_kernel(const RowArgs a) {
     constexpr int MAXJ = 1024 / (32 * VEC);                     // steps per lane for C <= 1024
     __shared__ float gstat[64][2];                              // GroupNorm (mean, rstd) of this CTA's batch (G <= 64)
+    extern __shared__ float dws[];                              // depthwise taps, transposed: [7][C] (+ bias [C])
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.C, L = a.L;
-    const long long row0 = (long long)blockIdx.x * ROW_WARPS;   // CTA = ROW_WARPS consecutive rows of ONE batch
-    const int tiles_per_b = (L + ROW_WARPS - 1) / ROW_WARPS;
+    constexpr int CTA_ROWS = ROW_WARPS * ROWS_PER_WARP;
+    const int tiles_per_b = (L + CTA_ROWS - 1) / CTA_ROWS;      // CTA = CTA_ROWS consecutive rows of ONE batch
     const int b = blockIdx.x / tiles_per_b;
-    const int l = (blockIdx.x - b * tiles_per_b) * ROW_WARPS + warp;
-    (void)row0;
+    const int lbase = (blockIdx.x - b * tiles_per_b) * CTA_ROWS + warp * ROWS_PER_WARP;
+    if (a.dw_w != nullptr) {
+        for (int i = threadIdx.x; i < 7 * C; i += ROW_WARPS * 32) { const int t = i / C, c = i - t * C; dws[i] = a.dw_w[c * 7 + t]; }
+        for (int i = threadIdx.x; i < C; i += ROW_WARPS * 32) dws[7 * C + i] = a.dw_b != nullptr ? a.dw_b[i] : 0.f;
+    }
     if (a.gn_partials != nullptr) {
         if (threadIdx.x < a.G) {
             float n = 0.f, mu = 0.f, M2 = 0.f;
@@ -140,10 +150,13 @@ cl_rows_kernel(const RowArgs a) {
             gstat[threadIdx.x][0] = mu;
             gstat[threadIdx.x][1] = rsqrtf(M2 / n + a.gn_eps);
         }
-        __syncthreads();
     }
-    if (l >= L) return;
+    __syncthreads();
     const int nj = C / (32 * VEC);
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+    const int l = lbase + rr;
+    if (l >= L) break;
     const float *xr = a.x + ((size_t)b * L + l) * C;
     float v[MAXJ * VEC];
     // load (+ depthwise conv over the 7 neighbouring rows; rows outside [0, L) are the conv's zero padding)
@@ -161,7 +174,7 @@ cl_rows_kernel(const RowArgs a) {
         } else {
             float acc[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = a.dw_b != nullptr ? a.dw_b[c + i] : 0.f;
+            for (int i = 0; i < VEC; ++i) acc[i] = dws[7 * C + c + i];
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
                 const int ll = l + t - 3;
@@ -169,12 +182,13 @@ cl_rows_kernel(const RowArgs a) {
                 const float *xp = a.x + ((size_t)b * L + ll) * C + c;
                 if (VEC == 4) {
                     const float4 xv = *reinterpret_cast<const float4 *>(xp);
-                    acc[0] = fmaf(a.dw_w[(c + 0) * 7 + t], xv.x, acc[0]);
-                    acc[1 % VEC] = fmaf(a.dw_w[(c + 1 % VEC) * 7 + t], xv.y, acc[1 % VEC]);
-                    acc[2 % VEC] = fmaf(a.dw_w[(c + 2 % VEC) * 7 + t], xv.z, acc[2 % VEC]);
-                    acc[3 % VEC] = fmaf(a.dw_w[(c + 3 % VEC) * 7 + t], xv.w, acc[3 % VEC]);
+                    const float4 wv = *reinterpret_cast<const float4 *>(dws + t * C + c);
+                    acc[0] = fmaf(wv.x, xv.x, acc[0]);
+                    acc[1 % VEC] = fmaf(wv.y, xv.y, acc[1 % VEC]);
+                    acc[2 % VEC] = fmaf(wv.z, xv.z, acc[2 % VEC]);
+                    acc[3 % VEC] = fmaf(wv.w, xv.w, acc[3 % VEC]);
                 } else {
-                    acc[0] = fmaf(a.dw_w[c * 7 + t], xp[0], acc[0]);
+                    acc[0] = fmaf(dws[t * C + c], xp[0], acc[0]);
                 }
             }
 #pragma unroll
@@ -233,6 +247,7 @@ cl_rows_kernel(const RowArgs a) {
             split_store(v[j * VEC], a.out.p, a.out.n, base + c);
         }
     }
+    }   // rows of this warp
 }
 
 // ---- softmax over the key axis -----------------------------------------------------------------------------------------
@@ -314,12 +329,14 @@ extern "C" int lina_codec_cl_rows(const float *x, const float *dw_w, const float
     a.ln_scale = ln_scale; a.ln_shift = ln_shift; a.out_f32 = out_f32;
     a.B = B; a.L = L; a.C = C; a.G = G; a.gn_tiles = (L + GN_ROWS - 1) / GN_ROWS; a.swish = swish;
     a.gn_eps = gn_eps; a.ln_eps = ln_eps;
-    const long long nblk = (long long)B * ((L + ROW_WARPS - 1) / ROW_WARPS);
+    constexpr int CTA_ROWS = ROW_WARPS * ROWS_PER_WARP;
+    const long long nblk = (long long)B * ((L + CTA_ROWS - 1) / CTA_ROWS);
     LINA_REQUIRE(nblk <= 2147483647LL, LINA_ERR_UNSUPPORTED, "codec_cl_rows: grid too large");
+    const size_t dsm = dw_w != nullptr ? (size_t)8 * C * sizeof(float) : 0;
     bool vec = C % 128 == 0 && al16(x) && (out_f32 == nullptr || al16(out_f32));
     for (int i = 0; i < n_parts; ++i) vec = vec && (((uintptr_t)out_parts[i] & 7u) == 0);
-    if (vec) cl_rows_kernel<4><<<(unsigned)nblk, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
-    else cl_rows_kernel<1><<<(unsigned)nblk, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    if (vec) cl_rows_kernel<4><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
+    else cl_rows_kernel<1><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
     LINA_LAUNCH_OK("cl_rows_kernel");
     return LINA_OK;
 }

@@ -20,7 +20,7 @@
 // Accumulation is PROMOTED to fp32 registers: the tensor core's own fp32 accumulator truncates after every K = 16 step
 // (measured here: relative error ~ steps * 2^-24, 2.5e-5 after 432 steps -- 30 x what an fp32 SIMT GEMM leaves, and a
 // bias, not noise: it survives averaging and the ISTFT head's exp() amplifies it).  So the two 256-column TMEM accumulators
-// are a ping-pong STAGE: the issuer accumulates `span` K blocks (default 2 = 8 MMA steps) into one of them, commits, and
+// are a ping-pong STAGE: the issuer accumulates `span` K blocks (default 8 = 32 MMA steps) into one of them, commits, and
 // moves to the other; the epilogue warps drain each finished span with tcgen05.ld and add it into 128 fp32 registers per
 // thread with IEEE round-to-nearest adds -- the same two-level scheme fp8 GEMMs use on Hopper.  The tile's epilogue math
 // and stores then run from those registers while the issuer is already two spans into the next tile.
@@ -34,7 +34,8 @@ using namespace sm100;
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
 constexpr int STAGES = 4;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr uint32_t OFF_BAR = STAGES * STAGE_BYTES;
+constexpr uint32_t OFF_STAGE = STAGES * STAGE_BYTES;          // per epilogue warp: one 32 x 32 fp32 chunk (4 KB) for coalescing
+constexpr uint32_t OFF_BAR = OFF_STAGE + 8 * 4096;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;          // + barriers / TMEM slot, + slack for the 1024-byte round-up
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + EPI_WARPS * 32;                  // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-9: epilogue
@@ -56,7 +57,7 @@ struct GemmParams {
     bf16 *out_split[MAX_PARTS];
     long long ld_split;
     int out_parts;
-    int vec_f32, vec_split, vec_res;
+    int vec_f32, vec_split, vec_res, vec_bias;
 };
 
 __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
@@ -70,7 +71,32 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     }
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. about one ulp of
+// the fp32 value 1 +- erf; branch-free, 2 MUFU + ~12 FMA-pipe instructions against ~35 with a divergent select for erff --
+// the epilogue runs on 8 warps per SM, its instruction count is what the tensor pipe ends up waiting for)
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.f)));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    pl *= t;
+    const float e = ex2_approx(-1.4426950408889634f * u * u);
+    const float erf_abs = fmaf(-pl, e, 1.f);
+    const float h = 0.5f * x;
+    return fmaf(copysignf(erf_abs, x), h, h);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 struct TileCoord { int batch, l0, n0; };
 __device__ __forceinline__ TileCoord tile_coord(const GemmParams &p, int tile) {
@@ -82,7 +108,11 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams &p, int tile) {
     return c;
 }
 
+// EPI bits: 0-1 = act (0 none, 1 gelu, 2 swish), 2 = fp32 output, 3 = bf16 parts output, 4 = residual
+template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int ACT = EPI & 3;
+    constexpr bool OUT_F32 = (EPI & 4) != 0, OUT_PARTS = (EPI & 8) != 0, HAS_RES = (EPI & 16) != 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
@@ -191,9 +221,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_sm100_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            const int l = c.l0 + r;
-            if (l >= p.L || !cols_live) continue;
-            const long long grow = (long long)c.batch * p.L + l;
+            if (!cols_live) continue;
+            // Memory phase of the epilogue.  A thread owns one ROW of the tile (TMEM lane = row), so direct global accesses
+            // would touch 32 different 128-byte lines per warp instruction (measured: the LSU, not the math, bounded the
+            // epilogue).  Each 32 x 32 chunk therefore passes through a per-warp shared-memory tile (XOR-swizzled 16-byte
+            // slots: 4 wavefronts per 512-byte access, the minimum) and global memory sees whole row segments: 4 lines per
+            // instruction for fp32, 8 half-lines for a bf16 part.
+            const int row0 = c.l0 + quarter * 32;                       // first row of this warp's 32-row block
+            const long long grow0 = (long long)c.batch * p.L + row0;
+            const uint32_t st4 = smem_u32(smem + OFF_STAGE + (warp - 2) * 4096);       // 16-byte slots, shared-space address
+            const int l = row0 + lane;
+            const long long grow = grow0 + lane;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int n = c.n0 + half * 128 + cc * 32;
@@ -203,63 +241,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_sm100_kernel(const __grid_co
                 for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
                 const bool full_chunk = n + 32 <= p.N;
                 if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) v[j] += __ldg(p.bias + n + j);
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                } else if (p.act == 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
-                }
-                if (p.gamma != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) v[j] *= __ldg(p.gamma + n + j);
-                }
-                if (p.residual != nullptr) {
-                    const float *rp = p.residual + grow * p.ld_res + n;
-                    if (p.vec_res && full_chunk) {
+                    if (full_chunk && p.vec_bias) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(reinterpret_cast<const float4 *>(rp) + j);
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + j);
                             v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rp + j);
+                        for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
                     }
                 }
-                if (p.out_f32 != nullptr) {
-                    float *op = p.out_f32 + grow * p.ld_out + n;
+                if (ACT == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (ACT == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+                }
+                if (p.gamma != nullptr) {
+                    if (full_chunk && p.vec_bias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(p.gamma + n) + j);
+                            v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] *= __ldg(p.gamma + n + j);
+                    }
+                }
+                if (HAS_RES) {
+                    if (l < p.L) {
+                        const float *rp = p.residual + grow * p.ld_res + n;
+                        if (p.vec_res && full_chunk) {        // 32 independent loads in flight per lane: latency, not LSU passes,
+#pragma unroll                                               // is what the staged variant of this read lost to
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(rp) + j);
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rp + j);
+                        }
+                    }
+                }
+                if (OUT_F32) {
                     if (p.vec_f32 && full_chunk) {
+                        __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4 *>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
+                            sts128(st4 + (lane * 8 + (j ^ (lane & 7))) * 16,
+                                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                              __float_as_uint(v[4 * j + 3])));
+                        __syncwarp();
+#pragma unroll
+                        for (int step = 0; step < 8; ++step) {
+                            const int rr = step * 4 + (lane >> 3), slot = lane & 7;
+                            if (row0 + rr < p.L)
+                                reinterpret_cast<uint4 *>(p.out_f32 + (grow0 + rr) * p.ld_out + n)[slot] = lds128(st4 + (rr * 8 + (slot ^ (rr & 7))) * 16);
+                        }
+                    } else if (l < p.L) {
+                        float *op = p.out_f32 + grow * p.ld_out + n;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (n + j < p.N) op[j] = v[j];
                     }
                 }
-                if (p.out_parts > 0) {
+                if (OUT_PARTS) {
                     // bf16 split of the result: part 0 = bf16(v), part i = bf16(remainder)
 #pragma unroll
                     for (int part = 0; part < MAX_PARTS; ++part) {
                         if (part >= p.out_parts) break;
-                        bf16 *spp = p.out_split[part] + grow * p.ld_split + n;
                         uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const bf16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
-                            v[2 * j] -= __bfloat162float(a);
-                            v[2 * j + 1] -= __bfloat162float(b);
-                            pk[j] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+                        for (int j = 0; j < 16; ++j) {                      // one cvt per pair; the remainders feed the next part
+                            pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                            v[2 * j] -= __uint_as_float(pk[j] << 16);
+                            v[2 * j + 1] -= __uint_as_float(pk[j] & 0xFFFF0000u);
                         }
                         if (p.vec_split && full_chunk) {
+                            // rows of 64 B: slot s of row r sits at r * 4 + (s ^ ((r >> 1) & 3))
+                            __syncwarp();
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                reinterpret_cast<uint4 *>(spp)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        } else {
+                                sts128(st4 + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+                            __syncwarp();
+#pragma unroll
+                            for (int step = 0; step < 4; ++step) {
+                                const int rr = step * 8 + (lane >> 2), slot = lane & 3;
+                                if (row0 + rr < p.L)
+                                    reinterpret_cast<uint4 *>(p.out_split[part] + (grow0 + rr) * p.ld_split + n)[slot] =
+                                        lds128(st4 + (rr * 4 + (slot ^ ((rr >> 1) & 3))) * 16);
+                            }
+                        } else if (l < p.L) {
+                            bf16 *spp = p.out_split[part] + grow * p.ld_split + n;
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (n + j < p.N) spp[j] = __ushort_as_bfloat16((unsigned short)((pk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu));
@@ -329,7 +404,7 @@ extern "C" int lina_gemm_bf16_terms(const lina_gemm_args *g, void *stream) {
     p.n_terms = g->n_terms;
     for (int i = 0; i < g->n_terms; ++i) { p.term_a[i] = g->term_a[i]; p.term_b[i] = g->term_b[i]; }
     p.taps = g->taps; p.pad = g->pad; p.K = g->K; p.kblocks = (g->K + BK - 1) / BK;
-    p.span = g->span > 0 ? g->span : 2;
+    p.span = g->span > 0 ? g->span : 8;
     p.L = g->L; p.NB = g->NB; p.N = g->N;
     p.tiles_m_per_batch = (g->L + BM - 1) / BM;
     p.tiles_n = (g->N + BN - 1) / BN;
@@ -351,18 +426,35 @@ extern "C" int lina_gemm_bf16_terms(const lina_gemm_args *g, void *stream) {
     LINA_REQUIRE(g->residual == nullptr || g->ld_res >= g->N, LINA_ERR_BAD_ARG, "gemm: ld_res < N");
     p.vec_f32 = g->out_f32 != nullptr && aligned16(g->out_f32) && g->ld_out % 4 == 0;
     p.vec_res = g->residual != nullptr && aligned16(g->residual) && g->ld_res % 4 == 0;
+    p.vec_bias = (g->bias == nullptr || aligned16(g->bias)) && (g->gamma == nullptr || aligned16(g->gamma));
     p.vec_split = g->out_parts > 0 && g->ld_split % 8 == 0;
     for (int i = 0; i < g->out_parts; ++i) p.vec_split = p.vec_split && aligned16(g->out_split[i]);
 
-    static thread_local uint64_t configured = 0;
-    if (lina_first_use_on_device(&configured))
-        LINA_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     static thread_local int n_sm[64] = {0};
     int dev = 0;
     LINA_CUDA_OK(cudaGetDevice(&dev));
     if (n_sm[dev & 63] == 0) LINA_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
     const int grid = p.total_tiles < n_sm[dev & 63] ? p.total_tiles : n_sm[dev & 63];
-    gemm_sm100_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    const int epi = g->act | (g->out_f32 != nullptr ? 4 : 0) | (g->out_parts > 0 ? 8 : 0) | (g->residual != nullptr ? 16 : 0);
+    int rc = LINA_ERR_UNSUPPORTED;
+    // one instantiation per epilogue shape the decoder uses (a compact straight-line epilogue each, instead of one kernel
+    // carrying every path); anything else is refused
+#define LINA_GEMM_CASE(E)                                                                                              \
+    case E: {                                                                                                          \
+        static thread_local uint64_t configured = 0;                                                                   \
+        if (lina_first_use_on_device(&configured))                                                                     \
+            LINA_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); \
+        gemm_sm100_kernel<E><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);                                   \
+        rc = LINA_OK;                                                                                                  \
+    } break;
+    switch (epi) {       // act (0 none, 1 gelu, 2 swish) | fp32 out 4 | parts out 8 | residual 16
+        LINA_GEMM_CASE(4) LINA_GEMM_CASE(5) LINA_GEMM_CASE(6) LINA_GEMM_CASE(8) LINA_GEMM_CASE(9) LINA_GEMM_CASE(10)
+        LINA_GEMM_CASE(12) LINA_GEMM_CASE(13) LINA_GEMM_CASE(14) LINA_GEMM_CASE(20) LINA_GEMM_CASE(21) LINA_GEMM_CASE(22)
+        LINA_GEMM_CASE(24) LINA_GEMM_CASE(25) LINA_GEMM_CASE(26) LINA_GEMM_CASE(28) LINA_GEMM_CASE(29) LINA_GEMM_CASE(30)
+        default: break;
+    }
+#undef LINA_GEMM_CASE
+    LINA_REQUIRE(rc == LINA_OK, LINA_ERR_UNSUPPORTED, "gemm: epilogue combination %d (act | fp32 4 | parts 8 | residual 16) is not built", epi);
     LINA_LAUNCH_OK("gemm_sm100_kernel");
     return LINA_OK;
 }

@@ -100,7 +100,7 @@ def test_promotion_span_controls_the_accumulation_error():
     ref = x.double() @ w.double().t()
     xs, ws = G.split(x.to(DEV), 3), G.split(w.to(DEV), 3)
     errs = {}
-    for span in (1, 2, 4, 1000):
+    for span in (1, 2, 3, 4, 6, 8, 12, 1000):
         out, _ = G.gemm_terms(xs, ws, NB=NB, Ln=Ln, N=N, K=K, span=span)
         errs[span] = _rel(out, ref)
     fp32 = _rel(x.to(DEV) @ w.to(DEV).t(), ref)
