@@ -297,7 +297,7 @@ int lina_codec_istft_head_ld(const float *h, long long ldh, const float *window,
  * codes -> sum over quantizers of codebook rows (DEC/pretrained.py:231-237), without the [B,C,L] feature tensor: */
 int lina_codec_cl_gather(const int64_t *codes, const float *codebooks, float *out_f32, void *const *out_parts, int n_parts,
                          int Kq, int B, int L, int bins, int C, void *stream);
-/* GroupNorm(G, C) statistics of [B, L, C] (DEC/models.py:15-16): Welford partials per (batch, 64-row tile, group),
+/* GroupNorm(G, C) statistics of [B, L, C] (DEC/models.py:15-16): Welford partials per (batch, 32-row tile, group),
  * merged by the consumer (lina_codec_cl_rows). */
 size_t lina_codec_cl_gn_partials_bytes(int B, int L, int G);
 int lina_codec_cl_gn_partials(const float *x, float *partials, int B, int L, int C, int G, void *stream);
@@ -312,6 +312,21 @@ int lina_codec_cl_rows(const float *x, const float *dw_w, const float *dw_b, con
  * n..ldP-1 zero (DEC/models.py:119-120). */
 int lina_codec_cl_softmax(const float *S, void *const *out_parts, int n_parts, long long rows, int n, long long ldS,
                           long long ldP, void *stream);
+
+/* Linear layers of ONE autoregressive step (M = batch <= lina_skinny_linear_max_rows() rows, bf16): weight-streaming kernel
+ * with the step's row-wise neighbours fused in (csrc/skinny_linear.cu).  Replaces, per MixingBlock and token
+ * (model/base_blocks.py:65-69, model/gla.py:91-99,225), nn.LayerNorm + the residual add in front of a projection and
+ * SwiGLU's silu(gate) * u behind it:
+ *   s   = x + delta                      (only with delta; written to sum_out, [M, K] contiguous; delta [M, ldd])
+ *   h   = LayerNorm(s) * ln_gamma + ln_beta   (only with ln_gamma / ln_beta; else h = x)
+ *   y   = h W^T + bias                   W [N, ldw] row-major
+ *   out = y                              (swiglu_pair_offset == 0)
+ *   out[:, j] = silu(y[:, j]) * y[:, swiglu_pair_offset + j]   (> 0: W holds gate rows [0, N) and u rows [offset, offset + N))
+ * Roundings follow the unfused sequence (bf16 after the add, after the LayerNorm, after the linear, after the product). */
+int lina_skinny_linear_max_rows(void);
+int lina_skinny_linear(const void *x, long long ldx, const void *delta, long long ldd, const void *ln_gamma, const void *ln_beta,
+                       float ln_eps, void *sum_out, const void *W, long long ldw, const void *bias, void *out, long long ldo,
+                       int M, int N, int K, int swiglu_pair_offset, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core contractions of the WavTokenizer decoder at fp32 fidelity (csrc/gemm_sm100.cu): replaces the cuDNN / cuBLAS

@@ -6,7 +6,7 @@
 // its fp32 result (hi [, mid], lo: see gemm_sm100.cu) instead of the fp32 tensor: same bytes, no extra pass.
 //
 //   lina_codec_cl_gather      codes -> codebook rows summed over quantizers -> split parts   (DEC/pretrained.py:231-237)
-//   lina_codec_cl_gn_partials per-(batch, 64-row tile, group) Welford partials of GroupNorm(32, C)   (DEC/models.py:15-16)
+//   lina_codec_cl_gn_partials per-(batch, 32-row tile, group) Welford partials of GroupNorm(32, C)   (DEC/models.py:15-16)
 //   lina_codec_cl_rows        [depthwise conv k=7] -> [GroupNorm apply] -> [swish] -> [LayerNorm * scale + shift] per row,
 //                             fp32 and / or split out   (ConvNeXtBlock :48-51, AdaLayerNorm :81-86, ResnetBlock :61-70,
 //                             AttnBlock :109, final_layer_norm, pos_net[5] + backbone.norm)
@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int GN_ROWS = 64;          // rows per partial tile
+constexpr int GN_ROWS = 32;          // rows per partial tile
 constexpr int MAXP = 3;
 
 __device__ __forceinline__ void split_store(float v, bf16 *const *parts, int nparts, size_t idx) {
@@ -80,11 +80,18 @@ cl_gn_partials_kernel(const float *__restrict__ x, float *__restrict__ partials,
     // problem in fp32 and need no division per element; (mean, M2) follow exactly as for Welford
     const float K0 = xp[0];
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < nrow; ++r) {
-        const float d = xp[(size_t)r * C] - K0;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
+    if (nrow == GN_ROWS) {                      // full tile: every load of the tile in flight at once
+        float d[GN_ROWS];
+#pragma unroll
+        for (int r = 0; r < GN_ROWS; ++r) d[r] = xp[(size_t)r * C];
+#pragma unroll
+        for (int r = 0; r < GN_ROWS; ++r) { const float t = d[r] - K0; s1 += t; s2 = fmaf(t, t, s2); }
+    } else {
+        for (int r = 0; r < nrow; ++r) {
+            const float t = xp[(size_t)r * C] - K0;
+            s1 += t;
+            s2 = fmaf(t, t, s2);
+        }
     }
     const float mean = K0 + s1 / (float)nrow;
     const float m2 = fmaxf(s2 - s1 * s1 / (float)nrow, 0.f);
@@ -120,10 +127,9 @@ struct RowArgs {
 constexpr int ROW_WARPS = 8;
 constexpr int ROWS_PER_WARP = 4;                 // consecutive rows of one warp (the CTA covers 32 consecutive rows)
 
-template <int VEC>      // 4: C % 128 == 0 (float4 per lane and step); 1: any C
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+template <int VEC, int MAXJ>      // VEC 4: C % 128 == 0 (float4 per lane and step), 1: any C; MAXJ: steps per lane, C <= 32 * VEC * MAXJ
+__global__ void __launch_bounds__(ROW_WARPS * 32, (VEC * MAXJ <= 24) ? 3 : 2)
 cl_rows_kernel(const RowArgs a) {
-    constexpr int MAXJ = 1024 / (32 * VEC);                     // steps per lane for C <= 1024
     __shared__ float gstat[64][2];                              // GroupNorm (mean, rstd) of this CTA's batch (G <= 64)
     extern __shared__ float dws[];                              // depthwise taps, transposed: [7][C] (+ bias [C])
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,8 +341,10 @@ extern "C" int lina_codec_cl_rows(const float *x, const float *dw_w, const float
     const size_t dsm = dw_w != nullptr ? (size_t)8 * C * sizeof(float) : 0;
     bool vec = C % 128 == 0 && al16(x) && (out_f32 == nullptr || al16(out_f32));
     for (int i = 0; i < n_parts; ++i) vec = vec && (((uintptr_t)out_parts[i] & 7u) == 0);
-    if (vec) cl_rows_kernel<4><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
-    else cl_rows_kernel<1><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
+    if (vec && C <= 768) cl_rows_kernel<4, 6><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
+    else if (vec) cl_rows_kernel<4, 8><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
+    else if (C <= 256) cl_rows_kernel<1, 8><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
+    else cl_rows_kernel<1, 32><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);
     LINA_LAUNCH_OK("cl_rows_kernel");
     return LINA_OK;
 }

@@ -48,6 +48,7 @@ class GateEnvelope:
     accumulate into the flag and the backbone reads it ONCE at the end -- no per-layer host synchronisation."""
     _flags = {}
     depth = 0
+    flagged_calls = 0        # mixer calls since the last read that relied on the device flag (no static certificate)
 
     @classmethod
     def flag(cls, device) -> torch.Tensor:
@@ -61,6 +62,7 @@ class GateEnvelope:
     @classmethod
     def tripped(cls, device) -> bool:
         """Read and clear (host synchronisation).  Never called during graph capture."""
+        cls.flagged_calls = 0
         f = cls.flag(device)
         hit = bool(f.item())
         if hit:
@@ -139,6 +141,30 @@ class GatedLinearAttention(nn.Module):
     _wcat = None
     _wcat4 = None
 
+    _gate_cert = None
+
+    def gate_preactivation_bound(self, input_norm_bound: float) -> float:
+        """Upper bound of |gk_proj(x)| over every channel for any input with ||x||_2 <= input_norm_bound:
+        max_c ( ||(W2 W1)_c||_2 * bound + |b_c| ), cached per weight version (one small GEMM when the weights change).  With
+        gate = logsigmoid(.) / normalizer a chunk of 64 tokens sums to at least 64 * logsigmoid(-bound) / normalizer, so a
+        bound below ~20 (normalizer 16) CERTIFIES that the tensor-core kernels' single-pivot range (-80) cannot be left and
+        no device-side check (and no host synchronisation) is needed for this layer."""
+        w1, w2, b2 = self.gk_proj[0].weight, self.gk_proj[1].weight, self.gk_proj[1].bias
+        key = tuple((t.data_ptr(), tensor_version(t), t.dtype) for t in (w1, w2) + ((b2,) if b2 is not None else ()))
+        if self._gate_cert is None or self._gate_cert[0] != key:
+            with torch.no_grad():
+                rows = (w2.detach().float() @ w1.detach().float()).norm(dim=1)
+                bias = b2.detach().float().abs() if b2 is not None else torch.zeros_like(rows)
+                self._gate_cert = (key, float(rows.max()), float(bias.max()))       # host reads: once per weight version
+        return self._gate_cert[1] * input_norm_bound + self._gate_cert[2]
+
+    def gates_certified(self, input_norm_bound) -> bool:
+        if input_norm_bound is None:
+            return False
+        x_min = -self.gate_preactivation_bound(float(input_norm_bound))
+        per_token = (x_min - math.log1p(math.exp(x_min))) if x_min > -30 else x_min      # logsigmoid
+        return 64.0 * per_token / float(self.gate_logit_normalizer) >= fla_ops.GATE_SUM_LIMIT
+
     # -- single-token fast path --------------------------------------------------------------------
     def _cat_weight(self):
         """[q;k;v;g;gk0] projection weights stacked so a decode step needs one GEMM for them."""
@@ -150,12 +176,18 @@ class GatedLinearAttention(nn.Module):
 
     def _step(self, x: torch.Tensor, state: Tuple[torch.Tensor, ...]) -> torch.Tensor:
         B = x.shape[0]
-        H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
         proj = F.linear(x.view(B, -1), self._cat_weight())
         if proj.dtype != x.dtype:
             raise TypeError(f"GatedLinearAttention._step: projection is {proj.dtype}, input is {x.dtype}")
+        return self.o_proj(self._step_core(proj, state)).view(B, 1, -1)
+
+    def _step_core(self, proj: torch.Tensor, state: Tuple[torch.Tensor, ...]) -> torch.Tensor:
+        """The step between the two GEMMs: proj [B, q;k;v;g;gk0] -> norm-gated o [B, value_dim]; states updated in place."""
+        B = proj.shape[0]
+        H, K, V, kd, vd = self.num_heads, self.head_qk_dim, self.head_v_dim, self.key_dim, self.value_dim
         xq, xk, xv, g, lo = torch.split(proj, [kd, kd, vd, vd, proj.shape[1] - 2 * kd - 2 * vd], dim=1)
         ldx = proj.shape[1]                            # the four slices are read in place with this row stride
+        x = proj
         if self.use_short_conv:
             cq, ck, cv, S = state
             W = self.conv_size
@@ -183,7 +215,7 @@ class GatedLinearAttention(nn.Module):
                                   float(self.gate_logit_normalizer), float(self.g_norm_swish_gate.eps), ldx, L.stream(x))
         L.count_launches(3)
         L.check(rc, "lina_gla_step_lr")
-        return self.o_proj(out).view(B, 1, -1)
+        return out
 
     # -- whole-sequence inference fast path ----------------------------------------------------------
     def _cat_weight4(self):
@@ -204,7 +236,7 @@ class GatedLinearAttention(nn.Module):
                 and self.head_v_dim * x.element_size() // 16 <= 128
                 and self.q_proj.weight.dtype == x.dtype)
 
-    def _prefill(self, x: torch.Tensor, last_state, use_cache: bool, past_key_values) -> torch.Tensor:
+    def _prefill(self, x: torch.Tensor, last_state, use_cache: bool, past_key_values, input_norm_bound=None) -> torch.Tensor:
         """model/gla.py:146-225 for a whole sequence without autograd: one [q;k;v;g] GEMM, ONE pass for the three
         short convs + the gate non-linearity (lina_gla_prefill_prep), the GLA op on the [B,T,H,D] layout, the
         norm-gate reading g in place from the projection buffer, o_proj."""
@@ -249,8 +281,11 @@ class GatedLinearAttention(nn.Module):
             # q, k hold the gated MMA operands q~ = scale q e^G, k~ = k e^-G; gk is never materialised
             nt = (T + 63) // 64
             decay = torch.empty(B, H, nt, K, dtype=torch.float32, device=x.device)
-            check = fla_ops.GATE_CHECK and not torch.cuda.is_current_stream_capturing()
+            check = (fla_ops.GATE_CHECK and not torch.cuda.is_current_stream_capturing()
+                     and not self.gates_certified(input_norm_bound))
             flag = GateEnvelope.flag(x.device) if check else None
+            if check:
+                GateEnvelope.flagged_calls += 1
             rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldq, L.ptr(xk), ldk, L.ptr(xv), ldv, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                                  L.ptr(gk_raw), gk_raw.stride(1), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay),
                                                  L.ptr(cq), L.ptr(ck), L.ptr(cv), L.dt(cq) if cq is not None else 0,
@@ -332,7 +367,7 @@ class GatedLinearAttention(nn.Module):
             return o
 
         if self._can_prefill(hidden_states, reset_mask, attention_mask) and (not use_cache or last_state is not None):
-            return self._prefill(hidden_states, last_state, use_cache, past_key_values)
+            return self._prefill(hidden_states, last_state, use_cache, past_key_values, kwargs.get("input_norm_bound"))
 
         q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
         if self.use_short_conv:
@@ -447,6 +482,14 @@ class AttentiveGLA(AttentiveRNN):
             x = d(x, use_cache=init_state is not None, past_key_values=init_state)
         return x, att
 
+    def _all_certified(self) -> bool:
+        """Every mixer's gates are bounded inside the tensor-core envelope by its weights alone (cached per weight version):
+        no device flag will be written, so no cache snapshot and no host read are needed."""
+        blocks = list(self.encoder) + list(self.decoder)
+        if hasattr(self.cross_att, "pos_net"):
+            blocks.append(self.cross_att.pos_net)
+        return all(hasattr(b, "_ln_output_norm_bound") and b.tmix.gates_certified(b._ln_output_norm_bound()) for b in blocks)
+
     def _forward_fused(self, x, ctx, mask, reset_mask, init_state, crossatt_pos):
         """Inference pass with the residual adds folded into the LayerNorms.  The 13 mixers run on the pre-gated tensor-core
         kernels without looking at their gates one by one; the gate-envelope flag they accumulate is read ONCE here."""
@@ -464,12 +507,14 @@ class AttentiveGLA(AttentiveRNN):
 
         capturing = torch.cuda.is_current_stream_capturing()
         snap = None
-        if init_state is not None and not capturing and fla_ops.GATE_CHECK and x.shape[1] > 1:
+        if init_state is not None and not capturing and fla_ops.GATE_CHECK and x.shape[1] > 1 and not self._all_certified():
             snap = [tuple(t.clone() for t in st) for st in init_state.states]      # the pass updates the cache in place
+        GateEnvelope.flagged_calls = 0
         with GateEnvelope.deferred():
             out = run()
-        if capturing or not fla_ops.GATE_CHECK or x.shape[1] == 1 or not GateEnvelope.tripped(x.device):
-            return out
+        if (capturing or not fla_ops.GATE_CHECK or x.shape[1] == 1 or GateEnvelope.flagged_calls == 0
+                or not GateEnvelope.tripped(x.device)):
+            return out                                        # every mixer certified by its weights, or the flag is clear
         # some chunk's summed log gate fell below -80: redo the pass with the exact kernels (the reference is exact for any gate)
         if snap is not None:
             for st, sn in zip(init_state.states, snap):
@@ -541,14 +586,16 @@ class AttentiveGLA(AttentiveRNN):
                     xr, d = dd.forward_fused(xr, d, **kw)
                 return xr + d, att, cache
 
-            if y_embd.shape[1] == 1 or torch.cuda.is_current_stream_capturing() or not fla_ops.GATE_CHECK:
+            if (y_embd.shape[1] == 1 or torch.cuda.is_current_stream_capturing() or not fla_ops.GATE_CHECK
+                    or self._all_certified()):
                 return run()                                  # single-token steps run the exact recurrence (lina_gla_step)
             # multi-token prompt prefill: same deferred gate-envelope policy as _forward_fused
             snap = [tuple(t.clone() for t in st) for st in cache.states]
             seen = getattr(cache, "_seen_tokens", None)
+            GateEnvelope.flagged_calls = 0
             with GateEnvelope.deferred():
                 out = run()
-            if not GateEnvelope.tripped(y_embd.device):
+            if GateEnvelope.flagged_calls == 0 or not GateEnvelope.tripped(y_embd.device):
                 return out
             for st, sn in zip(cache.states, snap):
                 for a, b in zip(st, sn):

@@ -212,33 +212,67 @@ class LinaModel(nn.Module):
             q_s = self._sample(self.logits_head(y_out), k, first_greedy_quant, temp)
             return q_s, att, self.rvq_embed(q_s).sum(0)
 
-        graph = None
+        world_b = batch_size * world
         if cuda_graph:
-            # static buffers; the step reads y_buf and writes q_buf / att_buf / emb_buf
+            # ONE graph replay per token and nothing else on the host: besides the model step the graph writes the sampled ids
+            # (all-gathered over ``dist_group`` INSIDE the graph) and the attention rows into their slot of the output
+            # buffers (device-side step counter), keeps the "all stopped" flag, and picks the next input (prompt embedding
+            # while teacher-forcing, the sampled token's embedding afterwards).
+            n_txt = x_enc.shape[1]
+            qs_out = torch.zeros(self.n_quant, world_b, max_seqlen, device=device, dtype=torch.long)
+            t_dev = torch.zeros(1, device=device, dtype=torch.long)
             y_buf = y_embd.clone()
+            all_stop = torch.zeros(world_b, 1, device=device, dtype=torch.bool)
+            p_tab = prompt if (exists(prompt) and p_len > 0) else None
+            p_len_dev = torch.full((1,), max(p_len, 0), device=device, dtype=torch.long)
+            atts_out = None
+
+            def graph_step():
+                nonlocal atts_out
+                q_s, att, emb = one_step(y_buf, 0)
+                q_all = gather_tokens(q_s, dist_group) if dist_group is not None else q_s
+                qs_out.index_copy_(2, t_dev, q_all)
+                if att is not None:
+                    if atts_out is None:
+                        atts_out = torch.zeros(att.shape[0], att.shape[1], max_seqlen, att.shape[3], device=device, dtype=att.dtype)
+                    atts_out.index_copy_(2, t_dev, att)
+                all_stop.logical_or_((q_all == stop_token).prod(dim=0).bool())
+                if p_tab is not None:                          # modeling_lina.py:175-178: the prompt is teacher-forced
+                    forced = p_tab.index_select(1, torch.minimum(t_dev, p_len_dev - 1))
+                    emb = torch.where(t_dev < p_len_dev, forced, emb)
+                y_buf.copy_(emb)
+                t_dev.add_(1)
+
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                      # warm-up outside capture (allocs, cuBLAS handles)
-                snap = [tuple(s.clone() for s in st) for st in state.states]
+            with torch.cuda.stream(side):                      # warm-up outside capture (allocations, cuBLAS / NCCL handles)
+                snap = [tuple(s_.clone() for s_ in st) for st in state.states]
+                y_snap = y_buf.clone()
                 for _ in range(2):
-                    one_step(y_buf, 0)
-                for st, sn in zip(state.states, snap):
-                    for a, b in zip(st, sn):
-                        a.copy_(b)
+                    graph_step()
+
+                def restore():
+                    for st, sn in zip(state.states, snap):
+                        for a, b in zip(st, sn):
+                            a.copy_(b)
+                    y_buf.copy_(y_snap)
+                    t_dev.zero_()
+                    all_stop.zero_()
+                    qs_out.zero_()
+                restore()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                q_buf, att_buf, emb_buf = one_step(y_buf, 0)
-            for st, sn in zip(state.states, snap):             # capture does not execute; restore anyway
-                for a, b in zip(st, sn):
-                    a.copy_(b)
+                graph_step()
+            restore()                                          # capture does not execute; restore anyway
 
         if _timing is not None:                                # bench hook: device time of the steady-state loop
             _timing["start"], _timing["end"] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             _timing["start"].record()
         qs, atts, stop_tokens = [], [], []
-        all_stop = torch.zeros(batch_size * world, 1, device=device, dtype=torch.bool)
         t_start = 0
+        if not cuda_graph:
+            all_stop = torch.zeros(world_b, 1, device=device, dtype=torch.bool)
         if prefill_prompt and exists(prompt) and p_len > 0:
             n_pre = min(p_len + 1, max_seqlen)                      # inputs of steps 0 .. p_len: start token, then the prompt
             y_seq = torch.cat([y_embd, prompt[:, :n_pre - 1]], dim=1)
@@ -249,40 +283,51 @@ class LinaModel(nn.Module):
                 atts.append(att_pre[:, :, t:t + 1] if att_pre is not None else None)
                 q_all = gather_tokens(q_sampled, dist_group) if dist_group is not None else q_sampled
                 qs.append(q_all)
-                is_stop = (q_all == stop_token).prod(dim=0)
-                stop_tokens.append(is_stop)
-                all_stop.logical_or_(is_stop.bool())
+                all_stop.logical_or_((q_all == stop_token).prod(dim=0).bool())
             y_embd = self.rvq_embed(q_sampled).sum(0)               # first free position: fed with the last sampled token
             t_start = n_pre
-        for t in range(t_start, max_seqlen):
-            if graph is not None:
+        if cuda_graph:
+            if t_start > 0:                                         # hand the prefilled positions to the graph's buffers
+                qs_out[:, :, :t_start] = torch.cat(qs, dim=2)
+                if atts_out is not None and atts[0] is not None:
+                    atts_out[:, :, :t_start] = torch.cat(atts, dim=2)
                 y_buf.copy_(y_embd)
+                t_dev.fill_(t_start)
+            n_steps = t_start
+            for t in range(t_start, max_seqlen):
                 graph.replay()
-                q_sampled, att, emb = q_buf.clone(), att_buf.clone() if att_buf is not None else None, emb_buf.clone()
-            else:
+                n_steps = t + 1
+                if not force_max_seqlen and n_steps % stop_check_interval == 0 and bool(all_stop.all()):
+                    break
+            if _timing is not None:
+                _timing["end"].record()
+                _timing["steps"] = n_steps
+            qs = qs_out[:, :, :n_steps]
+            atts = atts_out[:, :, :n_steps] if atts_out is not None else None
+            is_stop = (qs == stop_token).prod(dim=0)                # [b_global, steps]
+            stop_tokens = torch.cat([is_stop, torch.ones(world_b, 1, device=device, dtype=is_stop.dtype)], dim=1).float()
+        else:
+            for t in range(t_start, max_seqlen):
                 q_sampled, att, emb = one_step(y_embd, t)
-            atts.append(att)
-            if dist_group is not None:
-                # the one exchange of the data path: [q, b_local, 1] int64 ids -> [q, b_global, 1]
-                q_all = gather_tokens(q_sampled, dist_group)
-            else:
-                q_all = q_sampled
-            qs.append(q_all)
-            is_stop = (q_all == stop_token).prod(dim=0)
-            stop_tokens.append(is_stop)
-            all_stop.logical_or_(is_stop.bool())
-            if not force_max_seqlen and (t + 1) % stop_check_interval == 0 and bool(all_stop.all()):
-                break
-            y_embd = prompt[:, [t]] if (exists(prompt) and t < p_len) else emb
-
-        if _timing is not None:
-            _timing["end"].record()
-            _timing["steps"] = len(qs)
-        atts = torch.cat(atts, dim=2) if exists(atts[0]) else None
-        qs = torch.stack(qs, dim=2).squeeze(-1)
-        bg = batch_size * world
-        stop_tokens.append(torch.ones(bg, 1, device=device))
-        stop_tokens = torch.stack(stop_tokens, dim=1).squeeze(-1)
+                atts.append(att)
+                if dist_group is not None:
+                    # the one exchange of the data path: [q, b_local, 1] int64 ids -> [q, b_global, 1]
+                    q_all = gather_tokens(q_sampled, dist_group)
+                else:
+                    q_all = q_sampled
+                qs.append(q_all)
+                all_stop.logical_or_((q_all == stop_token).prod(dim=0).bool())
+                if not force_max_seqlen and (t + 1) % stop_check_interval == 0 and bool(all_stop.all()):
+                    break
+                y_embd = prompt[:, [t]] if (exists(prompt) and t < p_len) else emb
+            if _timing is not None:
+                _timing["end"].record()
+                _timing["steps"] = len(qs)
+            atts = torch.cat(atts, dim=2) if exists(atts[0]) else None
+            qs = torch.stack(qs, dim=2).squeeze(-1)
+            is_stop = (qs == stop_token).prod(dim=0)
+            stop_tokens = torch.cat([is_stop, torch.ones(world_b, 1, device=device, dtype=is_stop.dtype)], dim=1).float()
+        bg = world_b
         n = stop_tokens.shape[1]
         rvq = (undelay_rvq(qs) - self.n_special_token_in).clamp_min(0)
         stop_idx = (stop_tokens * torch.arange(n, device=device).unsqueeze(0)).long()

@@ -398,3 +398,22 @@ def test_modules_unpickled_without_init_have_their_lazy_caches():
         import sys
         for name in done:
             sys.modules.pop(name, None)
+
+
+def test_gate_certificate_from_weights_alone():
+    """GatedLinearAttention.gates_certified: ||(W2 W1)_c|| * ||LN output|| + |b_c| bounds the gate pre-activation; when the
+    bound keeps 64 * logsigmoid(-bound) / normalizer above -80 the inference path needs no device flag and no host read."""
+    import lina_speech_b200.model as M
+    torch.manual_seed(0)
+    blk = M.AttentiveGLA(256, 1, 4, blind=True, use_short_conv=True, pos_type="convolutional").encoder[0]
+    bound = blk._ln_output_norm_bound()
+    assert abs(bound - 16.0) < 1e-5                                   # default LayerNorm: gamma 1, beta 0 -> sqrt(256)
+    assert blk.tmix.gates_certified(bound)                           # xavier(gain 2^-2.5) gate projections: tiny pre-activations
+    assert not blk.tmix.gates_certified(None)
+    with torch.no_grad():
+        blk.tmix.gk_proj[1].bias[3] = -48.0                          # logsigmoid(-48) / 16 * 64 = -192 < -80
+    assert not blk.tmix.gates_certified(bound)
+    with torch.no_grad():
+        blk.tmix.gk_proj[1].bias[3] = 0.0
+        blk.norm1.weight.mul_(400.0)                                 # a huge LayerNorm gain voids the certificate too
+    assert not blk.tmix.gates_certified(blk._ln_output_norm_bound())
