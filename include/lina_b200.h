@@ -313,6 +313,14 @@ int lina_codec_cl_rows(const float *x, const float *dw_w, const float *dw_b, con
 int lina_codec_cl_softmax(const float *S, void *const *out_parts, int n_parts, long long rows, int n, long long ldS,
                           long long ldP, void *stream);
 
+/* One decode step of a single-head softmax attention against memoised text-side tensors (BlindCrossAttention, model/crossatt.py:
+ * 105-155, eval branch :13-19): w = softmax(LayerNorm?(q) K^T * scale), out = w V per sequence.  q [B, ldq]; keys / vals
+ * [B, n, d] (batch stride in elements; 0 = one table shared by every sequence, e.g. the positional embeddings);
+ * att_out [B, att_bstride] receives w (nullable); out [B, ldo].  ln_w / ln_b NULL = no LayerNorm on q. */
+int lina_cross_att_step(const void *q, long long ldq, const void *ln_w, const void *ln_b, float eps, const void *keys,
+                        long long key_bstride, const void *vals, long long val_bstride, void *att_out, long long att_bstride,
+                        void *out, long long ldo, int B, int n, int d, float scale, int dtype, void *stream);
+
 /* Linear layers of ONE autoregressive step (M = batch <= lina_skinny_linear_max_rows() rows, bf16): weight-streaming kernel
  * with the step's row-wise neighbours fused in (csrc/skinny_linear.cu).  Replaces, per MixingBlock and token
  * (model/base_blocks.py:65-69, model/gla.py:91-99,225), nn.LayerNorm + the residual add in front of a projection and

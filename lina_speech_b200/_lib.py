@@ -71,6 +71,8 @@ PROTOTYPES = {
     "lina_codec_cl_gn_partials_bytes": (_sz, [_i] * 3),
     "lina_codec_cl_gn_partials": (_i, [_p, _p] + [_i] * 4 + [_p]),
     "lina_codec_cl_rows": (_i, [_p] * 6 + [_i, _f, _i, _p, _p, _f, _p, _p] + [_i] * 4 + [_p]),
+    "lina_cross_att_step": (_i, [_p, C.c_longlong, _p, _p, _f, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong,
+                                 _i, _i, _i, _f, _i, _p]),
     "lina_skinny_linear_max_rows": (_i, []),
     "lina_skinny_linear": (_i, [_p, C.c_longlong, _p, C.c_longlong, _p, _p, _f, _p, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _i, _i, _i, _p]),
     "lina_codec_cl_softmax": (_i, [_p, _p, _i, C.c_longlong, _i, C.c_longlong, C.c_longlong, _p]),

@@ -111,12 +111,36 @@ def _gates_in_envelope(gk: torch.Tensor) -> bool:
     return bool(_min_chunk_gate_sum(gk).item() >= GATE_SUM_LIMIT)        # NaN gates compare False -> exact path
 
 
+_CERTIFIED = False        # set by gates_certified_scope: the caller proved the gates inside the envelope (no device read needed)
+
+
+class gates_certified_scope:
+    """``with gates_certified_scope(True): chunk_gla(...)`` -- the caller vouches that every 64-token chunk's summed log gate
+    stays above GATE_SUM_LIMIT (GatedLinearAttention derives this from its weights, model/gla.py:gates_certified), so the
+    operator skips its reduction + host read and the backward may use the tensor-core path."""
+
+    def __init__(self, ok: bool):
+        self.ok = bool(ok)
+
+    def __enter__(self):
+        global _CERTIFIED
+        self.prev, _CERTIFIED = _CERTIFIED, self.ok
+        return self
+
+    def __exit__(self, *exc):
+        global _CERTIFIED
+        _CERTIFIED = self.prev
+        return False
+
+
 def _route(kind: str, q, v, gk, uses_tc):
     """'recurrent' | 'chunk' | 'fused_chunk' -> (kernel family that serves the forward, gates_ok): the chunk forms fall back
     to the exact recurrence when they would run on the tensor-core kernel with gates outside its numeric envelope.
     gates_ok is None when the gates were not looked at (the backward looks then, if it wants the tensor-core path)."""
     if kind == "recurrent" or not GATE_CHECK:
         return kind, (None if GATE_CHECK else True)
+    if _CERTIFIED:
+        return kind, True
     B, H, T, K = q.shape
     if not uses_tc(B, H, T, K, v.shape[-1], L._DT.get(q.dtype, -1)):
         return kind, None

@@ -16,6 +16,34 @@ AUTOCAST_LN = os.environ.get("LINA_AUTOCAST_LN", "1") != "0"
 SKINNY_STEP = os.environ.get("LINA_SKINNY_STEP", "0") == "1"
 
 
+class AsyncBound:
+    """A scalar bound derived from parameters, refreshed WITHOUT stalling the stream.  The first value is read synchronously;
+    afterwards, when the parameters' versions change (every optimizer step in training), the new value is computed on the
+    device, copied to pinned host memory without blocking, and adopted once its event has completed -- until then the last
+    known value answers.  Consumers apply a 2x safety margin for that one-step staleness."""
+
+    def __init__(self):
+        self.key, self.value, self.pending = None, None, None
+
+    def get(self, key, compute):
+        """``compute()`` -> 0-dim device tensor (or python float on CPU)."""
+        if self.pending is not None and self.pending[2].query():
+            self.value, self.pending = float(self.pending[1]), None
+        if key != self.key:
+            self.key = key
+            with torch.no_grad():
+                v = compute()
+            if self.value is None or not torch.is_tensor(v) or not v.is_cuda:
+                self.value, self.pending = float(v), None
+            elif self.pending is None:
+                host = torch.empty((), dtype=torch.float32, pin_memory=True)
+                host.copy_(v.float(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(v.device))
+                self.pending = (key, host, ev)
+        return self.value
+
+
 def _ver(t) -> int:
     try:
         return t._version
@@ -181,6 +209,9 @@ class MixingBlock(nn.Module):
         self.drop = nn.Dropout(dropout)
 
     def forward(self, x, **kwargs):
+        if hasattr(self.tmix, "gates_certified") and isinstance(self.norm1, nn.LayerNorm) and self.norm1.elementwise_affine \
+                and self.norm1.bias is not None:
+            kwargs = dict(kwargs, input_norm_bound=self._ln_output_norm_bound())
         t = self.tmix(autocast_layernorm(x, self.norm1), **kwargs)
         x = (t[0] if type(t) is tuple else t) + x
         x = self.cmix(autocast_layernorm(x, self.norm2)) + x
@@ -189,13 +220,13 @@ class MixingBlock(nn.Module):
     _ln_bound = None
 
     def _ln_output_norm_bound(self) -> float:
+        """||LayerNorm(.)||_2 <= sqrt(d) max|gamma| + ||beta||_2 (see AsyncBound for how it follows the parameters)."""
         n = self.norm1
+        if self._ln_bound is None:
+            self._ln_bound = AsyncBound()
         key = (n.weight.data_ptr(), _ver(n.weight), n.bias.data_ptr(), _ver(n.bias))
-        if self._ln_bound is None or self._ln_bound[0] != key:
-            with torch.no_grad():
-                d = n.weight.numel()
-                self._ln_bound = (key, float(n.weight.detach().float().abs().max()) * d ** 0.5 + float(n.bias.detach().float().norm()))
-        return self._ln_bound[1]
+        d = n.weight.numel()
+        return self._ln_bound.get(key, lambda: n.weight.detach().float().abs().max() * d ** 0.5 + n.bias.detach().float().norm())
 
     # -- inference fast path: residual adds fused into the following LayerNorm -------------------------------
     def can_fuse(self, x) -> bool:

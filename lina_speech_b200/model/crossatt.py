@@ -15,6 +15,15 @@ from einops import rearrange
 from .positional import ConvPos, SinPos
 
 
+import os
+
+# LINA_FUSED_CROSSATT_STEP=1: the single-token cross attention runs as two launches of lina_cross_att_step instead of the torch
+# sequence (LayerNorm, q k^T, scale, softmax, w v: ~10 launches).  Measured on B200 inside the CUDA-graphed decode step
+# (profiles/ab_decode_r02.json): 0.93 ms per step against 0.89 ms op by op at batch 32 -- one CTA per sequence streams its
+# 2 x 256 KB of keys / values at 17 us per launch, the batched library matmuls spread them over all SMs.  Default off.
+FUSED_STEP = os.environ.get("LINA_FUSED_CROSSATT_STEP", "0") == "1"
+
+
 def exists(x):
     return x is not None
 
@@ -86,12 +95,55 @@ class BlindCrossAttention(nn.Module):
         if pos is None:
             pos = torch.arange(k.shape[2], device=k.device).unsqueeze(0)
         pos_emb = self.pos_embed(pos).unsqueeze(1)
+        if key is not None:                       # memoised for the decode loop: the fused step kernel reads plain [n, d] rows
+            k, v, pos_emb = k.contiguous(), v.contiguous(), pos_emb.contiguous()
         out = (k, v, pos_emb)
         if key is not None:
             self._memo = (ctx, key, out)
         return out
 
+    def _can_step_fused(self, q, mask, pos) -> bool:
+        return (FUSED_STEP and q.dim() == 3 and q.shape[1] == 1 and q.is_cuda and mask is None and pos is None
+                and not self.training and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+                and q.dtype in (torch.float32, torch.bfloat16, torch.float16) and self.q.weight.dtype == q.dtype
+                and q.shape[-1] % (16 // q.element_size()) == 0)
+
+    def _step_fused(self, q, ctx, **kwargs):
+        """One token: q projection (GEMM), then ONE launch for LayerNorm + softmax(q k^T) + the read of the positional table,
+        the pos_net block, and ONE launch for softmax(x pos^T) + the read of the text values (lina_cross_att_step); the two
+        attention rows land in their slots of one [B, 2, 1, n] tensor."""
+        from .. import _lib as L
+        k, v, pos_emb = self._text_side(ctx, None)                      # [B,1,n,d], [B,1,n,d], [1,1,n,d]
+        B, d = q.shape[0], k.shape[-1]
+        n = k.shape[2]
+        if not (k.is_contiguous() and v.is_contiguous() and pos_emb.is_contiguous() and k.dtype == q.dtype == v.dtype
+                and pos_emb.dtype == q.dtype and k.shape[0] == B):
+            return None
+        qlin = self.q(q).view(B, d)
+        att = torch.empty(B, 2, 1, n, dtype=q.dtype, device=q.device)
+        x = torch.empty(B, d, dtype=q.dtype, device=q.device)
+        scale = 1.0 / math.sqrt(d)
+        lib = L.lib()
+        rc = lib.lina_cross_att_step(L.ptr(qlin), qlin.stride(0), L.ptr(self.ln_q.weight), L.ptr(self.ln_q.bias), float(self.ln_q.eps),
+                                     L.ptr(k), n * d, L.ptr(pos_emb), 0, L.ptr(att), 2 * n, L.ptr(x), d, B, n, d, scale, L.dt(q),
+                                     L.stream(q))
+        L.count_launches(1)
+        L.check(rc, "lina_cross_att_step")
+        y = self.pos_net(x.view(B, 1, d), **kwargs)
+        y = (y[0] if type(y) is tuple else y).reshape(B, d)
+        out = torch.empty(B, d, dtype=q.dtype, device=q.device)
+        att2 = att[:, 1]
+        rc = lib.lina_cross_att_step(L.ptr(y), y.stride(0), None, None, 0.0, L.ptr(pos_emb), 0, L.ptr(v), n * d, L.ptr(att2), 2 * n,
+                                     L.ptr(out), d, B, n, d, scale, L.dt(q), L.stream(q))
+        L.count_launches(1)
+        L.check(rc, "lina_cross_att_step")
+        return out.view(B, 1, d), att
+
     def forward(self, q, k, mask=None, time_step=None, pos=None, **kwargs):
+        if self._can_step_fused(q, mask, pos):
+            r = self._step_fused(q, k, **kwargs)
+            if r is not None:
+                return r
         q = self.ln_q(self.q(q)).unsqueeze(1)
         k, v, pos_emb = self._text_side(k, pos)
         if mask is not None:

@@ -145,23 +145,24 @@ class GatedLinearAttention(nn.Module):
 
     def gate_preactivation_bound(self, input_norm_bound: float) -> float:
         """Upper bound of |gk_proj(x)| over every channel for any input with ||x||_2 <= input_norm_bound:
-        max_c ( ||(W2 W1)_c||_2 * bound + |b_c| ), cached per weight version (one small GEMM when the weights change).  With
+        max_c ( ||(W2 W1)_c||_2 * bound + |b_c| ), following the weights through AsyncBound (one small GEMM when they change).  With
         gate = logsigmoid(.) / normalizer a chunk of 64 tokens sums to at least 64 * logsigmoid(-bound) / normalizer, so a
         bound below ~20 (normalizer 16) CERTIFIES that the tensor-core kernels' single-pivot range (-80) cannot be left and
         no device-side check (and no host synchronisation) is needed for this layer."""
+        from .base_blocks import AsyncBound
         w1, w2, b2 = self.gk_proj[0].weight, self.gk_proj[1].weight, self.gk_proj[1].bias
         key = tuple((t.data_ptr(), tensor_version(t), t.dtype) for t in (w1, w2) + ((b2,) if b2 is not None else ()))
-        if self._gate_cert is None or self._gate_cert[0] != key:
-            with torch.no_grad():
-                rows = (w2.detach().float() @ w1.detach().float()).norm(dim=1)
-                bias = b2.detach().float().abs() if b2 is not None else torch.zeros_like(rows)
-                self._gate_cert = (key, float(rows.max()), float(bias.max()))       # host reads: once per weight version
-        return self._gate_cert[1] * input_norm_bound + self._gate_cert[2]
+        if self._gate_cert is None:
+            self._gate_cert = (AsyncBound(), AsyncBound())
+        rows = self._gate_cert[0].get(key, lambda: (w2.detach().float() @ w1.detach().float()).norm(dim=1).max())
+        bias = self._gate_cert[1].get(key, lambda: b2.detach().float().abs().max() if b2 is not None else 0.0)
+        return rows * input_norm_bound + bias
 
     def gates_certified(self, input_norm_bound) -> bool:
         if input_norm_bound is None:
             return False
-        x_min = -self.gate_preactivation_bound(float(input_norm_bound))
+        # 2x margin: in training the bounds may lag the parameters by one optimizer step (AsyncBound)
+        x_min = -2.0 * self.gate_preactivation_bound(float(input_norm_bound))
         per_token = (x_min - math.log1p(math.exp(x_min))) if x_min > -30 else x_min      # logsigmoid
         return 64.0 * per_token / float(self.gate_logit_normalizer) >= fla_ops.GATE_SUM_LIMIT
 
@@ -399,14 +400,18 @@ class GatedLinearAttention(nn.Module):
             gk = gk.masked_fill(reset_mask.unsqueeze(1).unsqueeze(3), reset_val)
 
         recurrent_state = last_state[-1] if use_cache else None
-        if mode == "fused_recurrent":
-            o, recurrent_state = fused_recurrent_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
-        elif mode == "fused_chunk":
-            o, recurrent_state = fused_chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
-        elif mode == "chunk":
-            o, recurrent_state = chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
-        else:
-            raise NotImplementedError(f"Not supported mode `{mode}`.")
+        # gates provably inside the tensor-core kernels' range (weights + the norm bound of the LayerNorm in front): the
+        # operator then skips its per-call reduction and host read -- 13 synchronisations per training step otherwise
+        cert = reset_mask is None and self.gates_certified(kwargs.get("input_norm_bound"))
+        with fla_ops.gates_certified_scope(cert):
+            if mode == "fused_recurrent":
+                o, recurrent_state = fused_recurrent_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+            elif mode == "fused_chunk":
+                o, recurrent_state = fused_chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+            elif mode == "chunk":
+                o, recurrent_state = chunk_gla(q, k, v, gk, initial_state=recurrent_state, output_final_state=use_cache)
+            else:
+                raise NotImplementedError(f"Not supported mode `{mode}`.")
 
         if past_key_values is not None and not self.training:          # model/gla.py:205-213
             if self.use_short_conv:

@@ -409,6 +409,7 @@ def test_gate_certificate_from_weights_alone():
     bound = blk._ln_output_norm_bound()
     assert abs(bound - 16.0) < 1e-5                                   # default LayerNorm: gamma 1, beta 0 -> sqrt(256)
     assert blk.tmix.gates_certified(bound)                           # xavier(gain 2^-2.5) gate projections: tiny pre-activations
+    assert 2 * blk.tmix.gate_preactivation_bound(bound) < 20         # ... with the 2x staleness margin
     assert not blk.tmix.gates_certified(None)
     with torch.no_grad():
         blk.tmix.gk_proj[1].bias[3] = -48.0                          # logsigmoid(-48) / 16 * 64 = -192 < -80

@@ -522,3 +522,39 @@ def test_eval_under_autocast_takes_the_general_path():
             y1, _, _ = rnn.step(x[:, :1], ctx, 0, cache)
     assert torch.isfinite(y).all() and torch.isfinite(y1).all()
     _close(y, ref, 5e-2 * ref.abs().max().item(), 0.0, what="autocast eval vs fp32 eval")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cross_attention_fused_step_equals_the_op_by_op_path(dtype):
+    """BlindCrossAttention for one token: lina_cross_att_step (LayerNorm + softmax(q k^T) + weighted read, twice) against
+    the torch sequence of model/crossatt.py:105-155 (eval branch) -- outputs, both attention rows, and the pos_net state."""
+    import lina_speech_b200.model as M
+    import lina_speech_b200.model.crossatt as CA
+    torch.manual_seed(2)
+    d, B, n = 256, 3, 37
+    rnn = M.AttentiveGLA(d, 1, 4, blind=True, use_short_conv=True, pos_type="convolutional").to(DEV).to(dtype).eval()
+    ca = rnn.cross_att
+    ctx = torch.randn(B, n, d, device=DEV, dtype=dtype)
+    ys = torch.randn(B, 4, d, device=DEV, dtype=dtype)
+    res = {}
+    saved = CA.FUSED_STEP
+    try:
+        for name, flag in (("fused", True), ("torch", False)):
+            CA.FUSED_STEP = flag
+            ca.clear_memo()
+            cache = rnn.init_state(batch_size=B)
+            outs, atts = [], []
+            with torch.inference_mode():
+                for t in range(ys.shape[1]):
+                    o, a = ca(ys[:, t:t + 1], ctx, time_step=t, past_key_values=cache, use_cache=True)
+                    outs.append(o); atts.append(a)
+            res[name] = (torch.cat(outs, 1).float().cpu(), torch.cat(atts, 2).float().cpu(), cache.states[2][-1].float().cpu())
+    finally:
+        CA.FUSED_STEP = saved
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    for i, what in enumerate(("output", "attention rows", "pos_net state")):
+        a, b = res["fused"][i], res["torch"][i]
+        assert a.shape == b.shape
+        err = (a - b).abs().max().item()
+        assert err <= tol * max(1.0, b.abs().max().item()), f"{what} ({dtype}): max diff {err:.3e}"
+    assert abs(res["fused"][1].sum(-1) - 1).max() < 2e-2
