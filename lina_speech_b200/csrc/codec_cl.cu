@@ -36,14 +36,12 @@ __device__ __forceinline__ void split_store4(float4 v, const Parts &o, size_t id
 #pragma unroll
     for (int p = 0; p < MAXP; ++p) {
         if (p >= o.n) break;
-        unsigned short h[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bf16 t = __float2bfloat16_rn(a[i]);
-            h[i] = __bfloat16_as_ushort(t);
-            a[i] -= __bfloat162float(t);
-        }
-        *reinterpret_cast<uint2 *>(o.p[p] + idx) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        uint32_t w0, w1;                                 // one cvt per pair; the remainders feed the next part
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(a[1]), "f"(a[0]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(a[3]), "f"(a[2]));
+        a[0] -= __uint_as_float(w0 << 16); a[1] -= __uint_as_float(w0 & 0xFFFF0000u);
+        a[2] -= __uint_as_float(w1 << 16); a[3] -= __uint_as_float(w1 & 0xFFFF0000u);
+        *reinterpret_cast<uint2 *>(o.p[p] + idx) = make_uint2(w0, w1);
     }
 }
 
@@ -131,7 +129,11 @@ template <int VEC, int MAXJ>      // VEC 4: C % 128 == 0 (float4 per lane and st
 __global__ void __launch_bounds__(ROW_WARPS * 32, (VEC * MAXJ <= 24) ? 3 : 2)
 cl_rows_kernel(const RowArgs a) {
     __shared__ float gstat[64][2];                              // GroupNorm (mean, rstd) of this CTA's batch (G <= 64)
-    extern __shared__ float dws[];                              // depthwise taps, transposed: [7][C] (+ bias [C])
+    extern __shared__ float dyn[];
+    // dynamic shared memory: [gnA | gnB] (2C, GroupNorm folded to x * A[c] + B[c] for this CTA's batch) | [lnS | lnT] (2C) |
+    // depthwise taps transposed [7][C] + bias [C]; absent stages take no space (offsets from the host-side layout)
+    float *gnA = dyn, *lnS = dyn + (a.gn_partials != nullptr ? 2 * a.C : 0);
+    float *dws = lnS + (a.ln_scale != nullptr ? 2 * a.C : 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.C, L = a.L;
     constexpr int CTA_ROWS = ROW_WARPS * ROWS_PER_WARP;
@@ -156,6 +158,17 @@ cl_rows_kernel(const RowArgs a) {
             gstat[threadIdx.x][0] = mu;
             gstat[threadIdx.x][1] = rsqrtf(M2 / n + a.gn_eps);
         }
+        __syncthreads();
+        const int cpg = C / a.G;
+        for (int c = threadIdx.x; c < C; c += ROW_WARPS * 32) {
+            const int g = c / cpg;
+            const float A = gstat[g][1] * a.gn_w[c];
+            gnA[c] = A;
+            gnA[C + c] = a.gn_b[c] - gstat[g][0] * A;
+        }
+    }
+    if (a.ln_scale != nullptr) {
+        for (int c = threadIdx.x; c < C; c += ROW_WARPS * 32) { lnS[c] = a.ln_scale[c]; lnS[C + c] = a.ln_shift != nullptr ? a.ln_shift[c] : 0.f; }
     }
     __syncthreads();
     const int nj = C / (32 * VEC);
@@ -202,22 +215,21 @@ cl_rows_kernel(const RowArgs a) {
         }
     }
     if (a.gn_partials != nullptr) {
-        const int cpg = C / a.G;
 #pragma unroll
         for (int j = 0; j < MAXJ; ++j) {
             if (j >= nj) break;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const int c = (j * 32 + lane) * VEC + i, g = c / cpg;
-                v[j * VEC + i] = (v[j * VEC + i] - gstat[g][0]) * gstat[g][1] * a.gn_w[c] + a.gn_b[c];
+                const int c = (j * 32 + lane) * VEC + i;
+                v[j * VEC + i] = fmaf(v[j * VEC + i], gnA[c], gnA[C + c]);
             }
         }
     }
-    if (a.swish) {
+    if (a.swish) {                                     // x * sigmoid(x): ex2 + rcp on the MUFU (relative error ~1e-6)
 #pragma unroll
         for (int j = 0; j < MAXJ * VEC; ++j) {
             if (j >= nj * VEC) break;
-            v[j] = v[j] / (1.f + expf(-v[j]));
+            v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
         }
     }
     if (a.ln_scale != nullptr) {
@@ -235,7 +247,7 @@ cl_rows_kernel(const RowArgs a) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 const int c = (j * 32 + lane) * VEC + i;
-                v[j * VEC + i] = (v[j * VEC + i] - mean) * rstd * a.ln_scale[c] + (a.ln_shift != nullptr ? a.ln_shift[c] : 0.f);
+                v[j * VEC + i] = fmaf((v[j * VEC + i] - mean) * rstd, lnS[c], lnS[C + c]);
             }
         }
     }
@@ -338,7 +350,8 @@ extern "C" int lina_codec_cl_rows(const float *x, const float *dw_w, const float
     constexpr int CTA_ROWS = ROW_WARPS * ROWS_PER_WARP;
     const long long nblk = (long long)B * ((L + CTA_ROWS - 1) / CTA_ROWS);
     LINA_REQUIRE(nblk <= 2147483647LL, LINA_ERR_UNSUPPORTED, "codec_cl_rows: grid too large");
-    const size_t dsm = dw_w != nullptr ? (size_t)8 * C * sizeof(float) : 0;
+    const size_t dsm = (size_t)((gn_partials != nullptr ? 2 : 0) + (ln_scale != nullptr ? 2 : 0) + (dw_w != nullptr ? 8 : 0)) * C * sizeof(float);
+    LINA_REQUIRE(dsm <= 48 * 1024, LINA_ERR_UNSUPPORTED, "codec_cl_rows: C = %d too large for the coefficient tables", C);
     bool vec = C % 128 == 0 && al16(x) && (out_f32 == nullptr || al16(out_f32));
     for (int i = 0; i < n_parts; ++i) vec = vec && (((uintptr_t)out_parts[i] & 7u) == 0);
     if (vec && C <= 768) cl_rows_kernel<4, 6><<<(unsigned)nblk, ROW_WARPS * 32, dsm, (cudaStream_t)stream>>>(a);

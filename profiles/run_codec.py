@@ -9,7 +9,7 @@ from lina_speech_b200.codec import WavTokenizer
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 750
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-prec = sys.argv[4] if len(sys.argv) > 4 else "fp32"
+prec = sys.argv[4] if len(sys.argv) > 4 else "bf16x3"
 torch.manual_seed(0)
 wt = WavTokenizer.from_hparams().cuda().eval()
 wt.gemm_precision = prec
