@@ -378,31 +378,14 @@ typedef struct {
 } lina_gemm_args;
 int lina_gemm_bf16_terms(const lina_gemm_args *args, void *stream);
 
-/* ---------------------------------------------------------------------------------------------
- * Debug / bring-up: one-CTA tcgen05 GEMM D[128,N] = A[128,KD] * B[N,KD]^T (fp32 in, bf16 math) with the
- * operand placements of the GLA kernel (a_mode: 0 smem K-major, 1 smem MN-major, 2 TMEM; b_mode: 0 / 1).
- * `swap` exchanges the descriptor's leading/stride byte offsets.  Not part of the reference's API.
- * ------------------------------------------------------------------------------------------- */
 /* A/B switches for kernel variants (bring-up only; process-global, not thread-safe): key 0 = rows per thread of the
  * prep / short-conv tile kernel (8 or 16), key 1 = 1 selects the round-1 sliding-window short-conv kernel,
  * key 2 = bit mask of tcgen05 GLA kernel options, key 3 = 1 selects the scalar-fp32 short-conv tile kernel for bf16,
  * key 4 = 1 runs the pre-gated GLA kernel's state pass on one warpgroup, key 5 = 1 selects the round-1 short-conv backward,
- * key 6 = 1 gives the pre-gated GLA kernel three operand stages + one v stage (default 2 + 2), key 7 = 1 turns on its
- * cluster-multicast operand loads, key 8 = 2 routes lina_codec_istft_head (n_fft = 1280) back to the generic shared-memory
+ * (keys 6 / 7 selected a three-stage operand ring and cluster-multicast operand loads of the pre-gated GLA kernel: both measured
+ * slower or neutral in round 1 and no longer built), key 8 = 2 routes lina_codec_istft_head (n_fft = 1280) back to the generic shared-memory
  * FFT (default: the warp-per-frame fixed-radix kernel, csrc/fft640.cuh: 0.25 vs 0.69 ms at 32 x 750 frames). */
 int lina_debug_set_variant(int key, int value);
-int lina_debug_umma_probe(const float *A, const float *B, float *D, int N, int KD, int a_mode, int b_mode,
-                          int swap, void *stream);
-/* Round-2 bring-up (not yet run on hardware): M x N x 16 MMAs with M in {64,128}, no-swizzle K-major operands; D receives the
- * RAW accumulator tile [128 TMEM lanes][N] (cells the MMA did not write hold -12345) so the M = 64 lane mapping can be read. */
-int lina_debug_umma_probe_m(const float *A, const float *B, float *D, int M, int N, int KD, void *stream);
-/* Same with 128-byte-swizzled operands (a_mode / b_mode: 0 K-major, 1 MN-major); use_tma != 0 loads A from
- * A_bf16 [128,KD] through a 2-D tensor map with CU_TENSOR_MAP_SWIZZLE_128B instead of writing it by hand. */
-int lina_debug_umma_probe_sw128(const float *A, const float *B, float *D, const void *A_bf16, int N, int KD,
-                                int a_mode, int b_mode, int use_tma, void *stream);
-/* Cycles of `nmma` back-to-back M=128 x N x 16 bf16 MMAs issued by one thread (A from TMEM / smem K-major /
- * smem MN-major, B K-/MN-major, same or alternating accumulator): out[6] = (issue, issue+completion) x 3 reps. */
-int lina_debug_umma_timing(long long *out, int N, int a_tmem, int a_mn, int b_mn, int nmma, int same_d, void *stream);
 /* The tcgen05 GLA kernel (K = 256, bf16) with a clock64 timeline of CTA (0,0) written to
  * trace[6 roles][64 items][4 events] (int64) -- profiles/trace_gla_chunk.py prints it. */
 int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,

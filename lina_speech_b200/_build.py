@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblina_b200.so")
+DEBUG_CSRC = os.path.join(CSRC, "debug")
+DEBUG_LIB = os.path.join(LIBDIR, "liblina_b200_debug.so")     # bring-up probes (include/lina_b200_debug.h), not the product
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -34,6 +36,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "lina_b200.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "lina_b200_debug.h"))
     objs, procs = [], []
     for s in sources():
         src, obj = os.path.join(CSRC, s), os.path.join(objdir, s[:-3] + ".o")
@@ -43,17 +46,29 @@ def build(verbose: bool = False, force: bool = False) -> str:
             if verbose:
                 print(" ".join(cmd), flush=True)
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    # the bring-up probes compile into their own shared object (with their own copy of the error-string helper)
+    dbg_objs = [os.path.join(objdir, "abi.o")]
+    for s in sorted(f for f in os.listdir(DEBUG_CSRC) if f.endswith(".cu")):
+        src, obj = os.path.join(DEBUG_CSRC, s), os.path.join(objdir, "debug_" + s[:-3] + ".o")
+        dbg_objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    relink = bool(procs)
     for s, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if verbose and out.strip():
             print(out)
-    if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}")
+    for lib, lobjs in ((LIB, objs), (DEBUG_LIB, dbg_objs)):
+        if force or relink or _stale(lib, lobjs):
+            cmd = [nvcc, "-shared", "-o", lib] + lobjs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}")
     return LIB
 
 

@@ -77,13 +77,19 @@ PROTOTYPES = {
     "lina_skinny_linear": (_i, [_p, C.c_longlong, _p, C.c_longlong, _p, _p, _f, _p, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _i, _i, _i, _p]),
     "lina_codec_cl_softmax": (_i, [_p, _p, _i, C.c_longlong, _i, C.c_longlong, C.c_longlong, _p]),
     "lina_debug_set_variant": (_i, [_i, _i]),
+    "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
+    "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
+}
+
+# liblina_b200_debug.so (include/lina_b200_debug.h): bring-up probes, not part of the product library
+DEBUG_LIB_PATH = os.path.join(_HERE, "lib", "liblina_b200_debug.so")
+DEBUG_PROTOTYPES = {
     "lina_debug_umma_probe": (_i, [_p] * 3 + [_i] * 5 + [_p]),
     "lina_debug_umma_probe_m": (_i, [_p] * 3 + [_i] * 3 + [_p]),
     "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
     "lina_debug_umma_timing": (_i, [_p] + [_i] * 6 + [_p]),
-    "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
-    "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
 }
+
 
 class GemmArgs(C.Structure):
     """``lina_gemm_args`` of include/lina_b200.h (field order and types are the header's)."""
@@ -117,9 +123,28 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def check(rc: int, what: str) -> None:
+_debug_lib: Optional[C.CDLL] = None
+
+
+def debug_lib() -> C.CDLL:
+    """The bring-up probe library (tests/test_umma_probe_gpu.py, profiles/probe_m64.py, profiles/umma_timing.py)."""
+    global _debug_lib
+    if _debug_lib is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError(f"liblina_b200_debug.so not found at {DEBUG_LIB_PATH}: run __graft_entry__.build()")
+        l = C.CDLL(DEBUG_LIB_PATH)
+        for name, (res, args) in DEBUG_PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        fn = l.lina_last_error_string
+        fn.restype, fn.argtypes = C.c_char_p, []
+        _debug_lib = l
+    return _debug_lib
+
+
+def check(rc: int, what: str, l: Optional[C.CDLL] = None) -> None:
     if rc != 0:
-        msg = lib().lina_last_error_string().decode(errors="replace")
+        msg = (l or lib()).lina_last_error_string().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 

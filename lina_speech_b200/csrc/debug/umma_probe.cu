@@ -1,8 +1,8 @@
 // Single-CTA tcgen05 probe: D[128,N] = A[128,KD] * B[N,KD]^T in bf16 -> fp32, with every operand
 // placement the GLA kernel uses (smem K-major, smem MN-major, A from TMEM).  Exists to pin the
 // descriptor conventions of sm100.cuh on real hardware (tests/test_umma_probe_gpu.py).
-#include "common.cuh"
-#include "sm100.cuh"
+#include "../common.cuh"
+#include "../sm100.cuh"
 
 using namespace sm100;
 
@@ -177,7 +177,7 @@ extern "C" int lina_debug_umma_probe_m(const float *A, const float *B, float *D,
 }
 
 // ---- second probe: 128-byte-swizzled operands (K-major / MN-major) and a TMA-loaded A ----------------------
-#include "tma.cuh"
+#include "../tma.cuh"
 
 namespace {
 

@@ -11,7 +11,7 @@ for M in (128, 64):
     A[:, 0] = torch.arange(1, M + 1, device="cuda"); A[:, 1] = 1.0 / 256
     B[:, 0] = 1.0; B[:, 1] = torch.arange(N, device="cuda")
     D = torch.empty(128, N, device="cuda")
-    L.check(L.lib().lina_debug_umma_probe_m(L.ptr(A), L.ptr(B), L.ptr(D), M, N, KD, None), "probe_m")
+    L.check(L.debug_lib().lina_debug_umma_probe_m(L.ptr(A), L.ptr(B), L.ptr(D), M, N, KD, None), "probe_m")
     torch.cuda.synchronize()
     d = D.cpu()
     written = d > -12000

@@ -26,6 +26,19 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/lina_b200.h but not exported: {missing}"
 
 
+def test_debug_library_is_separate_from_the_product():
+    """the bring-up probes live in liblina_b200_debug.so / include/lina_b200_debug.h, not in the product library"""
+    from lina_speech_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "lina_b200_debug.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lina_[a-z0-9_]+)\s*\(", src)))
+    assert names == sorted(_lib.DEBUG_PROTOTYPES)
+    dbg = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(dbg, n) and not hasattr(raw, n), n
+
+
 def test_ctypes_prototypes_match_header():
     from lina_speech_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == _declared()

@@ -12,7 +12,7 @@ def _run(N, KD, a_mode, b_mode, swap):
     A = torch.randn(128, KD, device="cuda")
     B = torch.randn(N, KD, device="cuda")
     D = torch.zeros(128, N, device="cuda")
-    rc = L.lib().lina_debug_umma_probe(L.ptr(A), L.ptr(B), L.ptr(D), N, KD, a_mode, b_mode, swap, L.stream(A))
+    rc = L.debug_lib().lina_debug_umma_probe(L.ptr(A), L.ptr(B), L.ptr(D), N, KD, a_mode, b_mode, swap, L.stream(A))
     L.check(rc, "lina_debug_umma_probe")
     torch.cuda.synchronize()
     ref = A.bfloat16().float() @ B.bfloat16().float().t()
@@ -36,7 +36,7 @@ def _run_sw(N, KD, a_mode, b_mode, use_tma):
     B = torch.randn(N, KD, device="cuda")
     D = torch.zeros(128, N, device="cuda")
     Ab = A.bfloat16().contiguous()
-    rc = L.lib().lina_debug_umma_probe_sw128(L.ptr(A), L.ptr(B), L.ptr(D), L.ptr(Ab), N, KD, a_mode, b_mode, use_tma,
+    rc = L.debug_lib().lina_debug_umma_probe_sw128(L.ptr(A), L.ptr(B), L.ptr(D), L.ptr(Ab), N, KD, a_mode, b_mode, use_tma,
                                              L.stream(A))
     L.check(rc, "lina_debug_umma_probe_sw128")
     torch.cuda.synchronize()
