@@ -158,6 +158,15 @@ int lina_gla_prefill_prep_gated(const void *xq, long long ldq, const void *xk, l
 int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
                                      const void *h0, int h0_dtype, void *o, float *ht,
                                      int B, int H, int T, int K, int V, void *stream);
+/* Same with a device workspace (256-byte aligned, lina_gla_chunk_fwd_pregated_ws_bytes(); 0 = none needed).  The kernel runs
+ * (batch, head, pair of 128-wide V slices) tiles on CTA pairs; when the last wave of tiles would leave more than half of the
+ * GPU idle (512 V slices on 148 SMs: 3.46 waves), those tiles are cut in two along T -- the first halves run first, leave
+ * their fp32 state slice in the workspace, the second halves run last -- the role FLA/fla/ops/common/chunk_h.py:15-98 gives NT
+ * in its grid.  Results are bit-identical to the call without workspace. */
+size_t lina_gla_chunk_fwd_pregated_ws_bytes(int B, int H, int T, int K, int V);
+int lina_gla_chunk_fwd_pregated_bthd_ws(const void *qg, const void *kg, const void *v, const float *decay,
+                                        const void *h0, int h0_dtype, void *o, float *ht, void *ws, size_t ws_bytes,
+                                        int B, int H, int T, int K, int V, void *stream);
 
 /* General form of the same kernel: [B,H,T,D] (bthd = 0) or [B,T,H,D] (bthd = 1) operands; row_decay != 0: `decay` is
  * [B,H,NT,V] and scales the VALUE dim of the state, out_f32 != 0: o is fp32 (only (0,0) and (1,1) are instantiated).

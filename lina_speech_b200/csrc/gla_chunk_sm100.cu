@@ -78,8 +78,8 @@ template <int K> struct Cfg {
     static_assert(OFF_G % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 
-enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_QK_EMPTY2, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_EMPTY,
-       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_RAW_FULL0, B_RAW_FULL1, B_RAW_FULL2, B_G_EMPTY0, B_G_EMPTY1, B_V_FULL0, B_V_FULL1,
+enum { B_QK_FULL0 = 0, B_QK_FULL1, B_QK_EMPTY0, B_QK_EMPTY1, B_P_FULL, B_P_TEMPTY, B_PS_FULL, B_PS_FULL1, B_PS_EMPTY, B_PS_EMPTY1,
+       B_O_FULL, B_O_EMPTY, B_ST_FULL, B_RAW_FULL0, B_RAW_FULL1, B_G_EMPTY0, B_G_EMPTY1, B_V_FULL0, B_V_FULL1,
        B_V_EMPTY0, B_V_EMPTY1, B_SA_BLK0 /* .. B_SA_BLK0 + K/32 - 1: one per 32-column block of the state */, B_COUNT = B_SA_BLK0 + 8 };
 static_assert(B_COUNT <= 32, "mbarrier slots");
 
@@ -107,6 +107,13 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
 
 struct TMaps { CUtensorMap q, k, g, v; };
 
+// Work list of the PAIR variant (OPT bit 8).  The grid is 1-D, two CTAs (one cluster) per entry.  `U` tiles = (batch, head) x
+// pairs of V slices; entry ci < rem: FIRST part (items [0, n_split)) of tile ci; rem <= ci < U: all of tile ci; ci >= U: SECOND
+// part of tile ci - U.  A first part leaves its state slice in hx[(tile * 2 + rank)][K][128] (fp32) and raises flags[tile * 2 + rank];
+// the second part starts from it.  Blocks are dispatched in index order, so a first part has long finished when the second
+// part of the same tile (U entries later) starts: the cut tiles fill what would be a quarter-empty last wave.
+struct SplitArgs { float *hx; uint32_t *flags; int rem, n_split, U, nvp; };
+
 // OPT bit 1: the gate pre-pass keeps its gk rows in registers between the column-sum pass and the rescale pass
 //            (8 fewer 16-byte shared loads per thread and item).
 // OPT bit 2 (PRE): the operands arrive PRE-GATED -- tm.q / tm.k map q~ = scale q e^G and k~ = k e^-G (written by
@@ -116,7 +123,7 @@ template <int K, int OPT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restrict__ h0, int h0_dtype,
                            bf16 *__restrict__ o, float *__restrict__ ht, int T, int V, int H, int bthd, float scale,
-                           long long *__restrict__ trace, const float *__restrict__ decay) {
+                           long long *__restrict__ trace, const float *__restrict__ decay, const SplitArgs sp) {
     constexpr bool PRE = (OPT & 4) != 0;
     // OPT bit 3 (ROW, with PRE): the chunk decay scales the VALUE dim (rows of the transposed state = TMEM lanes) instead of
     //            the key dim: decay is [B,H,NT,V].  This is the form the backward needs (contraction over V, state S^T).
@@ -128,24 +135,28 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     //            next item starts on block 0 while the later blocks are still being rescaled.
     constexpr bool STATE2 = (OPT & 32) != 0;
     static_assert(!STATE2 || PRE, "the extra state-pass warpgroups are the pre-pass warps");
-    // OPT bit 6 (CL, with PRE): the V/128 CTAs of one (batch, head) form a thread-block CLUSTER and share the q~ / k~ loads:
-    //            each CTA fetches 1/csize of the 64x64 boxes of a stage and TMA multicasts them into every CTA's operand
-    //            tiles (L2 -> SM traffic of the kernel 2.4 GB -> 0.9 GB at the bench shape; it was the binding resource once
-    //            MMA issue was fixed).  A stage is reloaded only when ALL CTAs have released it (multicast tcgen05.commit).
-    constexpr bool CL = (OPT & 64) != 0;
-    static_assert(!CL || PRE, "cluster multicast is implemented for pre-gated operands");
+    // (OPT bits 6 / 7 were a cluster-multicast operand load and a three-stage operand ring: measured neutral / slower in round 1
+    //  -- DESIGN 4.1b -- and removed.)
+    // OPT bit 8 (PAIR, with PRE | STATE2): two CTAs holding neighbouring V slices of one (batch, head) form a CLUSTER and share the
+    //            score MMA: P = q~ k~^T does not depend on the V slice, so CTA r computes it for the items n with n % 2 == r, masks
+    //            it, and delivers the bf16 tile to both CTAs (own shared memory + one 8 KB DSMEM bulk copy that completes on the
+    //            peer's mbarrier).  Per item the tensor pipe of a CTA then runs 16 + 4 + 4 (+ 16 every other item) MMAs instead
+    //            of 40.  Issue order per item: (1) OT = SA q~^T, (3) ST += v^T k~, (2) OT += v^T P^T, (0) of the NEXT item when it
+    //            is this CTA's -- the state pass (the serial chain of the kernel) starts as early as possible and (2), (0) run
+    //            under it.  The grid is a work list (SplitArgs) so that tiles can be cut in two along T.
+    constexpr bool PAIR = (OPT & 256) != 0;
+    static_assert(!PAIR || (PRE && (OPT & 32) != 0 && (OPT & (8 | 16)) == 0), "PAIR builds on the pre-gated, three-warpgroup variant");
     constexpr int NB = K / 32;
     constexpr int NG = STATE2 ? (NB >= 3 ? 3 : NB) : 1;
     static_assert(!ROW || PRE, "row decay needs pre-gated operands");
     using cfg = Cfg<K>;
-    // With pre-gated operands the gk side tiles (2 * G_BYTES = QK_BYTES) are unused: they hold EITHER a second v stage (default)
-    // OR a third q~/k~ stage (QK3, OPT bit 7).  Measured at the bench shape in one process: 2+2 stages 0.264 ms, 3+1 stages
-    // 0.295 ms, 2+2 with cluster multicast 0.276 ms -- after the issue-loop fix the kernel is bound by the tensor pipe fed
-    // from shared memory (~2780 of ~3200 cycles per item: SS MMAs run at ~75 B/clk of operand reads), not by loads.
-    constexpr bool QK3 = (OPT & 128) != 0;        // OPT bit 7
-    constexpr int NS = (PRE && QK3) ? 3 : 2;
-    constexpr bool V2 = PRE && !QK3;
-    static_assert(2 * cfg::G_BYTES == cfg::QK_BYTES, "third stage lives in the gk tiles");
+    // With pre-gated operands the gk side tiles (2 * G_BYTES = QK_BYTES) are unused: they hold a second v stage (16 KB) and, with
+    // PAIR, the second P tile (8 KB).
+    constexpr int NS = 2;
+    constexpr bool V2 = PRE;
+    constexpr uint32_t OFF_P1 = cfg::OFF_G + VT_BYTES;            // PAIR: P tile of the odd items
+    static_assert(!V2 || 2 * cfg::G_BYTES >= VT_BYTES, "the second v stage lives in the gk tiles");
+    static_assert(!PAIR || 2 * cfg::G_BYTES >= VT_BYTES + PT_BYTES, "second v stage + second P tile live in the gk tiles");
     constexpr uint32_t V_STAGE1 = V2 ? cfg::OFF_G : cfg::OFF_V;
     constexpr int KC = cfg::KC, KB = cfg::KB, NRG = cfg::NRG, RPG = cfg::RPG;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,10 +166,20 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     float *part = reinterpret_cast<float *>(smem + cfg::OFF_PART);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bh = blockIdx.y, v0 = blockIdx.x * BV;
-    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
-    const int n_items = (T + C - 1) / C;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const int n_total = (T + C - 1) / C;
+    int bh = blockIdx.y, v0 = blockIdx.x * BV, n_begin = 0, n_items = n_total, piece = 0, hx_slot = 0;
+    if (PAIR) {
+        const int ci = blockIdx.x >> 1;
+        int tile = ci;
+        if (ci < sp.rem) piece = 1;
+        else if (ci >= sp.U) { tile = ci - sp.U; piece = 2; }
+        bh = tile / sp.nvp;
+        v0 = ((tile - bh * sp.nvp) * 2 + (int)crank) * BV;
+        if (piece == 1) n_items = sp.n_split;
+        else if (piece == 2) { n_begin = sp.n_split; n_items = n_total - sp.n_split; }
+        hx_slot = tile * 2 + (int)crank;
+    }
     const int bb = bh / H, hh = bh - bb * H;
     // o is [B,H,T,V] (bthd == 0) or [B,T,H,V] (bthd == 1)
     const size_t obase = bthd ? ((size_t)bb * T * H + hh) * V : (size_t)bh * T * V;
@@ -167,13 +188,20 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) { printf("gla_chunk_sm100: dynamic smem base not 1024-byte aligned\n"); __trap(); }
         mbar_init(&bars[B_QK_FULL0], NPREP); mbar_init(&bars[B_QK_FULL1], NPREP);
-        mbar_init(&bars[B_QK_EMPTY0], csize); mbar_init(&bars[B_QK_EMPTY1], csize); mbar_init(&bars[B_QK_EMPTY2], csize);
+        mbar_init(&bars[B_QK_EMPTY0], 1); mbar_init(&bars[B_QK_EMPTY1], 1);
         mbar_init(&bars[B_P_FULL], 1); mbar_init(&bars[B_P_TEMPTY], 64);
-        mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
+        if (PAIR) {
+            // P tile j is written by CTA j: 64 mask threads arrive at home, one expect_tx arrive + 8 KB of bulk copy at the peer;
+            // it is free again when the (2) MMAs of BOTH CTAs have read it (multicast tcgen05.commit: 2 arrivals)
+            mbar_init(&bars[B_PS_FULL], crank == 0 ? 64 : 1); mbar_init(&bars[B_PS_FULL1], crank == 1 ? 64 : 1);
+            mbar_init(&bars[B_PS_EMPTY], 2); mbar_init(&bars[B_PS_EMPTY1], 2);
+        } else {
+            mbar_init(&bars[B_PS_FULL], 64); mbar_init(&bars[B_PS_EMPTY], 1);
+        }
         mbar_init(&bars[B_O_FULL], 1); mbar_init(&bars[B_O_EMPTY], 128);
         mbar_init(&bars[B_ST_FULL], 1);
         for (int b = 0; b < NB; ++b) mbar_init(&bars[B_SA_BLK0 + b], 128);
-        mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1); mbar_init(&bars[B_RAW_FULL2], 1);
+        mbar_init(&bars[B_RAW_FULL0], 1); mbar_init(&bars[B_RAW_FULL1], 1);
         mbar_init(&bars[B_G_EMPTY0], NPREP); mbar_init(&bars[B_G_EMPTY1], NPREP);
         mbar_init(&bars[B_V_FULL0], 1); mbar_init(&bars[B_V_EMPTY0], 1);
         mbar_init(&bars[B_V_FULL1], 1); mbar_init(&bars[B_V_EMPTY1], 1);
@@ -182,11 +210,11 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
-    if (CL) cluster_sync_all();          // every CTA's mbarriers are initialised before any peer multicasts into them
+    if (PAIR) cluster_sync_all();        // both CTAs' mbarriers are initialised before the peer signals them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    auto qk_stage_off = [](int st) -> uint32_t { return st < 2 ? cfg::OFF_QK + st * cfg::QK_BYTES : cfg::OFF_G; };
+    auto qk_stage_off = [](int st) -> uint32_t { return cfg::OFF_QK + st * cfg::QK_BYTES; };
     // chunk-decay ring: NS + 1 slots (the loader runs NS items ahead of the state pass); the 4th lives in the unused `part`
     auto dvec_slot = [&](int n) -> float * { const int sl = n % (NS + 1); return sl < 3 ? dvec + sl * K : part; };
     int sg = -1;                                   // state-pass group of this warp
@@ -286,7 +314,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             while (nq < n_items || nv < n_items) {
                 bool progressed = false;
                 if (nq < n_items) {
-                    const int n = nq, s = n % NS, u = n / NS, t0 = n * C;
+                    const int n = nq, s = n % NS, u = n / NS, t0 = (n_begin + n) * C;
                     if (mbar_try_wait(&bars[B_QK_EMPTY0 + s], (u & 1) ^ 1) &&
                         (PRE || mbar_try_wait(&bars[B_G_EMPTY0 + s], (u & 1) ^ 1))) {
                         const uint32_t qk_tile = smem_u32(smem + qk_stage_off(s));
@@ -294,24 +322,13 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                         TRACE(1, n, 0);
                         mbar_expect_tx(&bars[B_RAW_FULL0 + s], PRE ? (2u * K * C * 2u + (ROW ? 0u : K * 4u)) : cfg::RAW_TX);
                         if (PRE && !ROW)   // chunk-decay ring slot <- decay[b, h, n, :]
-                            tma_load_1d(smem_u32(dvec_slot(n)), decay + ((size_t)bh * n_items + n) * K, K * 4u,
+                            tma_load_1d(smem_u32(dvec_slot(n)), decay + ((size_t)bh * n_total + n_begin + n) * K, K * 4u,
                                         &bars[B_RAW_FULL0 + s]);
-                        if (CL) {
-                            // box i of the stage (q~ boxes then k~ boxes) is fetched by CTA i % csize and multicast to the cluster
 #pragma unroll
-                            for (int i = 0; i < 2 * KB; ++i) {
-                                if ((uint32_t)i % csize != crank) continue;
-                                const int kb = i < KB ? i : i - KB;
-                                tma_load_4d_mc(qk_tile + kb * cfg::QK_BLK + (i < KB ? 0 : 8192), i < KB ? &tm.q : &tm.k, kb * 64, t0,
-                                               hh, bb, &bars[B_RAW_FULL0 + s], cmask);
-                            }
-                        } else {
-#pragma unroll
-                            for (int kb = 0; kb < KB; ++kb) {
-                                if (!PRE) tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
-                                tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
-                                tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
-                            }
+                        for (int kb = 0; kb < KB; ++kb) {
+                            if (!PRE) tma_load_4d(g_tile + kb * cfg::G_BLK, &tm.g, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                            tma_load_4d(qk_tile + kb * cfg::QK_BLK, &tm.q, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
+                            tma_load_4d(qk_tile + kb * cfg::QK_BLK + 8192, &tm.k, kb * 64, t0, hh, bb, &bars[B_RAW_FULL0 + s]);
                         }
                         TRACE(1, n, 1);
                         ++nq;
@@ -319,7 +336,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     }
                 }
                 if (nv < n_items) {
-                    const int n = nv, t0 = n * C;
+                    const int n = nv, t0 = (n_begin + n) * C;
                     const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;         // v stage and its use count
                     if (mbar_try_wait(&bars[B_V_EMPTY0 + sv], (uv & 1) ^ 1)) {
                         mbar_expect_tx(&bars[B_V_FULL0 + sv], VT_BYTES);
@@ -352,18 +369,81 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             // instruction cost ~10 dependent uniform-datapath ops per MMA, and the single issuing thread is the kernel's
             // critical resource (40 MMAs per 64-token item).
             const uint32_t qk0 = smem_u32(smem + cfg::OFF_QK);
-            const uint32_t qk1 = qk0 + cfg::QK_BYTES, qk2 = smem_u32(smem + cfg::OFF_G);
-            const uint64_t d_q0 = smem_desc_sw128(qk0, 0, 1024), d_q1 = smem_desc_sw128(qk1, 0, 1024), d_q2 = smem_desc_sw128(qk2, 0, 1024);
-            const uint64_t d_k0 = smem_desc_sw128(qk0 + 8192, 0, 1024), d_k1 = smem_desc_sw128(qk1 + 8192, 0, 1024),
-                           d_k2 = smem_desc_sw128(qk2 + 8192, 0, 1024);
-            const uint64_t d_k30 = smem_desc_sw128(qk0 + 8192, cfg::QK_BLK, 1024), d_k31 = smem_desc_sw128(qk1 + 8192, cfg::QK_BLK, 1024),
-                           d_k32 = smem_desc_sw128(qk2 + 8192, cfg::QK_BLK, 1024);
+            const uint32_t qk1 = qk0 + cfg::QK_BYTES;
+            const uint64_t d_q0 = smem_desc_sw128(qk0, 0, 1024), d_q1 = smem_desc_sw128(qk1, 0, 1024);
+            const uint64_t d_k0 = smem_desc_sw128(qk0 + 8192, 0, 1024), d_k1 = smem_desc_sw128(qk1 + 8192, 0, 1024);
+            const uint64_t d_k30 = smem_desc_sw128(qk0 + 8192, cfg::QK_BLK, 1024), d_k31 = smem_desc_sw128(qk1 + 8192, cfg::QK_BLK, 1024);
             const uint64_t d_v0 = smem_desc_sw128(v_tile, 8192, 1024), d_v1 = smem_desc_sw128(smem_u32(smem + V_STAGE1), 8192, 1024);
-            const uint64_t d_p = smem_desc_sw128(p_tile, 0, 1024);
+            const uint64_t d_p = smem_desc_sw128(p_tile, 0, 1024), d_p1 = smem_desc_sw128(smem_u32(smem + OFF_P1), 0, 1024);
+            if (PAIR) {
+                // (0) of item m (one of this CTA's): P = [q~;k~] k~^T into the CTA's own tensor-memory tile
+                auto issue_scores = [&](int m) {
+                    const int s = m & 1;
+                    const uint64_t dq = s ? d_q1 : d_q0, dk = s ? d_k1 : d_k0;
+                    wait_bar(&bars[B_RAW_FULL0 + s], (m >> 1) & 1);
+                    wait_bar(&bars[B_P_TEMPTY], ((m >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    TRACE(2, m, 0);
+#pragma unroll
+                    for (int ks = 0; ks < K / 16; ++ks) {
+                        const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
+                        mma_ss(tmem + COL_P, dq + off, dk + off, id_p, ks > 0);
+                    }
+                    mma_commit(&bars[B_P_FULL]);
+                };
+                if (crank == 0) issue_scores(0);
+                for (int n = 0; n < n_items; ++n) {
+                    const int s = n & 1, u = n >> 1, pb = n & 1;
+                    const uint64_t dq = s ? d_q1 : d_q0, dk3 = s ? d_k31 : d_k30, d_v = s ? d_v1 : d_v0;
+                    if ((uint32_t)pb != crank) mbar_expect_tx(&bars[B_PS_FULL + pb], PT_BYTES);   // the peer's bulk copy of P_n lands here
+                    wait_bar(&bars[B_RAW_FULL0 + s], u & 1);
+                    wait_bar(&bars[B_O_EMPTY], (n & 1) ^ 1);
+                    TRACE(0, n, 0);
+                    // (1) OT = SA q~^T   (A from TMEM), two k-steps per 32-column block of the state as the blocks become ready
+#pragma unroll
+                    for (int cb = 0; cb < NB; ++cb) {
+                        wait_bar(&bars[B_SA_BLK0 + cb], n & 1);
+                        tc_fence_after();
+                        if (cb == 0) TRACE(2, n, 1);
+#pragma unroll
+                        for (int ks = 2 * cb; ks < 2 * cb + 2; ++ks) {
+                            const uint64_t off = (uint64_t)(((ks >> 2) * cfg::QK_BLK + (ks & 3) * 32) >> 4);
+                            mma_ts(tmem + COL_OT, tmem + COL_SA + ks * 8, dq + off, id_p, ks > 0);
+                        }
+                    }
+                    TRACE(0, n, 1);
+                    wait_bar(&bars[B_V_FULL0 + s], u & 1);
+                    tc_fence_after();
+                    TRACE(0, n, 2);
+                    // (3) ST += v^T k~
+#pragma unroll
+                    for (int ks = 0; ks < C / 16; ++ks)
+                        mma_ss(tmem + COL_ST, d_v + (uint64_t)(ks * 128), dk3 + (uint64_t)(ks * 128), id_s, 1);
+                    mma_commit(&bars[B_ST_FULL]);
+                    mma_commit(&bars[B_QK_EMPTY0 + s]);           // q~_n, k~_n are done with: (0)_n, (1)_n, (3)_n
+                    const bool next_mine = n + 1 < n_items && (uint32_t)((n + 1) & 1) == crank;
+                    TRACE(0, n, 3);
+                    wait_bar(&bars[B_PS_FULL + pb], u & 1);
+                    fence_proxy_async_smem();
+                    tc_fence_after();
+                    TRACE(2, n, 2);
+                    // (2) OT += v^T P^T
+                    const uint64_t dp = pb ? d_p1 : d_p;
+#pragma unroll
+                    for (int ks = 0; ks < C / 16; ++ks)
+                        mma_ss(tmem + COL_OT, d_v + (uint64_t)(ks * 128), dp + (uint64_t)(ks * 2), id_o, 1);
+                    mma_commit(&bars[B_O_FULL]);
+                    mma_commit_mc(&bars[B_PS_EMPTY + pb], (uint16_t)3);
+                    mma_commit(&bars[B_V_EMPTY0 + s]);
+                    // (0) of the next item, if it is ours: runs under the state pass of this one
+                    if (next_mine) issue_scores(n + 1);
+                    TRACE(2, n, 3);
+                }
+            } else {
             for (int n = 0; n < n_items; ++n) {
                 const int s = n % NS, u = n / NS;
-                const uint64_t dq = s == 0 ? d_q0 : (s == 1 ? d_q1 : d_q2), dk = s == 0 ? d_k0 : (s == 1 ? d_k1 : d_k2);
-                const uint64_t dk3 = s == 0 ? d_k30 : (s == 1 ? d_k31 : d_k32);
+                const uint64_t dq = s == 0 ? d_q0 : d_q1, dk = s == 0 ? d_k0 : d_k1;
+                const uint64_t dk3 = s == 0 ? d_k30 : d_k31;
                 const int sv = V2 ? (n & 1) : 0, uv = V2 ? (n >> 1) : n;
                 const uint64_t d_v = sv ? d_v1 : d_v0;
                 wait_bar(&bars[(PRE ? B_RAW_FULL0 : B_QK_FULL0) + s], u & 1);
@@ -405,10 +485,10 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                 for (int ks = 0; ks < C / 16; ++ks)
                     mma_ss(tmem + COL_ST, d_v + (uint64_t)(ks * 128), dk3 + (uint64_t)(ks * 128), id_s, 1);
                 mma_commit(&bars[B_ST_FULL]);
-                if (CL) mma_commit_mc(&bars[B_QK_EMPTY0 + s], cmask);
-                else mma_commit(&bars[B_QK_EMPTY0 + s]);
+                mma_commit(&bars[B_QK_EMPTY0 + s]);
                 mma_commit(&bars[B_V_EMPTY0 + sv]);
                 TRACE(2, n, 3);
+            }
             }
         }
         __syncwarp();
@@ -416,7 +496,43 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         // ====================== warps 16,17: causal mask of P (rows t = TMEM lanes 0..63) ======================
         const int qd = warp - 16, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        uint8_t *p_tile = smem + cfg::OFF_P;
+        uint8_t *p_tile = smem + (PAIR && crank == 1 ? OFF_P1 : cfg::OFF_P);
+        if (PAIR) {
+            // this CTA's items m = crank, crank + 2, ...: mask P_m and deliver it to both CTAs of the pair
+            const uint32_t peer = crank ^ 1u;
+            const uint32_t p_remote = mapa_shared(smem_u32(p_tile), peer);
+            const uint32_t bar_remote = mapa_shared(smem_u32(&bars[B_PS_FULL + crank]), peer);
+            for (int m = (int)crank; m < n_items; m += 2) {
+                const int j = m >> 1;
+                wait_bar(&bars[B_P_FULL], j & 1);
+                tc_fence_after();
+                if (r == 0) TRACE(3, m, 0);
+                uint32_t pr[2][32];
+                tmem_ld32(tmem + lane_addr + COL_P, pr[0]);
+                tmem_ld32(tmem + lane_addr + COL_P + 32, pr[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_P_TEMPTY]);
+                wait_bar(&bars[B_PS_EMPTY + crank], (j & 1) ^ 1);      // (2) of item m - 2 has read this tile in BOTH CTAs
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int s0 = g * 8 + 2 * jj;
+                        const float a = s0 <= r ? __uint_as_float(pr[s0 >> 5][s0 & 31]) : 0.f;
+                        const float b = s0 + 1 <= r ? __uint_as_float(pr[(s0 + 1) >> 5][(s0 + 1) & 31]) : 0.f;
+                        w[jj] = pack_bf16(a, b);
+                    }
+                    *reinterpret_cast<uint4 *>(p_tile + sw128_off(r, g)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async_smem();
+                named_sync(2, 64);                                     // all 64 rows written and fenced
+                if (r == 0) dsmem_bulk_copy(p_remote, smem_u32(p_tile), PT_BYTES, bar_remote);
+                mbar_arrive(&bars[B_PS_FULL + crank]);
+                if (r == 0) TRACE(3, m, 1);
+            }
+        } else
         for (int n = 0; n < n_items; ++n) {
             wait_bar(&bars[B_P_FULL], n & 1);
             tc_fence_after();
@@ -450,7 +566,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         const int qd = warp - 8, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         for (int n = 0; n < n_items; ++n) {
-            const int t0 = n * C;
+            const int t0 = (n_begin + n) * C;
             wait_bar(&bars[B_O_FULL], n & 1);
             tc_fence_after();
             if (r == 0) TRACE(4, n, 0);
@@ -486,13 +602,23 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
         const int qd = warp & 3, r = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         const size_t sbase = (size_t)bh * K * V + v0 + r;          // + kappa * V
+        float *hx = PAIR && piece != 0 ? sp.hx + (size_t)hx_slot * K * BV + r : nullptr;      // + kappa * BV
+        if (PAIR && piece == 2) {
+            // second part of a cut tile: the first part (dispatched U work-list entries earlier) has published its state
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(sp.flags + hx_slot) == 0u) {
+                if (clock64() - t0 > 4000000000LL) { printf("gla_chunk_sm100: state hand-off timeout (block %d)\n", blockIdx.x); __trap(); }
+            }
+        }
         // initial state -> ST (fp32) and SA (bf16)
 #pragma unroll 1
         for (int cb = sg; cb < NB; cb += NG) {
             uint32_t f[32], pk[16];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float x = h0 != nullptr ? load_dyn(h0, h0_dtype, sbase + (size_t)(cb * 32 + j) * V) : 0.f;
+                float x;
+                if (PAIR && piece == 2) x = hx[(size_t)(cb * 32 + j) * BV];
+                else x = h0 != nullptr ? load_dyn(h0, h0_dtype, sbase + (size_t)(cb * 32 + j) * V) : 0.f;
                 f[j] = __float_as_uint(x);
             }
 #pragma unroll
@@ -512,7 +638,7 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
             const float *dv = dvec_slot(n);
             const bool last = n == n_items - 1;
             float rd = 1.f;
-            if (ROW) rd = decay[((size_t)bh * n_items + n) * V + v0 + r];
+            if (ROW) rd = decay[((size_t)bh * n_total + n_begin + n) * V + v0 + r];
 #pragma unroll 1
             for (int cb = sg; cb < NB; cb += NG) {
                 uint32_t f[32], pk[16];
@@ -534,24 +660,52 @@ gla_chunk_fwd_sm100_kernel(const __grid_constant__ TMaps tm, const void *__restr
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&bars[B_SA_BLK0 + cb]);        // this block of SA / ST is final for the next item
+                } else if (PAIR && piece == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hx[(size_t)(cb * 32 + j) * BV] = __uint_as_float(f[j]);
                 } else if (ht != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) ht[sbase + (size_t)(cb * 32 + j) * V] = __uint_as_float(f[j]);
                 }
             }
             if (r == 0 && sg == 0) TRACE(5, n, 1);
+            if (r == 0 && sg == 1) TRACE(5, n, 2);
+            if (r == 0 && sg == 2) TRACE(5, n, 3);
         }
+        if (PAIR && piece == 1) __threadfence();
     }
     tc_fence_before();
     __syncthreads();
-    if (CL) cluster_sync_all();          // no CTA leaves while a peer may still arrive on its barriers
+    if (PAIR && piece == 1 && tid == 0) st_release_gpu(sp.flags + hx_slot, 1u);
+    if (PAIR) cluster_sync_all();        // no CTA leaves while the peer may still signal its barriers
     if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// How many tiles (CTA pairs) of the PAIR variant are cut in two, and the workspace that takes: with `slots` = SMs / 2 pairs
+// resident at a time, U tiles run in U / slots full waves plus a last wave of U % slots; when that last wave is at most half
+// full (and there is a full wave before it, and T has at least 4 chunks), its tiles are split and the halves fill it.
+struct SplitPlan { int rem; size_t flag_bytes, bytes; };
+static SplitPlan split_plan(int B, int H, int T, int V) {
+    SplitPlan p = {0, 0, 0};
+    static thread_local int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    const int slots = sms / 2, U = B * H * (V / BV / 2), n_total = (T + C - 1) / C;
+    if (slots <= 0 || (V / BV) % 2 != 0) return p;
+    const int rem = U % slots;
+    if (U < slots || rem == 0 || 2 * rem > slots || n_total < 4) return p;
+    p.rem = rem;
+    p.flag_bytes = (((size_t)rem * 2 * sizeof(uint32_t)) + 255) / 256 * 256;
+    p.bytes = p.flag_bytes + (size_t)rem * 2 * 256 * BV * sizeof(float);       // K <= 256
+    return p;
 }
 
 template <int K, int OPT = 0>
 int launch(const void *q, const void *k, const void *v, const void *gk, const void *h0, int h0_dtype, void *o,
            float *ht, int B, int H, int T, int V, int bthd, float scale, cudaStream_t st, long long *trace = nullptr,
-           const float *decay = nullptr, int ldq = 0, int ldk = 0, int ldv = 0) {
+           const float *decay = nullptr, int ldq = 0, int ldk = 0, int ldv = 0, void *ws = nullptr, size_t ws_bytes = 0) {
     using cfg = Cfg<K>;
     static thread_local uint64_t configured = 0;
     if (lina_first_use_on_device(&configured))
@@ -590,20 +744,33 @@ int launch(const void *q, const void *k, const void *v, const void *gk, const vo
         }
     }
     dim3 grid(V / BV, B * H);
-    if ((OPT & 64) != 0) {               // the V/128 CTAs of a (batch, head) are one cluster
+    SplitArgs sp = {nullptr, nullptr, 0, 0, 0, 0};
+    if ((OPT & 256) != 0) {
+        // work list of CTA pairs (see SplitArgs): full tiles, plus `rem` tiles cut in two along T when that fills the last wave
+        const int n_total = (T + C - 1) / C;
+        sp.nvp = V / BV / 2;
+        sp.U = B * H * sp.nvp;
+        const SplitPlan pl = split_plan(B, H, T, V);
+        if (ws != nullptr && ws_bytes >= pl.bytes && pl.rem > 0) {
+            sp.rem = pl.rem;
+            sp.n_split = (n_total + 1) / 2;
+            sp.flags = reinterpret_cast<uint32_t *>(ws);
+            sp.hx = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(ws) + pl.flag_bytes);
+            LINA_CUDA_OK(cudaMemsetAsync(sp.flags, 0, pl.flag_bytes, st));
+        }
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = grid; lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = st;
+        lc.gridDim = dim3(2 * (sp.U + sp.rem)); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = V / BV; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
         bf16 *op = (bf16 *)o;
         LINA_CUDA_OK(cudaLaunchKernelEx(&lc, gla_chunk_fwd_sm100_kernel<K, OPT>, tm, h0, h0_dtype, op, ht, T, V, H, bthd, scale,
-                                        trace, decay));
+                                        trace, decay, sp));
         return LINA_OK;
     }
     gla_chunk_fwd_sm100_kernel<K, OPT><<<grid, NTHREADS, cfg::SMEM, st>>>(tm, h0, h0_dtype, (bf16 *)o, ht, T, V, H, bthd, scale,
-                                                                        trace, decay);
+                                                                        trace, decay, sp);
     LINA_LAUNCH_OK("gla_chunk_fwd_sm100_kernel");
     return LINA_OK;
 }
@@ -631,8 +798,6 @@ static int chunk_fwd_tc(const void *q, const void *k, const void *v, const void 
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 64) return launch<64>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
     if (K == 128) return launch<128>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
-    if (g_lina_variant[2] & 2)             // A/B: the gate pre-pass keeps its gk rows in registers (neutral, not default)
-        return launch<256, 2>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
     return launch<256, 0>(q, k, v, gk, h0, h0_dtype, o, ht, B, H, T, V, bthd, scale, st);
 }
 
@@ -657,25 +822,24 @@ extern "C" int lina_gla_chunk_fwd_bthd(const void *q, const void *k, const void 
 
 // Pre-gated operands (see OPT bit 2 of the kernel): qg = scale q e^G, kg = k e^-G [B,T,H,K] bf16, decay [B,H,NT,K] fp32
 // with NT = ceil(T / 64), as written by lina_gla_prefill_prep_gated; v, o [B,T,H,V]; h0 / ht [B,H,K,V].
-extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
-                                                const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T,
-                                                int K, int V, void *stream) {
+// Default kernel: CTA pairs sharing the score MMA (PAIR) when V / 128 is even and K >= 128; with a workspace of
+// lina_gla_chunk_fwd_pregated_ws_bytes() the tiles of a less-than-half-full last wave are cut in two along T.
+// A/B (lina_debug_set_variant): key 9 = 1 selects the round-1 one-CTA-per-tile kernel (2 = pairs without the T cut), key 4 = 1 the
+// one-state-warpgroup form of the round-1 kernel.
+static int pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay, const void *h0, int h0_dtype, void *o,
+                         float *ht, void *ws, size_t ws_bytes, int B, int H, int T, int K, int V, void *stream) {
     LINA_REQUIRE(qg && kg && v && decay && o, LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: null tensor pointer");
     LINA_REQUIRE(h0 == nullptr || lina_dtype_ok(h0_dtype), LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: bad h0 dtype");
     LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16), LINA_ERR_UNSUPPORTED,
                  "gla_chunk_fwd_pregated: outside the tensor-core envelope (K in {64,128,256}, V %% 128 == 0, T >= 32)");
     LINA_REQUIRE(((uintptr_t)decay & 15u) == 0, LINA_ERR_UNSUPPORTED, "gla_chunk_fwd_pregated: decay must be 16-byte aligned");
+    LINA_REQUIRE(ws == nullptr || ((uintptr_t)ws & 255u) == 0, LINA_ERR_BAD_ARG, "gla_chunk_fwd_pregated: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int nvs = V / BV;
-    if (g_lina_variant[4] == 0 && g_lina_variant[7] == 1 && (nvs == 2 || nvs == 4 || nvs == 8)) {   // A/B: + cluster multicast
-        if (K == 64) return launch<64, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
-        if (K == 128) return launch<128, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
-        return launch<256, 100>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
-    }
-    if (g_lina_variant[4] == 0 && g_lina_variant[6] == 1) {   // A/B: three q~/k~ stages + one v stage (default: two + two)
-        if (K == 64) return launch<64, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
-        if (K == 128) return launch<128, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
-        return launch<256, 164>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+    if (g_lina_variant[4] == 0 && g_lina_variant[9] != 1 && nvs % 2 == 0 && K >= 128) {
+        if (g_lina_variant[9] == 2) ws = nullptr;                // A/B: pairs without the T cut
+        if (K == 128) return launch<128, 292>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay, 0, 0, 0, ws, ws_bytes);
+        return launch<256, 292>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay, 0, 0, 0, ws, ws_bytes);
     }
     if (g_lina_variant[4] == 0) {            // three warpgroups share the state pass (variant 4 = 1: one warpgroup)
         if (K == 64) return launch<64, 36>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
@@ -685,6 +849,23 @@ extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, 
     if (K == 64) return launch<64, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     if (K == 128) return launch<128, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
     return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, 1, 1.f, st, nullptr, decay);
+}
+
+extern "C" int lina_gla_chunk_fwd_pregated_bthd(const void *qg, const void *kg, const void *v, const float *decay,
+                                                const void *h0, int h0_dtype, void *o, float *ht, int B, int H, int T,
+                                                int K, int V, void *stream) {
+    return pregated_bthd(qg, kg, v, decay, h0, h0_dtype, o, ht, nullptr, 0, B, H, T, K, V, stream);
+}
+
+extern "C" size_t lina_gla_chunk_fwd_pregated_ws_bytes(int B, int H, int T, int K, int V) {
+    if (!tc_eligible(B, H, T, K, V, LINA_BF16) || K < 128) return 0;
+    return split_plan(B, H, T, V).bytes;
+}
+
+extern "C" int lina_gla_chunk_fwd_pregated_bthd_ws(const void *qg, const void *kg, const void *v, const float *decay,
+                                                   const void *h0, int h0_dtype, void *o, float *ht, void *ws, size_t ws_bytes,
+                                                   int B, int H, int T, int K, int V, void *stream) {
+    return pregated_bthd(qg, kg, v, decay, h0, h0_dtype, o, ht, ws, ws_bytes, B, H, T, K, V, stream);
 }
 
 // General pre-gated entry: layout [B,H,T,D] (bthd = 0) or [B,T,H,D] (bthd = 1); row_decay != 0: decay is [B,H,NT,V] and scales
@@ -727,5 +908,7 @@ extern "C" int lina_debug_gla_chunk_trace(const void *q, const void *k, const vo
 extern "C" int lina_debug_gla_pregated_trace(const void *qg, const void *kg, const void *v, const float *decay, void *o, int B,
                                              int H, int T, int K, int V, long long *trace, void *stream) {
     LINA_REQUIRE(tc_eligible(B, H, T, K, V, LINA_BF16) && K == 256, LINA_ERR_UNSUPPORTED, "trace: K=256 bf16 only");
+    if (g_lina_variant[9] != 1 && (V / BV) % 2 == 0)       // the CTA-pair kernel (rank 0 of the first pair is traced)
+        return launch<256, 292>(qg, kg, v, qg, nullptr, 0, o, nullptr, B, H, T, V, 1, 1.f, (cudaStream_t)stream, trace, decay);
     return launch<256, 36>(qg, kg, v, qg, nullptr, 0, o, nullptr, B, H, T, V, 1, 1.f, (cudaStream_t)stream, trace, decay);
 }

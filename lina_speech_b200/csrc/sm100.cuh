@@ -221,6 +221,26 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// ---- distributed shared memory: peer address, bulk copy into a peer CTA, gpu-scope flag handshake ----
+// shared::cluster address of the same shared::cta offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// async-proxy copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer's; complete_tx on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_smem, uint32_t bytes, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_smem), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -299,15 +299,18 @@ class GatedLinearAttention(nn.Module):
             h0 = recurrent_state.contiguous() if recurrent_state is not None else None
             o = torch.empty(B, T, H, V, dtype=x.dtype, device=x.device)
             ht = torch.empty(B, H, K, V, dtype=torch.float32, device=x.device) if use_cache else None
+            # hand-off space for tiles the kernel cuts in two along T (fills the last wave; 0 bytes when no cut applies)
+            ws_bytes = lib.lina_gla_chunk_fwd_pregated_ws_bytes(B, H, T, K, V)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
             prof = fla_ops.PROFILE
             if prof is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(torch.cuda.current_stream(x.device))
-            rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), L.ptr(h0),
-                                                      L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), B, H, T, K, V,
-                                                      L.stream(x))
+            rc = lib.lina_gla_chunk_fwd_pregated_bthd_ws(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), L.ptr(h0),
+                                                         L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht), L.ptr(ws),
+                                                         ws_bytes, B, H, T, K, V, L.stream(x))
             L.count_launches(1)
-            L.check(rc, "lina_gla_chunk_fwd_pregated_bthd")
+            L.check(rc, "lina_gla_chunk_fwd_pregated_bthd_ws")
             if prof is not None:
                 ev1.record(torch.cuda.current_stream(x.device))
                 prof.append(("chunk_pregated", ev0, ev1))

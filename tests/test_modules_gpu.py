@@ -290,9 +290,9 @@ def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
     torch.cuda.synchronize()
     _close(o.transpose(1, 2), ro, 3e-2 * ro.abs().max().item(), 0.0, what="o (pregated tcgen05)")
     _close(ht, rht, 3e-2 * rht.abs().max().item(), 0.0, what="final state")
-    # the kernel's build variants compute the same bits: one state warpgroup (key 4), three operand stages + one v stage
-    # (key 6), cluster-multicast operand loads across the V-slice CTAs (key 7; a cluster only when V / 128 is 2, 4 or 8)
-    for key in (4, 6, 7):
+    # the kernel's build variants compute the same bits: round-1 one-CTA-per-tile kernel with one state warpgroup (key 4 = 1) or
+    # three (key 9 = 1); the default is the CTA-pair kernel when V / 128 is even and K >= 128
+    for key in (4, 9):
         o2, ht2 = torch.empty_like(o), torch.empty_like(ht)
         lib.lina_debug_set_variant(key, 1)
         try:
@@ -304,6 +304,57 @@ def test_pregated_prep_and_chunk_kernel(B, T, H, K, V, use_h0):
         finally:
             lib.lina_debug_set_variant(key, 0)
         assert torch.equal(o2, o) and torch.equal(ht2, ht), f"variant {key} differs"
+
+
+@pytest.mark.parametrize("B,T,H,K,V,use_h0", [(10, 512, 4, 256, 512, True), (10, 500, 4, 256, 512, False), (20, 300, 4, 128, 256, True),
+                                              (3, 1024, 4, 256, 512, False), (32, 2048, 4, 256, 512, False)])
+def test_pair_kernel_and_time_cut_are_bit_identical_to_one_cta_per_tile(B, T, H, K, V, use_h0):
+    """The CTA-pair kernel (score MMA shared through DSMEM) without and with the workspace (tiles of the last wave cut in two
+    along T, fp32 state handed over in HBM) == the one-CTA-per-tile kernel, bit for bit, incl. the final state; the small case
+    is also checked against the oracle's restatement of the kernel contract."""
+    from lina_speech_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(B * T + K)
+    bf = torch.bfloat16
+    nt = (T + 63) // 64
+    qg = (torch.randn(B, T, H, K, device=DEV) * 0.5).to(bf)
+    kg = (torch.randn(B, T, H, K, device=DEV) * 0.5).to(bf)
+    v = torch.randn(B, T, H, V, device=DEV).to(bf)
+    decay = torch.rand(B, H, nt, K, device=DEV) * 0.5 + 0.5
+    h0 = torch.randn(B, H, K, V, device=DEV) if use_h0 else None
+    ws_bytes = lib.lina_gla_chunk_fwd_pregated_ws_bytes(B, H, T, K, V)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    U = B * H * (V // 256)
+    expect_cut = U >= sms // 2 and 0 < U % (sms // 2) <= sms // 4 and nt >= 4
+    assert (ws_bytes > 0) == expect_cut, (ws_bytes, U)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=DEV)
+
+    def run(variant, use_ws):
+        o = torch.full((B, T, H, V), float("nan"), dtype=bf, device=DEV)
+        ht = torch.full((B, H, K, V), float("nan"), dtype=torch.float32, device=DEV)
+        lib.lina_debug_set_variant(9, variant)
+        try:
+            rc = lib.lina_gla_chunk_fwd_pregated_bthd_ws(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(h0),
+                                                         L.dt(h0) if h0 is not None else 0, L.ptr(o), L.ptr(ht),
+                                                         L.ptr(ws) if use_ws else None, ws_bytes if use_ws else 0, B, H, T, K, V,
+                                                         L.stream(qg))
+            L.check(rc, "lina_gla_chunk_fwd_pregated_bthd_ws")
+            torch.cuda.synchronize()
+        finally:
+            lib.lina_debug_set_variant(9, 0)
+        return o, ht
+
+    o_ref, ht_ref = run(1, False)
+    assert torch.isfinite(o_ref.float()).all() and torch.isfinite(ht_ref).all()
+    for variant, use_ws, name in ((0, False, "pairs"), (0, True, "pairs + time cut"), (0, True, "pairs + time cut (second launch)")):
+        o, ht = run(variant, use_ws)
+        assert torch.equal(o, o_ref), f"{name}: o differs ({(o.float() - o_ref.float()).abs().max().item():.3e})"
+        assert torch.equal(ht, ht_ref), f"{name}: final state differs"
+    if B * T <= 6000 and T % 64 == 0:
+        ro, rs = GO.pregated_chunk_fwd(qg.transpose(1, 2).float().cpu(), kg.transpose(1, 2).float().cpu(),
+                                       v.transpose(1, 2).float().cpu(), decay.cpu(), h0.cpu() if h0 is not None else None)
+        _close(o_ref.transpose(1, 2), ro, 2e-2 * ro.abs().max().item(), 0.0, what="o vs kernel contract")
+        _close(ht_ref, rs, 2e-2 * rs.abs().max().item(), 0.0, what="state vs kernel contract")
 
 
 def test_bf16_layer_prefill_pregated_matches_op_by_op_and_oracle():
