@@ -138,6 +138,13 @@ int lina_gla_prefill_prep(const void *xq, const void *xk, const void *xv, long l
                           int B, int L, int Dk, int Dv, int W, float gate_normalizer, float clamp_min, int use_clamp,
                           int dtype, void *stream);
 
+/* Rank-R expansion linear out[m, n] = bias[n] + sum_{r<R} x[m, r] W[n, r] (bf16, fp32 accumulate; R in {8, 16, 32}; bias nullable;
+ * x rows `ldx` elements apart, out rows `ldo`): gk_proj[1] of GatedLinearAttention (model/gla.py:96-97,
+ * nn.Linear(gate_low_rank_dim, key_dim)) over a whole sequence -- an HBM-write-bound outer-product expansion that a library GEMM
+ * (K = 16) serves 10x off its bandwidth bound. */
+int lina_lowrank_linear(const void *x, long long ldx, const void *W, const void *bias, void *out, long long ldo,
+                        int M, int N, int R, int dtype, void *stream);
+
 /* Same pass with the chunk gating of the tensor-core GLA kernel folded in (bf16 only): instead of q, k, gk it writes
  *   qg = scale * q * e^G,  kg = k * e^-G   [B,L,H*K] bf16     (G = cumsum of gk inside each 64-token chunk, fp32)
  *   decay[b,h,n,:] = e^{G at the chunk end}  [B,H,ceil(L/64),K] fp32

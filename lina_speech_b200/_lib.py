@@ -36,6 +36,7 @@ PROTOTYPES = {
     "lina_gla_step_ld": (_i, [_p] * 15 + [_i] * 7 + [_f] * 3 + [_i, _i, _p]),
     "lina_gla_step_lr": (_i, [_p] * 4 + [_i, _p, _p, _i] + [_p] * 11 + [_i] * 7 + [_f] * 3 + [_i, _p]),
     "lina_gla_prefill_prep": (_i, [_p] * 3 + [C.c_longlong] + [_p] * 4 + [C.c_longlong] + [_p] * 7 + [_i] * 6 + [_f, _f, _i, _i, _p]),
+    "lina_lowrank_linear": (_i, [_p, C.c_longlong, _p, _p, _p, C.c_longlong, _i, _i, _i, _i, _p]),
     "lina_gla_prefill_prep_gated": (_i, [_p, C.c_longlong] * 3 + [_p] * 4 + [C.c_longlong] + [_p] * 7 + [_i] * 7 + [_f, _f, _p, _p]),
     "lina_gla_chunk_fwd_pregated_bthd": (_i, [_p] * 5 + [_i, _p, _p] + [_i] * 5 + [_p]),
     "lina_gla_chunk_fwd_pregated_ws_bytes": (_sz, [_i] * 5),

@@ -7,6 +7,11 @@
 static __device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
+static __device__ __forceinline__ uint32_t f2_to_bf2(float2 a) {     // (a.x -> low half, a.y -> high half), round to nearest even
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a.y), "f"(a.x));
+    return r;
+}
 static __device__ __forceinline__ float2 silu2(float2 a) {          // a * sigmoid(a) = h * tanh(h) + h, h = a / 2
     const float2 h = __fmul2_rn(a, make_float2(0.5f, 0.5f));
     const float2 t = make_float2(tanh_approx_(h.x), tanh_approx_(h.y));

@@ -38,6 +38,8 @@ CAT5 = os.environ.get("LINA_CAT5", "0") == "1"
 PREGATED = os.environ.get("LINA_PREGATED", "1") != "0"
 # "cat4": one [q;k;v;g] GEMM; "split": four GEMMs (the pre-gated pass and the norm-gate read each output in place)
 GEMM_GROUPING = os.environ.get("LINA_GEMM_GROUPING", "split")
+# LINA_LOWRANK_KERNEL=0 sends gk_proj[1] of the whole-sequence path back through F.linear (A/B)
+LOWRANK_KERNEL = os.environ.get("LINA_LOWRANK_KERNEL", "1") != "0"
 
 
 
@@ -237,6 +239,24 @@ class GatedLinearAttention(nn.Module):
                 and self.head_v_dim * x.element_size() // 16 <= 128
                 and self.q_proj.weight.dtype == x.dtype)
 
+    def _gate_expand(self, lo: torch.Tensor) -> torch.Tensor:
+        """gk_proj[1] (model/gla.py:96-97) on a whole sequence: [B,T,R] (any row stride) -> [B,T,key_dim].  bf16 with R in
+        {8,16,32} runs lina_lowrank_linear (the K = R library GEMM ran 10x off its write-bandwidth bound); else F.linear."""
+        lin = self.gk_proj[1]
+        R, N = lin.weight.shape[1], lin.weight.shape[0]
+        if (LOWRANK_KERNEL and lo.dtype == torch.bfloat16 and lin.weight.dtype == torch.bfloat16 and R in (8, 16, 32) and N % 4 == 0
+                and lo.dim() == 3 and lo.stride(2) == 1 and lo.stride(1) % 4 == 0 and lo.stride(0) == lo.shape[1] * lo.stride(1)
+                and lo.data_ptr() % 8 == 0 and (lin.bias is None or lin.bias.dtype == torch.bfloat16)):
+            Bn, Tn = lo.shape[0], lo.shape[1]
+            out = torch.empty(Bn, Tn, N, dtype=lo.dtype, device=lo.device)
+            w = lin.weight if lin.weight.is_contiguous() else lin.weight.contiguous()
+            rc = L.lib().lina_lowrank_linear(L.ptr(lo), lo.stride(1), L.ptr(w), L.ptr(lin.bias), L.ptr(out), N, Bn * Tn, N, R,
+                                             L.dt(lo), L.stream(lo))
+            L.count_launches(1)
+            L.check(rc, "lina_lowrank_linear")
+            return out
+        return F.linear(lo, lin.weight, lin.bias)
+
     def _prefill(self, x: torch.Tensor, last_state, use_cache: bool, past_key_values, input_norm_bound=None) -> torch.Tensor:
         """model/gla.py:146-225 for a whole sequence without autograd: one [q;k;v;g] GEMM, ONE pass for the three
         short convs + the gate non-linearity (lina_gla_prefill_prep), the GLA op on the [B,T,H,D] layout, the
@@ -263,7 +283,7 @@ class GatedLinearAttention(nn.Module):
                 lo = self.gk_proj[0](x)
             xq, xk, xv, g = (proj[..., :kd], proj[..., kd:2 * kd], proj[..., 2 * kd:2 * kd + vd],
                              proj[..., 2 * kd + vd:2 * kd + 2 * vd])
-        gk_raw = F.linear(lo, self.gk_proj[1].weight, self.gk_proj[1].bias)
+        gk_raw = self._gate_expand(lo)
         for t_ in (xq, xk, xv, g, gk_raw):                   # raw-pointer path: one dtype argument describes them all
             if t_.dtype != x.dtype:
                 raise TypeError(f"GatedLinearAttention._prefill: projection is {t_.dtype}, input is {x.dtype}")

@@ -99,8 +99,20 @@ class StateTuner:
         self.device = next(model.parameters()).device
         model.attentive_rnn.to_mode("fused_recurrent")          # the mode whose backward returns dh0
         model.train()
+        # Only the state factors are optimised (initial_state.py:99-104 hands Adam nothing else); the reference leaves
+        # requires_grad on the model weights, so its backward also computes -- and never reads -- every weight gradient.
+        # Here the weights are frozen for the duration of the tuning (restored by release()): same losses, same factors,
+        # no dW GEMMs.
+        self._frozen = [p for p in model.parameters() if p.requires_grad]
+        for p in self._frozen:
+            p.requires_grad_(False)
         self.factors = model.attentive_rnn.get_init_state_tuning_params(lora=rank, device=self.device)
         self.opt = torch.optim.Adam(reduce(tuple.__add__, self.factors), lr=lr)
+
+    def release(self) -> None:
+        for p in self._frozen:
+            p.requires_grad_(True)
+        self._frozen = []
 
     def loss_on(self, batch: dict, batch_size: int) -> torch.Tensor:
         on_dev = {name: (val.to(self.device) if torch.is_tensor(val) else val) for name, val in batch.items()}
@@ -122,17 +134,20 @@ def train_initial_state(model, dataset, tokenizer, n_samples: int, lr: float = 0
     if progress:
         from tqdm import tqdm
         rounds = tqdm(rounds)
-    for it in rounds:
-        examples = [dataset[next(picks)] for _ in range(batch_size)]
-        loss = tuner.loss_on(simple_collate(examples, tokenizer), batch_size)
-        history.append(loss.item())
-        loss.backward()
-        if (it + 1) % grad_acc == 0:
-            tuner.opt.step()
-            tuner.opt.zero_grad()
-            optimizer_steps += 1
-            if save_every_k_steps > 0 and optimizer_steps % save_every_k_steps == 0:
-                checkpoints.append(deepcopy(tuner.factors))
+    try:
+        for it in rounds:
+            examples = [dataset[next(picks)] for _ in range(batch_size)]
+            loss = tuner.loss_on(simple_collate(examples, tokenizer), batch_size)
+            history.append(loss.item())
+            loss.backward()
+            if (it + 1) % grad_acc == 0:
+                tuner.opt.step()
+                tuner.opt.zero_grad()
+                optimizer_steps += 1
+                if save_every_k_steps > 0 and optimizer_steps % save_every_k_steps == 0:
+                    checkpoints.append(deepcopy(tuner.factors))
+    finally:
+        tuner.release()
     model.eval()
     if save_every_k_steps > 0:
         return checkpoints + [tuner.factors], history

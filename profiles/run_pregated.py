@@ -1,5 +1,5 @@
 """The pre-gated GLA path alone at the bench shape (B=32, T=2048, H=4, K=256, V=512, bf16): lina_gla_prefill_prep_gated
-(v conv kernel + q/k gate kernel) followed by lina_gla_chunk_fwd_pregated_bthd -- the command ncu wraps for the per-kernel
+(v conv kernel + q/k gate kernel) followed by lina_gla_chunk_fwd_pregated_bthd_ws -- the command ncu wraps for the per-kernel
 captures under profiles/.  Prints CUDA-event time per launch of each."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,12 +28,17 @@ st = torch.cuda.current_stream().cuda_stream
 def prep():
     rc = lib.lina_gla_prefill_prep_gated(L.ptr(xq), ldx, L.ptr(xk), ldx, L.ptr(xv), ldx, L.ptr(wq), L.ptr(wk), L.ptr(wv),
                                          L.ptr(gk_raw), kd, L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, None, None, 0,
-                                         B, T, H, K, V, 4, 16.0, K ** -0.5, st)
+                                         B, T, H, K, V, 4, 16.0, K ** -0.5, None, st)
     assert rc == 0, lib.lina_last_error_string()
 
 
+ws_bytes = lib.lina_gla_chunk_fwd_pregated_ws_bytes(B, H, T, K, V)
+ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+
+
 def gla():
-    rc = lib.lina_gla_chunk_fwd_pregated_bthd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, 0, L.ptr(o), None, B, H, T, K, V, st)
+    rc = lib.lina_gla_chunk_fwd_pregated_bthd_ws(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(decay), None, 0, L.ptr(o), None, L.ptr(ws), ws_bytes,
+                                                 B, H, T, K, V, st)
     assert rc == 0, lib.lina_last_error_string()
 
 

@@ -357,6 +357,28 @@ def test_pair_kernel_and_time_cut_are_bit_identical_to_one_cta_per_tile(B, T, H,
         _close(ht_ref, rs, 2e-2 * rs.abs().max().item(), 0.0, what="state vs kernel contract")
 
 
+@pytest.mark.parametrize("M,N,R,strided,bias", [(65, 1024, 16, True, True), (300, 1024, 16, False, True), (64, 40, 8, False, False),
+                                                 (1000, 2052, 32, True, True)])
+def test_lowrank_linear_matches_fp32_linear(M, N, R, strided, bias):
+    """lina_lowrank_linear (gk_proj[1], model/gla.py:96-97, over a whole sequence) == the fp32 product of the same bf16 values
+    rounded once to bf16 (what a bf16 nn.Linear returns, up to the summation order inside the fp32 accumulation)."""
+    from lina_speech_b200 import _lib as L
+    torch.manual_seed(M + N)
+    bf = torch.bfloat16
+    wide = torch.randn(M, R + 24, device=DEV).to(bf)
+    x = wide[:, 24:] if strided else wide[:, :R].contiguous()
+    W = (torch.randn(N, R, device=DEV) * 0.3).to(bf)
+    b = torch.randn(N, device=DEV).to(bf) if bias else None
+    out = torch.full((M, N), float("nan"), dtype=bf, device=DEV)
+    rc = L.lib().lina_lowrank_linear(L.ptr(x), x.stride(0), L.ptr(W), L.ptr(b), L.ptr(out), N, M, N, R, L.dt(x), L.stream(x))
+    L.check(rc, "lina_lowrank_linear")
+    ref = x.float() @ W.float().t() + (b.float() if bias else 0.0)
+    err = (out.float() - ref).abs()
+    assert torch.isfinite(out.float()).all()
+    assert (err <= ref.abs() * 2.0 ** -8 + 1e-6).all(), f"max err {err.max().item():.3e}"      # half an ulp of bf16 (+ fp32 sum order)
+    assert (out == ref.to(bf)).float().mean() > 0.999            # the rare differences are round-to-nearest ties of the sum order
+
+
 def test_bf16_layer_prefill_pregated_matches_op_by_op_and_oracle():
     """GatedLinearAttention at the flagship head size (d1024, H4, K256, V512) in bf16: the pregated inference path ==
     the same layer with LINA_PREGATED / LINA_FUSED_PREFILL off (within bf16 rounding) == the oracle layer in fp32;
