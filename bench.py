@@ -484,13 +484,13 @@ def main_ours(args):
     pk = peaks()
     uses_tc = bool(_lib.lib().lina_gla_chunk_fwd_uses_tensor_cores(B, H, T, K, V, _lib.BF16))
     traffic = None                                   # DRAM bytes per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json" if pregated else "ncu_traffic_r01.json")
     if uses_tc and os.path.exists(tpath) and (B, H, T, K, V) == (32, 4, 2048, 256, 512):
         with open(tpath) as f:
-            t = json.load(f).get("gla_chunk_fwd_sm100_kernel<256,4>" if pregated else "gla_chunk_fwd_sm100_kernel<256>")
+            t = json.load(f).get("gla_chunk_fwd_sm100_kernel<256,292>" if pregated else "gla_chunk_fwd_sm100_kernel<256>")
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    roofline = {"kernel": ("lina_gla_chunk_fwd_pregated_bthd (tcgen05, operands gated by lina_gla_prefill_prep_gated)" if pregated
+    roofline = {"kernel": ("lina_gla_chunk_fwd_pregated_bthd_ws (tcgen05, CTA pairs + T cut, operands gated by lina_gla_prefill_prep_gated)" if pregated
                            else "lina_gla_chunk_fwd (tcgen05)" if uses_tc else "lina_gla_chunk_fwd (CUDA-core recurrence)"),
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic,

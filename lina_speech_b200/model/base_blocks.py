@@ -84,6 +84,12 @@ class SelfAttention(nn.Module):
         return y.transpose(1, 2).reshape(B, n, d)
 
 
+# hidden size of the inference-path SwiGLU GEMMs is zero-padded to a multiple of this: 1365 -> 1408 = 11 x 128, so N = 2816 = 11 x 256
+# tiles for the library GEMM (with 1368 it picks a 240 x 192 kernel at 1150 TF/s; A/B in one process, profiles/step_breakdown.py:
+# 36.1 / 36.3 ms per step with 8, 35.6 / 35.5 with 128 / 64).  LINA_SWIGLU_PAD=8 restores alignment-only padding.
+SWIGLU_PAD = int(os.environ.get("LINA_SWIGLU_PAD", "128"))
+
+
 class SwiGLU(nn.Module):
     """model/base_blocks.py:42-50: hidden = 4d//3, biases on both linears.
 
@@ -104,7 +110,7 @@ class SwiGLU(nn.Module):
         key = tuple((t.data_ptr(), _ver(t), t.dtype) for t in ps)
         if self._padded is None or self._padded[0] != key:
             hid = self.p_out.in_features
-            hp = (hid + 7) // 8 * 8
+            hp = (hid + SWIGLU_PAD - 1) // SWIGLU_PAD * SWIGLU_PAD
             wi, bi, wo = ps[0].detach(), ps[1].detach(), ps[2].detach()
             wi_p = wi.new_zeros(2 * hp, wi.shape[1]); bi_p = bi.new_zeros(2 * hp)
             wi_p[:hid], wi_p[hp:hp + hid] = wi[:hid], wi[hid:]
@@ -126,11 +132,12 @@ class SwiGLU(nn.Module):
             L.check(rc, "lina_swiglu_act")
             return F.linear(a.view(*x.shape[:-1], hp), wo_p, self.p_out.bias)
         hid = self.p_out.in_features
-        if x.is_cuda and hid % 8:
+        if x.is_cuda and hid % SWIGLU_PAD:
             # training / autograd path: the same zero padding, applied differentiably on the fly -- with hidden = 1365 the
             # unpadded GEMMs (N = 2730, K = 1365) run on cuBLAS' unaligned sm75/sm80 kernels, ~5x slower (56 ms of a
             # 300 ms training step at bs8 x seq4096)
-            hp, padn = (hid + 7) // 8 * 8, (hid + 7) // 8 * 8 - hid
+            hp = (hid + SWIGLU_PAD - 1) // SWIGLU_PAD * SWIGLU_PAD
+            padn = hp - hid
             wi, bi = self.p_in.weight, self.p_in.bias
             wi_p = torch.cat([F.pad(wi[:hid], (0, 0, 0, padn)), F.pad(wi[hid:], (0, 0, 0, padn))], dim=0)
             bi_p = torch.cat([F.pad(bi[:hid], (0, padn)), F.pad(bi[hid:], (0, padn))], dim=0)

@@ -40,6 +40,15 @@ for name, flag in (("lowrank kernel", True), ("library GEMM (K=16)", False), ("l
     res[name] = round(timed(), 3)
     print(f"{name:28s} {res[name]:8.3f} ms/step", flush=True)
 G.LOWRANK_KERNEL = True
+# SwiGLU hidden padding: 1365 -> 1368 (alignment only) vs 1408 = 11 x 128 (tile-friendly N = 2816 for the library GEMM)
+import lina_speech_b200.model.base_blocks as BB
+for pad in (8, 128, 64, 8):
+    BB.SWIGLU_PAD = pad
+    for m in lm.modules():
+        if isinstance(m, BB.SwiGLU):
+            m._padded = None
+    res[f"swiglu pad {pad}"] = round(timed(), 3)
+    print(f"swiglu hidden padded to a multiple of {pad:3d}: {res[f'swiglu pad {pad}']:8.3f} ms/step", flush=True)
 from torch.profiler import profile, ProfilerActivity
 NSTEP = 4
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
