@@ -400,15 +400,9 @@ int lina_gemm_bf16_terms(const lina_gemm_args *args, void *stream);
  * key 4 = 1 runs the pre-gated GLA kernel's state pass on one warpgroup, key 5 = 1 selects the round-1 short-conv backward,
  * (keys 6 / 7 selected a three-stage operand ring and cluster-multicast operand loads of the pre-gated GLA kernel: both measured
  * slower or neutral in round 1 and no longer built), key 8 = 2 routes lina_codec_istft_head (n_fft = 1280) back to the generic shared-memory
- * FFT (default: the warp-per-frame fixed-radix kernel, csrc/fft640.cuh: 0.25 vs 0.69 ms at 32 x 750 frames). */
+ * FFT (default: the warp-per-frame fixed-radix kernel, csrc/fft640.cuh: 0.25 vs 0.69 ms at 32 x 750 frames), key 9 = 1 selects
+ * the one-CTA-per-tile pre-gated GLA kernel of round 1 (2: CTA pairs without the T cut; default 0: pairs + T cut). */
 int lina_debug_set_variant(int key, int value);
-/* The tcgen05 GLA kernel (K = 256, bf16) with a clock64 timeline of CTA (0,0) written to
- * trace[6 roles][64 items][4 events] (int64) -- profiles/trace_gla_chunk.py prints it. */
-int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
-                               int H, int T, int K, int V, float scale, long long *trace, void *stream);
-
-int lina_debug_gla_pregated_trace(const void *qg, const void *kg, const void *v, const float *decay, void *o, int B,
-                                  int H, int T, int K, int V, long long *trace, void *stream);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,16 @@ def build(verbose: bool = False, force: bool = False) -> str:
                 print(" ".join(cmd), flush=True)
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     # the bring-up probes compile into their own shared object (with their own copy of the error-string helper)
-    dbg_objs = [os.path.join(objdir, "abi.o")]
+    # ... together with a copy of the GLA chunk kernel compiled with its clock64 timeline (-DLINA_GLA_TRACE) and every other
+    # product object (the traced kernel calls into the recurrence fallback and reads the variant table)
+    traced = os.path.join(objdir, "debug_gla_chunk_sm100_traced.o")
+    dbg_objs = [o for o in objs if not o.endswith(os.sep + "gla_chunk_sm100.o")] + [traced]
+    tsrc = os.path.join(CSRC, "gla_chunk_sm100.cu")
+    if force or _stale(traced, [tsrc] + headers):
+        cmd = [nvcc] + NVCC_FLAGS + ["-DLINA_GLA_TRACE", "-c", tsrc, "-o", traced]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append(("gla_chunk_sm100.cu (traced)", subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s in sorted(f for f in os.listdir(DEBUG_CSRC) if f.endswith(".cu")):
         src, obj = os.path.join(DEBUG_CSRC, s), os.path.join(objdir, "debug_" + s[:-3] + ".o")
         dbg_objs.append(obj)

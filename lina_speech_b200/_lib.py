@@ -80,8 +80,6 @@ PROTOTYPES = {
     "lina_skinny_linear": (_i, [_p, C.c_longlong, _p, C.c_longlong, _p, _p, _f, _p, _p, C.c_longlong, _p, _p, C.c_longlong, _i, _i, _i, _i, _p]),
     "lina_codec_cl_softmax": (_i, [_p, _p, _i, C.c_longlong, _i, C.c_longlong, C.c_longlong, _p]),
     "lina_debug_set_variant": (_i, [_i, _i]),
-    "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
-    "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
 }
 
 # liblina_b200_debug.so (include/lina_b200_debug.h): bring-up probes, not part of the product library
@@ -91,6 +89,9 @@ DEBUG_PROTOTYPES = {
     "lina_debug_umma_probe_m": (_i, [_p] * 3 + [_i] * 3 + [_p]),
     "lina_debug_umma_probe_sw128": (_i, [_p] * 4 + [_i] * 5 + [_p]),
     "lina_debug_umma_timing": (_i, [_p] + [_i] * 6 + [_p]),
+    "lina_debug_set_variant": (_i, [_i, _i]),
+    "lina_debug_gla_chunk_trace": (_i, [_p] * 5 + [_i] * 5 + [_f, _p, _p]),
+    "lina_debug_gla_pregated_trace": (_i, [_p] * 5 + [_i] * 5 + [_p, _p]),
 }
 
 

@@ -94,8 +94,12 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
 
 // bring-up timeline: role r, item n, event e -> clock64 of CTA (0,0)   (trace == nullptr in production)
 constexpr int TR_EV = 4, TR_MAXN = 64;
+#ifdef LINA_GLA_TRACE        // liblina_b200_debug.so only: the product kernel carries no timeline code
 #define TRACE(role, n, ev) do { if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (n) < TR_MAXN) \
     trace[((role) * TR_MAXN + (n)) * TR_EV + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, n, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -897,6 +901,7 @@ extern "C" int lina_gla_chunk_fwd_pregated(const void *qg, const void *kg, const
     return launch<256, 4>(qg, kg, v, qg, h0, h0_dtype, o, ht, B, H, T, V, bthd, 1.f, st, nullptr, decay, ldq, ldk, ldv);
 }
 
+#ifdef LINA_GLA_TRACE
 // bring-up: same kernel with a clock64 timeline of CTA (0,0): trace[6 roles][64 items][4 events]
 extern "C" int lina_debug_gla_chunk_trace(const void *q, const void *k, const void *v, const void *gk, void *o, int B,
                                           int H, int T, int K, int V, float scale, long long *trace, void *stream) {
@@ -912,3 +917,4 @@ extern "C" int lina_debug_gla_pregated_trace(const void *qg, const void *kg, con
         return launch<256, 292>(qg, kg, v, qg, nullptr, 0, o, nullptr, B, H, T, V, 1, 1.f, (cudaStream_t)stream, trace, decay);
     return launch<256, 36>(qg, kg, v, qg, nullptr, 0, o, nullptr, B, H, T, V, 1, 1.f, (cudaStream_t)stream, trace, decay);
 }
+#endif  // LINA_GLA_TRACE

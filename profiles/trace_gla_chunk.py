@@ -12,7 +12,7 @@ gk = (F.logsigmoid(torch.randn(B, H, T, K, device="cuda")) / 16).bfloat16()
 o = torch.empty_like(v)
 tr = torch.zeros(6, 64, 4, dtype=torch.int64, device="cuda")
 for _ in range(2):
-    L.check(L.lib().lina_debug_gla_chunk_trace(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(o), B, H, T, K, V,
+    L.check(L.debug_lib().lina_debug_gla_chunk_trace(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(gk), L.ptr(o), B, H, T, K, V,
                                                  K ** -0.5, L.ptr(tr), L.stream(q)), "trace")
 torch.cuda.synchronize()
 t = tr.cpu()

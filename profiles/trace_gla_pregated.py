@@ -13,7 +13,7 @@ decay = torch.rand(B, H, T // 64, K, device="cuda") * 0.2 + 0.7
 o = torch.empty(B, T, H, V, device="cuda", dtype=bf)
 tr = torch.zeros(6, 64, 4, dtype=torch.int64, device="cuda")
 for _ in range(2):
-    L.check(L.lib().lina_debug_gla_pregated_trace(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(o), B, H, T, K, V,
+    L.check(L.debug_lib().lina_debug_gla_pregated_trace(L.ptr(qg), L.ptr(kg), L.ptr(v), L.ptr(decay), L.ptr(o), B, H, T, K, V,
                                                   L.ptr(tr), L.stream(qg)), "trace")
 torch.cuda.synchronize()
 t = tr.cpu()

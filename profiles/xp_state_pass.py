@@ -1,4 +1,6 @@
-"""Timing experiment (results are WRONG on purpose): which part of the state pass of the pair kernel costs time?
+"""(Historical: the kernel-side knob this drives was removed after the measurement -- numbers in DESIGN 4.1c; to repeat it, re-add
+`xp` to SplitArgs and guard the three tcgen05.ld / st of the state pass with its bits.)
+Timing experiment (results are WRONG on purpose): which part of the state pass of the pair kernel costs time?
 variant key 10 bits: 1 = skip the fp32 write-back of ST, 2 = skip the bf16 SA write, 4 = skip the ST read."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -36,7 +36,9 @@ def test_debug_library_is_separate_from_the_product():
     dbg = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
-        assert hasattr(dbg, n) and not hasattr(raw, n), n
+        assert hasattr(dbg, n), n
+        # each library has its own copy of the A/B variant table (and its setter); everything else is debug-only
+        assert n == "lina_debug_set_variant" or not hasattr(raw, n), n
 
 
 def test_ctypes_prototypes_match_header():
