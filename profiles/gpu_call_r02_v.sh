@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 120 python profiles/trace_gla_pair.py 2>&1 | cut -c1-330 | tail -24
+timeout 300 python profiles/xp_state_pass.py 2>&1 | tail -10
