@@ -228,3 +228,33 @@ def test_flagship_greedy_generation_with_bf16_cache(flagship, prefill_prompt):
                                        f"{margin[b, t]:.4f} exceeds the bf16 noise bound {noise:.4f}")
     print(f"greedy generation, prefill_prompt={prefill_prompt}: first divergences (step, oracle margin) = {first}; "
           f"noise bound {noise:.4f}")
+
+
+def test_forward_graphed_replays_the_same_pass(flagship):
+    """LinaModel.forward_graphed: the CUDA-graph replay returns bit-identical logits / loss / attention to the eager pass, takes
+    host (pinned) inputs, follows new inputs of the same shape, and captures a second graph for a new shape."""
+    lm, _ = flagship
+    B, T, n_txt = 2, 257, 48
+    x, y, em, cm = _batch(B, T, n_txt, 3)
+    with torch.inference_mode():
+        ref = lm(x.to(DEV), y.to(DEV), em.to(DEV), cm.to(DEV))
+        got = lm.forward_graphed(x.pin_memory(), y.pin_memory(), em.to(DEV), cm.to(DEV))
+        torch.cuda.synchronize()
+        key = next(iter(lm._fwd_graphs))
+        assert lm._fwd_graphs[key] is not False, "the bench model's gates must be certified by its weights (graph path in use)"
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+        x2, y2, _, _ = _batch(B, T, n_txt, 4)
+        ref2 = lm(x2.to(DEV), y2.to(DEV), em.to(DEV), cm.to(DEV))
+        ref2 = tuple(t.clone() for t in ref2[:3])
+        got2 = lm.forward_graphed(x2, y2, em, cm)
+        assert len(lm._fwd_graphs) == 1
+        assert torch.equal(got2[0], ref2[0]) and torch.equal(got2[1], ref2[1]) and torch.equal(got2[2], ref2[2])
+        assert not torch.equal(ref2[0], ref[0])
+        x3, y3, em3, cm3 = _batch(1, 129, 20, 5)
+        got3 = lm.forward_graphed(x3, y3, em3, cm3)
+        ref3 = lm(x3.to(DEV), y3.to(DEV), em3.to(DEV), cm3.to(DEV))
+        assert len(lm._fwd_graphs) == 2
+        assert torch.equal(got3[0], ref3[0]) and torch.equal(got3[1], ref3[1])
+    with torch.enable_grad():                                   # autograd on: the eager pass serves the call
+        out = lm.forward_graphed(x.to(DEV), y.to(DEV), em.to(DEV), cm.to(DEV))
+        assert out[1].requires_grad
