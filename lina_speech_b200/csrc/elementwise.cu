@@ -98,6 +98,17 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
             for (int i = 0; i < VEC; ++i) s += v[c][i];
         }
     }
+    // the affine parameters are fetched BEFORE the two dependent reductions: at decode-step sizes (a few dozen rows) the kernel is
+    // one memory round trip long, and loading them after the statistics made it two
+    uint4 gr[LN_CH], br[LN_CH];
+#pragma unroll
+    for (int c = 0; c < LN_CH; ++c) {
+        const int ch = lane + c * 32;
+        if (ch < nch) {
+            gr[c] = *reinterpret_cast<const uint4 *>(gamma + (size_t)ch * VEC);
+            br[c] = *reinterpret_cast<const uint4 *>(beta + (size_t)ch * VEC);
+        }
+    }
     const float mean = warp_sum(s) / (float)N;
     float ss = 0.f;
 #pragma unroll
@@ -112,9 +123,7 @@ add_layernorm_kernel(const T *__restrict__ a, const T *__restrict__ x, const T *
     for (int c = 0; c < LN_CH; ++c) {
         const int ch = lane + c * 32;
         if (ch < nch) {
-            const uint4 gr = *reinterpret_cast<const uint4 *>(gamma + (size_t)ch * VEC);
-            const uint4 br = *reinterpret_cast<const uint4 *>(beta + (size_t)ch * VEC);
-            const T *ge = reinterpret_cast<const T *>(&gr), *be = reinterpret_cast<const T *>(&br);
+            const T *ge = reinterpret_cast<const T *>(&gr[c]), *be = reinterpret_cast<const T *>(&br[c]);
             uint4 outr;
             T *oe = reinterpret_cast<T *>(&outr);
 #pragma unroll

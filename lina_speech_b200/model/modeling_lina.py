@@ -132,9 +132,15 @@ class LinaModel(nn.Module):
         if self._fwd_graphs is None:
             self._fwd_graphs = {}
         g = self._fwd_graphs.get(key)
+        versions = tuple(p._version for p in self.parameters())
+        if g is not None and g is not False and g["versions"] != versions:
+            g = None                                          # a parameter was updated in place: tensors derived from the weights
+            self._fwd_graphs.pop(key)                         # (padded / concatenated copies) are baked into the graph -> re-capture
         if g is None:
             g = self._fwd_graphs[key] = self._capture_forward(x, y, encoder_mask, crossatt_mask, dev)
-        if g is False or not certified():                     # weights changed since capture: the certificate is re-derived
+            if g is not False:
+                g["versions"] = versions
+        if g is False or not certified():                     # gates not provably inside the tensor-core envelope: eager pass
             return self.forward(x.to(dev), y.to(dev), encoder_mask.to(dev), crossatt_mask.to(dev))
         for buf, src in zip(g["inputs"], (x, y, encoder_mask, crossatt_mask)):
             buf.copy_(src, non_blocking=True)

@@ -255,6 +255,18 @@ def test_forward_graphed_replays_the_same_pass(flagship):
         ref3 = lm(x3.to(DEV), y3.to(DEV), em3.to(DEV), cm3.to(DEV))
         assert len(lm._fwd_graphs) == 2
         assert torch.equal(got3[0], ref3[0]) and torch.equal(got3[1], ref3[1])
+        # an in-place parameter update invalidates the graph (it holds padded / concatenated copies of the weights): re-captured
+        w = lm.logits_head.weight
+        saved = w.detach().clone()
+        with torch.inference_mode(False), torch.no_grad():
+            w.mul_(0.5)
+        try:
+            got4 = tuple(t.clone() for t in lm.forward_graphed(x, y, em, cm)[:2])
+            ref4 = lm(x.to(DEV), y.to(DEV), em.to(DEV), cm.to(DEV))
+            assert torch.equal(got4[0], ref4[0]) and torch.equal(got4[1], ref4[1]) and not torch.equal(got4[0], ref[0])
+        finally:
+            with torch.inference_mode(False), torch.no_grad():
+                w.copy_(saved)
     with torch.enable_grad():                                   # autograd on: the eager pass serves the call
         out = lm.forward_graphed(x.to(DEV), y.to(DEV), em.to(DEV), cm.to(DEV))
         assert out[1].requires_grad
