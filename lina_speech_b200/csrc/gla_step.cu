@@ -96,9 +96,10 @@ template <> struct Vec<8> {  // bf16 state, 16 B
 };
 
 constexpr int SW = 8;     // warps per CTA
-constexpr int SU = 4;     // state rows in flight per thread
+// state rows in flight per thread: 4 when the grid oversubscribes the GPU (batch 128: 55 warps per SM), 8 at small batches, where
+// the few resident warps cannot keep enough bytes in flight for the HBM rate (batch 32: 14 warps per SM, 16.3 us for 67 MB)
 
-template <typename ST, int VEC>
+template <typename ST, int VEC, int SU>
 __global__ void __launch_bounds__(SW * 32)
 gla_step_state_kernel(ST *__restrict__ S, const float *__restrict__ qf, const float *__restrict__ kf,
                       const float *__restrict__ ef, const float *__restrict__ vf, float *__restrict__ of,
@@ -214,7 +215,15 @@ int launch_step(const void *xq, const void *xk, const void *xv, const void *gk_r
     LINA_LAUNCH_OK("gla_step_prep_kernel");
     constexpr int VEC = sizeof(CT) == 4 ? 4 : 8;
     dim3 grid((V + 32 * VEC - 1) / (32 * VEC), B * H);
-    gla_step_state_kernel<CT, VEC><<<grid, SW * 32, 0, st>>>((CT *)S, qf, kf, ef, vf, of, K, V);
+    static thread_local int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    if ((long long)grid.x * grid.y <= 4LL * sms)
+        gla_step_state_kernel<CT, VEC, 8><<<grid, SW * 32, 0, st>>>((CT *)S, qf, kf, ef, vf, of, K, V);
+    else
+        gla_step_state_kernel<CT, VEC, 4><<<grid, SW * 32, 0, st>>>((CT *)S, qf, kf, ef, vf, of, K, V);
     LINA_LAUNCH_OK("gla_step_state_kernel");
     const int rows = B * H;
     int nt = ((V / 4 + 31) / 32) * 32;           // V % 4 == 0 (checked); up to 4 float4 per thread -> V <= 4096
