@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 300 python profiles/host_profile_forward.py 2>&1 | grep -v Warn | tail -50
+timeout 300 python profiles/host_profile_forward2.py 2>&1 | grep -v Warn | tail -8
