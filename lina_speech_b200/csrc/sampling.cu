@@ -29,10 +29,9 @@ topk_sample_kernel(const T *__restrict__ logits, long long ld, int Vn, int k, fl
     __shared__ float row[MAXV];
     __shared__ int wcnt[2][ST / 32];
     __shared__ float red[ST / 32];
-    __shared__ float seg[ST];
+    __shared__ int wfirst[ST / 32], wlast[ST / 32];
     __shared__ uint32_t sel_prefix;
     __shared__ float bcast[2];
-    __shared__ int winner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T *r = logits + (size_t)blockIdx.x * ld;
     for (int i = tid; i < Vn; i += ST) row[i] = to_f(r[i]);
@@ -95,29 +94,34 @@ topk_sample_kernel(const T *__restrict__ logits, long long ld, int Vn, int k, fl
         row[i] = w;
         ssum += w;
     }
-    seg[tid] = ssum;
+    // block-wide scan of the 256 segment sums: the sample falls into the FIRST non-empty segment whose cumulative weight exceeds
+    // u * total (the last non-empty one when rounding leaves none), then that segment's owner walks its <= 33 entries
+    float incl = ssum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) red[warp] = incl;
     __syncthreads();
-    if (tid == 0) {                      // serial scan of the 256 segment sums (tiny): the segment holding u * total
-        float tot = 0.f;
-        for (int t = 0; t < ST; ++t) tot += seg[t];
-        const float target = uni[blockIdx.x] * tot;
-        float acc = 0.f, ex = 0.f;
-        int wseg = -1;
-        for (int t = 0; t < ST; ++t) {
-            if (seg[t] <= 0.f) continue;
-            wseg = t;                    // the last non-empty segment catches target == total (rounding)
-            ex = acc;
-            if (acc + seg[t] > target) break;
-            acc += seg[t];
-        }
-        winner = wseg;
-        bcast[0] = target;
-        bcast[1] = ex;
+    float wprefix = 0.f, tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST / 32; ++w) { const float t = red[w]; tot += t; if (w < warp) wprefix += t; }
+    const float ex = wprefix + incl - ssum;                  // weight of the segments before this thread's
+    const float target = uni[blockIdx.x] * tot;
+    const unsigned nonempty = __ballot_sync(0xffffffffu, ssum > 0.f);
+    const unsigned hit = __ballot_sync(0xffffffffu, ssum > 0.f && ex + ssum > target);
+    if (lane == 0) {
+        wfirst[warp] = hit ? warp * 32 + __ffs(hit) - 1 : ST;
+        wlast[warp] = nonempty ? warp * 32 + 31 - __clz(nonempty) : -1;
     }
     __syncthreads();
-    if (tid == winner) {
-        const float target = bcast[0];
-        float acc = bcast[1];
+    int first = ST, last = -1;
+#pragma unroll
+    for (int w = 0; w < ST / 32; ++w) { first = min(first, wfirst[w]); last = max(last, wlast[w]); }
+    const int win = first < ST ? first : last;
+    if (tid == win) {
+        float acc = ex;
         int pick = -1;
         for (int i = lo; i < hi; ++i) {
             const float w = row[i];

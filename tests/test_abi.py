@@ -106,3 +106,21 @@ def test_new_entry_points_validate_arguments_without_a_device():
     assert lib.lina_layernorm_f32in_fwd(None, None, None, None, None, None, 4, 8, 1e-5, _lib.BF16, None) == -1
     assert lib.lina_cross_entropy_rows(None, 0, None, None, None, None, 4, 8, 1, _lib.BF16, None) == -1
     assert lib.lina_debug_set_variant(99, 1) == -1 and lib.lina_debug_set_variant(0, 0) == 0
+
+
+def test_gla_time_cut_plan_sizes():
+    """lina_gla_chunk_fwd_pregated_ws_bytes: a workspace is asked for exactly when the last wave of CTA-pair tiles is at most half
+    full (and a full wave precedes it, and T has >= 4 chunks); its size is the flag block + one fp32 [K <= 256, 128] state slice
+    per CTA of the cut tiles.  Without a device the plan assumes 148 SMs (B200)."""
+    from lina_speech_b200 import _lib
+    lib = _lib.lib()
+    f = lib.lina_gla_chunk_fwd_pregated_ws_bytes
+    # bench shape: 32 * 4 * 2 = 256 pair tiles on 74 slots -> 3 waves + 34 tiles: cut those 34
+    assert f(32, 4, 2048, 256, 512) == 512 + 34 * 2 * 256 * 128 * 4
+    assert f(8, 4, 4096, 256, 512) == 0            # 64 tiles < 74 slots: one partial wave, nothing to gain
+    assert f(2, 4, 1024, 256, 512) == 0
+    assert f(37, 4, 2048, 256, 512) == 0           # 296 tiles = 4 full waves exactly
+    assert f(32, 4, 128, 256, 512) == 0            # two chunks only: too short to cut
+    assert f(32, 4, 2048, 64, 512) == 0            # K = 64 runs on the one-CTA-per-tile kernel
+    assert f(32, 4, 2048, 256, 384) == 0           # V / 128 odd: no CTA pairs
+    assert f(32, 4, 2048, 48, 512) == 0            # outside the tensor-core envelope
